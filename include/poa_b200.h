@@ -1,0 +1,161 @@
+/* poa_b200.h -- C ABI of the B200-native partial-order-alignment engine.
+ *
+ * This is the drop-in boundary for smoothxg's per-block POA hot path.  The reference has no
+ * plugin/FFI layer: the engine is chosen by an `if` inside the OpenMP block loop
+ * (reference src/smooth.cpp:2075-2119) and the abPOA arithmetic is reached through
+ * smooth_abpoa (src/smooth.cpp:133-627).  The cut that leaves everything else untouched is
+ * *inside* smooth_abpoa: this ABI replaces exactly src/smooth.cpp:256-351
+ *   abpoa_init_para / abpoa_post_set_para      (src/smooth.cpp:256-297)
+ *   abpoa_init / abpoa_reset / base encoding    (src/smooth.cpp:300-324)
+ *   abpoa_poa                                    (src/smooth.cpp:337, deps/abPOA/src/abpoa_align.c:304-344)
+ *   abpoa_generate_rc_msa                        (src/smooth.cpp:342-344, deps/abPOA/src/abpoa_output.c:149-192)
+ *   abpoa_generate_consensus                     (src/smooth.cpp:346-351, deps/abPOA/src/abpoa_output.c:1281-1312)
+ * and hands back, in flat arrays, every field of abpoa_t that the host side of smoothxg reads
+ * afterwards (MSA trimming src/smooth.cpp:362-516, build_odgi_abPOA src/smooth.cpp:2442-2574):
+ * node bases, in/out edge lists in abPOA's final (weight-sorted) order with weights, per-read node
+ * paths (what build_odgi_abPOA decodes from the read_ids bitsets, src/smooth.cpp:2488-2501),
+ * consensus node ids, and the row-column MSA.  Node ids are abPOA's: 0 = source, 1 = sink, creation
+ * order thereafter.  INTEGRATION.md shows the patch a smoothxg maintainer would apply.
+ *
+ * Plain C, plain pointers and sizes.  No C++/torch types cross this boundary.  All entry points
+ * are thread-safe with respect to distinct engines/batches; one engine may be shared by several
+ * host threads (calls serialise on an internal mutex).
+ *
+ * Everything behind this ABI runs on the GPU (hand-written sm_100a kernels); there is no CPU
+ * fallback.  Blocks the device could not finish (workspace exhausted even after the engine's
+ * automatic retry with larger workspaces, unsupported gap mode) come back with a non-zero
+ * per-block status and the call returns POA_B200_EBLOCK.
+ */
+#ifndef POA_B200_H
+#define POA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POA_B200_ABI_VERSION 1
+
+/* return / per-block status codes */
+enum {
+    POA_B200_OK        = 0,
+    POA_B200_ESLAB     = 1, /* per-block: DP workspace exhausted (retried automatically with a larger one) */
+    POA_B200_EARENA    = 2, /* per-block: result arena exhausted (retried automatically with a larger one) */
+    POA_B200_EINTERNAL = 3, /* per-block: traceback reached a dead end (the reference aborts here, abpoa_align_simd.c:448) */
+    POA_B200_EUNSUP    = 4, /* unsupported parameters (only the convex gap mode gap_open1>0 && gap_open2>0 is implemented) */
+    POA_B200_EBLOCK    = 5, /* call-level: at least one block has a non-zero status */
+    POA_B200_ECUDA     = 6, /* CUDA runtime error; see poa_b200_last_error() */
+    POA_B200_EARG      = 7, /* bad argument */
+    POA_B200_ENOMEM    = 8  /* host or device allocation failed */
+};
+
+/* Mirrors the abpoa_para_t fields smooth_abpoa sets (reference src/smooth.cpp:256-297).
+ * Penalties are positive numbers, as smoothxg passes them (src/smooth.cpp:282-287). */
+typedef struct poa_b200_params {
+    int32_t match, mismatch, gap_open1, gap_ext1, gap_open2, gap_ext2;
+    int32_t align_mode; /* 0 = global, 1 = local (src/smooth.cpp:259-263); local forces wb = -1 (abpoa_align.c:158) */
+    int32_t wb;         /* 311 = adaptive band, -1 = unbanded (src/smooth.cpp:266-270) */
+    float   wf;         /* 0.03 (src/smooth.cpp:271) */
+    int32_t out_cons;   /* src/smooth.cpp:275 */
+    int32_t out_msa;    /* src/smooth.cpp:278 */
+} poa_b200_params_t;
+
+/* Engine tuning; zero-initialise for defaults. */
+typedef struct poa_b200_engine_opts {
+    int32_t warps_per_block;   /* CUDA warps cooperating on one POA block: 1, 2, 4 or 8; 0 = choose from the batch size */
+    int32_t ctas_per_sm;       /* resident POA blocks per SM; 0 = occupancy-derived default */
+    int32_t emit_cigar;        /* 1: also return per-sequence graph cigars (debug / parity instrumentation) */
+    int32_t reserved0;
+    double  slab_rows_factor;  /* DP workspace rows per query base before a retry is needed; 0 = default (2.0) */
+    int64_t device_mem_budget; /* bytes of HBM the engine may use for workspaces; 0 = 70 % of free memory */
+} poa_b200_engine_opts_t;
+
+typedef struct poa_b200_engine poa_b200_engine_t;
+typedef struct poa_b200_batch  poa_b200_batch_t;
+typedef struct poa_b200_result poa_b200_result_t;
+
+/* One block of a finished batch.  All pointers point into memory owned by the result. */
+typedef struct poa_b200_block_view {
+    int32_t status;              /* POA_B200_OK or a per-block error */
+    int32_t n_node;              /* abg->node_n, including source (0) and sink (1) */
+    int32_t n_seq;
+    int32_t cons_len;            /* -1 when no consensus was requested */
+    int32_t msa_len;             /* -1 when no MSA was requested */
+    int32_t msa_rows;            /* n_seq (+1 when a consensus row is present) */
+    const int32_t *base;         /* [n_node] 0..3 = ACGT, 4 = N  (abg->node[i].base) */
+    const int32_t *in_n;         /* [n_node] in_edge_n */
+    const int32_t *in_id;        /* concatenated in_id lists, node order */
+    const int32_t *in_w;         /* concatenated in_edge_weight lists */
+    const int32_t *out_n;        /* [n_node] out_edge_n */
+    const int32_t *out_id;       /* concatenated out_id lists */
+    const int32_t *out_w;        /* concatenated out_edge_weight lists */
+    const int32_t *aln_n;        /* [n_node] aligned_node_n */
+    const int32_t *aln_id;       /* concatenated aligned_node_id lists */
+    const int32_t *path_len;     /* [n_seq] nodes on each read's path (0 if the read was not added, abpoa_graph.c:706-708) */
+    const int32_t *path_node;    /* concatenated per-read node ids, read order */
+    const int32_t *cons_node;    /* [max(cons_len,0)] abc->cons_node_ids[0] */
+    const uint8_t *msa;          /* [msa_rows * msa_len] abc->msa_base, gap = 5 */
+    const int32_t *best_score;   /* [n_seq] per-sequence alignment score (0 for the first sequence) */
+    const int32_t *n_cigar;      /* [n_seq] cigar words per sequence (all 0 unless emit_cigar) */
+    const uint64_t *cigar;       /* concatenated abpoa_cigar_t words (deps/abPOA/include/abpoa.h:46-51) */
+    int64_t in_total, out_total, aln_total, path_total, cigar_total;
+    int64_t inband_cells;        /* DP cells evaluated inside the band for this block */
+} poa_b200_block_view_t;
+
+typedef struct poa_b200_stats {
+    double  kernel_ms;       /* device time of the POA kernel(s) of the last launch (CUDA events on the launch stream) */
+    double  h2d_ms, d2h_ms;
+    int64_t inband_cells;    /* summed over blocks */
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t kernel_launches; /* POA kernel launches, retries included */
+    int32_t retried_blocks;
+    int32_t n_ctas;          /* persistent CTAs of the main launch */
+    int32_t warps_per_block;
+    int64_t workspace_bytes;
+    int64_t phase_cycles[8]; /* summed SM cycles per phase: rows, fill, backtrack, fuse, toposort, finalize, total, spare */
+} poa_b200_stats_t;
+
+int  poa_b200_abi_version(void);
+const char *poa_b200_strerror(int code);
+const char *poa_b200_last_error(void); /* thread-local text of the last CUDA/argument error */
+
+int  poa_b200_engine_create(int device, const poa_b200_engine_opts_t *opts, poa_b200_engine_t **out);
+void poa_b200_engine_destroy(poa_b200_engine_t *eng);
+
+/* One-shot, host buffers in / host result out (what the smoothxg loop body calls once per batch):
+ *   block_seq_off[n_blocks+1] -> index into seq_len/weight;  seq_off[n_seqs+1] -> index into bases;
+ *   bases = codes 0..4 (ab_char26_table encoding, deps/abPOA/src/abpoa_seq.c:15-32);
+ *   weight[n_seqs] = dedup multiplicity of each sequence (src/smooth.cpp:332-336). */
+int  poa_b200_run_batch(poa_b200_engine_t *eng, const poa_b200_params_t *params, int64_t n_blocks,
+                        const int64_t *block_seq_off, const int32_t *seq_len, const int64_t *seq_off,
+                        const uint8_t *bases, const int32_t *weight, poa_b200_result_t **result);
+
+/* Per-block convenience with abpoa_poa's own argument shapes (deps/abPOA/src/abpoa_align.c:304):
+ * seqs[i] = codes of sequence i, weights[i] = its dedup multiplicity. */
+int  poa_b200_poa_block(poa_b200_engine_t *eng, const poa_b200_params_t *params, int32_t n_seq,
+                        const uint8_t *const *seqs, const int32_t *seq_lens, const int32_t *weights,
+                        poa_b200_result_t **result);
+
+/* Staged API (inputs resident in HBM; used for kernel-only timing and by multi-GPU drivers). */
+int  poa_b200_batch_upload(poa_b200_engine_t *eng, const poa_b200_params_t *params, int64_t n_blocks,
+                           const int64_t *block_seq_off, const int32_t *seq_len, const int64_t *seq_off,
+                           const uint8_t *bases, const int32_t *weight, poa_b200_batch_t **batch);
+/* Enqueue the POA kernel on `stream` (a cudaStream_t, NULL = the engine's own stream); asynchronous. */
+int  poa_b200_batch_launch(poa_b200_batch_t *batch, void *stream);
+/* Wait, re-run blocks that exhausted a workspace, copy the results to the host. */
+int  poa_b200_batch_download(poa_b200_batch_t *batch, void *stream, poa_b200_result_t **result);
+/* Wait for the launch and re-run overflowed blocks, results stay on the device (kernel-only timing). */
+int  poa_b200_batch_finish(poa_b200_batch_t *batch, void *stream);
+void poa_b200_batch_free(poa_b200_batch_t *batch);
+int  poa_b200_batch_stats(const poa_b200_batch_t *batch, poa_b200_stats_t *stats);
+
+int64_t poa_b200_result_n_blocks(const poa_b200_result_t *res);
+int  poa_b200_result_block(const poa_b200_result_t *res, int64_t block, poa_b200_block_view_t *view);
+int  poa_b200_result_stats(const poa_b200_result_t *res, poa_b200_stats_t *stats);
+void poa_b200_result_free(poa_b200_result_t *res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POA_B200_H */

@@ -87,6 +87,12 @@ class Dump:
         hdr = r[:PD_CIGAR_TOT]
         return np.concatenate([hdr, body])
 
+    def compare_part(self) -> np.ndarray:
+        """Everything an instrumented run pins: result_part plus per-sequence scores, cigars and the
+        in-band cell count (header slots up to PD_INBAND_HI); excludes the full-matrix / edge-row counters."""
+        r = self.raw
+        return np.concatenate([r[:PD_FULL_LO], r[PD_HEADER_LEN:]])
+
 
 def _as(arr, dtype):
     return np.ascontiguousarray(arr, dtype=dtype)

@@ -1,0 +1,584 @@
+// poa_b200.cu -- host side of the C ABI (include/poa_b200.h) and the kernel entry points.
+//
+// Host responsibilities (the counterpart of what smooth_abpoa does around abpoa_poa, reference
+// src/smooth.cpp:256-351): validate parameters, build the 5x5 score matrix (abpoa_align.c:12-25),
+// order blocks by cost, size and carve per-CTA workspaces out of HBM, launch one persistent kernel
+// per batch, re-run blocks that exhausted a workspace with larger ones, and expose the flat result.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/poa_b200.h"
+#include "poa_core.cuh"
+#include "poa_host.hpp"
+
+using namespace poa;
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) poa_b200_block_kernel(DevParams P, DevBatch B, WsLayout L, char *ws_base, DevOut O) {
+    __shared__ Shared sh;
+    if (threadIdx.x == 0) ws_bind(sh.ws, ws_base + (long long)blockIdx.x * L.stride, L);
+    for (;;) {
+        if (threadIdx.x == 0) sh.blk = atomicAdd(O.counter, 1);
+        __syncthreads();
+        const int t = sh.blk;
+        __syncthreads();
+        if (t >= B.n_order) break;
+        poa_block<NW>(sh, P, B, L, O, B.order[t]);
+    }
+}
+
+namespace poa {
+thread_local std::string g_last_error;
+int set_err(int code, const std::string &msg) { g_last_error = msg; return code; }
+}  // namespace poa
+
+namespace {
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return set_err(POA_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+
+struct Arena {
+    int *d = nullptr;
+    unsigned long long cap = 0;   // words
+    unsigned long long used = 0;  // words, filled after the launch
+};
+
+}  // namespace
+
+struct poa_b200_engine {
+    int device = 0;
+    int n_sm = 0;
+    cudaStream_t stream = nullptr;
+    poa_b200_engine_opts_t opts{};
+    std::mutex mu;
+    size_t total_mem = 0;
+};
+
+struct poa_b200_result {
+    int64_t n_blocks = 0;
+    std::vector<int> hdr;                 // n_blocks * HDR_WORDS
+    std::vector<int> arena_of;            // per block: which arena holds its body
+    std::vector<int *> arenas;            // pinned host copies
+    std::vector<unsigned long long> arena_words;
+    poa_b200_stats_t stats{};
+    int emit_cigar = 0;
+    std::vector<std::vector<uint64_t>> cigar_cache;  // lazily repacked cigars (lo/hi words -> uint64)
+};
+
+struct poa_b200_batch {
+    poa_b200_engine *eng = nullptr;
+    poa_b200_params_t params{};
+    DevParams dp{};
+    int64_t n_blocks = 0, n_seqs = 0, n_bases = 0;
+    // host copies of the index arrays (needed to size things and for retries)
+    std::vector<long long> h_block_seq_off;
+    std::vector<long long> h_block_bases;  // total bases per block
+    std::vector<int> h_block_maxlen;
+    // device input
+    long long *d_block_seq_off = nullptr, *d_seq_off = nullptr;
+    int *d_seq_len = nullptr, *d_weight = nullptr, *d_order = nullptr;
+    uint8_t *d_bases = nullptr;
+    // device output / control
+    int *d_hdr = nullptr, *d_counter = nullptr;
+    unsigned long long *d_arena_used = nullptr, *d_phase = nullptr;
+    std::vector<Arena> arenas;
+    std::vector<int> arena_of;
+    std::vector<int> h_hdr;
+    // workspace
+    char *d_ws = nullptr;
+    long long ws_bytes = 0;
+    WsLayout layout{};
+    int n_ctas = 0, nw = 1;
+    int n_pending = 0;  // blocks in the launch in flight
+    bool launched = false, finished = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    poa_b200_stats_t stats{};
+};
+
+namespace {
+
+template <int NW>
+cudaError_t launch_nw(int n_ctas, cudaStream_t st, const DevParams &P, const DevBatch &B, const WsLayout &L, char *ws, const DevOut &O) {
+    poa_b200_block_kernel<NW><<<n_ctas, NW * 32, 0, st>>>(P, B, L, ws, O);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kernel(int nw, int n_ctas, cudaStream_t st, const DevParams &P, const DevBatch &B, const WsLayout &L, char *ws, const DevOut &O) {
+    switch (nw) {
+        case 1: return launch_nw<1>(n_ctas, st, P, B, L, ws, O);
+        case 2: return launch_nw<2>(n_ctas, st, P, B, L, ws, O);
+        case 4: return launch_nw<4>(n_ctas, st, P, B, L, ws, O);
+        default: return launch_nw<8>(n_ctas, st, P, B, L, ws, O);
+    }
+}
+
+void free_batch_device(poa_b200_batch *b) {
+    cudaFree(b->d_block_seq_off); cudaFree(b->d_seq_off); cudaFree(b->d_seq_len); cudaFree(b->d_weight);
+    cudaFree(b->d_order); cudaFree(b->d_bases); cudaFree(b->d_hdr); cudaFree(b->d_counter);
+    cudaFree(b->d_arena_used); cudaFree(b->d_phase); cudaFree(b->d_ws);
+    for (auto &a : b->arenas) cudaFree(a.d);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+}
+
+struct Sizing {
+    long long nmax, max_bases, max_len, max_seq, pool_growth, slab_bytes;
+};
+
+// Workspace sizing for a set of blocks.  level 0 = typical (fast path), 1 = 4x, 2 = worst case.
+Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int level, double rows_factor) {
+    long long max_bases = 1, max_len = 1, max_seq = 1;
+    for (int id : blocks) {
+        max_bases = std::max(max_bases, b->h_block_bases[id]);
+        max_len = std::max<long long>(max_len, b->h_block_maxlen[id]);
+        max_seq = std::max<long long>(max_seq, b->h_block_seq_off[id + 1] - b->h_block_seq_off[id]);
+    }
+    const long long worst_nodes = std::max<long long>(max_bases + 2, max_seq + 2);
+    long long nmax, rows;
+    const int wb = b->dp.local ? -1 : b->dp.wb;
+    long long width = max_len + 1;
+    if (level >= 2) { nmax = worst_nodes; rows = worst_nodes; }
+    else {
+        double f = rows_factor * (level == 1 ? 4.0 : 1.0);
+        rows = std::min<long long>(worst_nodes, (long long)(f * max_len) + 64);
+        nmax = std::min<long long>(worst_nodes, rows + max_len / 2 + 64);
+        if (wb >= 0) {
+            long long w = wb + (long long)(b->dp.wf * max_len);
+            width = std::min<long long>(max_len + 1, 2 * w + 1 + (level == 1 ? max_len / 2 : max_len / 8) + 32);
+        }
+    }
+    nmax = std::max<long long>(nmax, 1024);
+    const long long vecs_per_row = width / 8 + 2;
+    // int16 rows unless the block can reach the int32 regime (abpoa_align_simd.c:1293-1302)
+    const long long len = std::max(max_len, nmax);
+    const bool may32 = std::max<long long>(max_len * b->dp.match, len * b->dp.e1 + b->dp.o1) > (long long)INT16_MAX - b->dp.min_mis - b->dp.oe1 - b->dp.oe2;
+    Sizing s;
+    s.nmax = nmax; s.max_bases = max_bases; s.max_len = max_len; s.max_seq = max_seq;
+    const long long edges = std::min<long long>(max_bases + max_seq, level >= 2 ? (1LL << 60) : 3 * nmax);
+    s.pool_growth = 8 * edges + 64;
+    s.slab_bytes = rows * vecs_per_row * 5 * (may32 ? 32 : 16);
+    return s;
+}
+
+int run_launch(poa_b200_batch *b, const std::vector<int> &blocks, int level, cudaStream_t st, bool record_events) {
+    poa_b200_engine *eng = b->eng;
+    const double rows_factor = eng->opts.slab_rows_factor > 0 ? eng->opts.slab_rows_factor : 2.0;
+    Sizing sz = size_for(b, blocks, level, rows_factor);
+    WsLayout L;
+    make_layout(L, sz.nmax, sz.max_bases, sz.max_len, sz.max_seq, sz.pool_growth, sz.slab_bytes, b->dp.emit_cigar);
+    // how many CTAs
+    int nw = eng->opts.warps_per_block;
+    if (nw != 1 && nw != 2 && nw != 4 && nw != 8) {
+        long long target_warps = 16LL * eng->n_sm;
+        nw = 1;
+        while (nw < 8 && (long long)nw * (long long)blocks.size() < target_warps) nw *= 2;
+    }
+    int per_sm = eng->opts.ctas_per_sm > 0 ? eng->opts.ctas_per_sm : std::max(1, 16 / nw);
+    per_sm = std::min(per_sm, 32);
+    long long n_ctas = std::min<long long>((long long)blocks.size(), (long long)eng->n_sm * per_sm);
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    long long budget = eng->opts.device_mem_budget > 0 ? eng->opts.device_mem_budget : (long long)((double)(free_b + (size_t)b->ws_bytes) * 0.70);
+    n_ctas = std::max<long long>(1, std::min<long long>(n_ctas, budget / std::max<long long>(L.stride, 1)));
+    const long long need = n_ctas * L.stride;
+    if (need > b->ws_bytes) {
+        if (b->d_ws) { CU(cudaFree(b->d_ws)); b->d_ws = nullptr; b->ws_bytes = 0; }
+        cudaError_t e = cudaMalloc(&b->d_ws, (size_t)need);
+        if (e != cudaSuccess) return set_err(POA_B200_ENOMEM, std::string("workspace cudaMalloc failed: ") + cudaGetErrorString(e));
+        b->ws_bytes = need;
+    }
+    b->layout = L; b->n_ctas = (int)n_ctas; b->nw = nw;
+    // arena for this launch
+    long long est_words = 0;
+    for (int id : blocks) {
+        long long tb = b->h_block_bases[id], ns = b->h_block_seq_off[id + 1] - b->h_block_seq_off[id], ml = b->h_block_maxlen[id];
+        long long n_est = level >= 2 ? tb + 2 : std::min<long long>(tb + 2, (level == 1 ? 8 : 3) * ml + 64);
+        long long wds = 12 * n_est + tb + 3 * ns + 64;
+        if (b->dp.out_msa) wds += (ns + 1) * n_est / 4 + 8;
+        if (b->dp.emit_cigar) wds += 2 * (tb + ns * n_est);
+        est_words += wds;
+    }
+    est_words = est_words + est_words / 4 + 1024;
+    Arena ar;
+    ar.cap = (unsigned long long)est_words;
+    {
+        cudaError_t e = cudaMalloc(&ar.d, (size_t)ar.cap * 4);
+        if (e != cudaSuccess) return set_err(POA_B200_ENOMEM, std::string("arena cudaMalloc failed: ") + cudaGetErrorString(e));
+    }
+    b->arenas.push_back(ar);
+    // order: most expensive first
+    std::vector<int> order(blocks);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        double cx = (double)b->h_block_bases[x] * (double)b->h_block_bases[x];
+        double cy = (double)b->h_block_bases[y] * (double)b->h_block_bases[y];
+        return cx > cy;
+    });
+    CU(cudaMemcpyAsync(b->d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(b->d_counter, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(b->d_arena_used, 0, sizeof(unsigned long long), st));
+    DevBatch B;
+    B.block_seq_off = b->d_block_seq_off; B.seq_len = b->d_seq_len; B.seq_off = b->d_seq_off;
+    B.bases = b->d_bases; B.weight = b->d_weight; B.order = b->d_order; B.n_order = (int)order.size();
+    DevOut O;
+    O.hdr = b->d_hdr; O.arena = ar.d; O.arena_used = b->d_arena_used; O.arena_cap = ar.cap;
+    O.phase = b->d_phase; O.counter = b->d_counter;
+    if (record_events) CU(cudaEventRecord(b->ev0, st));
+    CU(launch_kernel(nw, (int)n_ctas, st, b->dp, B, L, b->d_ws, O));
+    if (record_events) CU(cudaEventRecord(b->ev1, st));
+    b->n_pending = (int)order.size();
+    b->stats.kernel_launches += 1;
+    if (record_events) { b->stats.n_ctas = (int)n_ctas; b->stats.warps_per_block = nw; b->stats.workspace_bytes = need; }
+    return POA_B200_OK;
+}
+
+// after a launch has completed: fetch headers, note which arena each finished block used, list failures
+int collect(poa_b200_batch *b, const std::vector<int> &blocks, cudaStream_t st, std::vector<int> &failed_ws, std::vector<int> &failed_arena) {
+    CU(cudaMemcpyAsync(b->h_hdr.data(), b->d_hdr, b->h_hdr.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    unsigned long long used = 0;
+    CU(cudaMemcpyAsync(&used, b->d_arena_used, sizeof(used), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    Arena &ar = b->arenas.back();
+    ar.used = std::min(used, ar.cap);
+    const int ai = (int)b->arenas.size() - 1;
+    for (int id : blocks) {
+        int st_ = b->h_hdr[(size_t)id * HDR_WORDS + H_STATUS];
+        if (st_ == ST_OK) b->arena_of[id] = ai;
+        else if (st_ == ST_ESLAB) failed_ws.push_back(id);
+        else if (st_ == ST_EARENA) failed_arena.push_back(id);
+    }
+    return POA_B200_OK;
+}
+
+int finish_locked(poa_b200_batch *b, cudaStream_t st) {
+    if (!b->launched) return set_err(POA_B200_EARG, "batch was not launched");
+    if (b->finished) return POA_B200_OK;
+    std::vector<int> blocks((size_t)b->n_blocks);
+    for (int64_t i = 0; i < b->n_blocks; ++i) blocks[(size_t)i] = (int)i;
+    int level = 0;
+    for (int round = 0; round < 6 && !blocks.empty(); ++round) {
+        std::vector<int> f_ws, f_ar;
+        int rc = collect(b, blocks, st, f_ws, f_ar);
+        if (rc) return rc;
+        if (round == 0) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+            b->stats.kernel_ms = ms;
+        }
+        if (f_ws.empty() && f_ar.empty()) { blocks.clear(); break; }
+        if (!f_ws.empty()) level = std::min(level + 1, 2);
+        std::vector<int> again(f_ws);
+        again.insert(again.end(), f_ar.begin(), f_ar.end());
+        std::sort(again.begin(), again.end());
+        b->stats.retried_blocks += (int)again.size();
+        // arena overflow: the next launch gets its own arena sized from the next level's estimate
+        rc = run_launch(b, again, f_ws.empty() ? std::max(level, 1) : level, st, false);
+        if (rc) return rc;
+        blocks = again;
+    }
+    if (!blocks.empty()) {
+        std::vector<int> f_ws, f_ar;
+        int rc = collect(b, blocks, st, f_ws, f_ar);
+        if (rc) return rc;
+    }
+    unsigned long long ph[PH_N];
+    CU(cudaMemcpy(ph, b->d_phase, sizeof(ph), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 8; ++k) b->stats.phase_cycles[k] = (int64_t)ph[k];
+    long long cells = 0;
+    for (int64_t i = 0; i < b->n_blocks; ++i) {
+        const int *h = &b->h_hdr[(size_t)i * HDR_WORDS];
+        if (h[H_STATUS] == ST_OK) cells += (long long)((unsigned long long)(unsigned)h[H_INBAND_LO] | ((unsigned long long)(unsigned)h[H_INBAND_HI] << 32));
+    }
+    b->stats.inband_cells = cells;
+    b->finished = true;
+    return POA_B200_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int poa_b200_abi_version(void) { return POA_B200_ABI_VERSION; }
+
+const char *poa_b200_strerror(int code) {
+    switch (code) {
+        case POA_B200_OK: return "ok";
+        case POA_B200_ESLAB: return "DP workspace exhausted";
+        case POA_B200_EARENA: return "result arena exhausted";
+        case POA_B200_EINTERNAL: return "traceback dead end";
+        case POA_B200_EUNSUP: return "unsupported parameters";
+        case POA_B200_EBLOCK: return "one or more blocks failed";
+        case POA_B200_ECUDA: return "CUDA error";
+        case POA_B200_EARG: return "bad argument";
+        case POA_B200_ENOMEM: return "out of memory";
+        default: return "unknown";
+    }
+}
+
+const char *poa_b200_last_error(void) { return g_last_error.c_str(); }
+
+int poa_b200_engine_create(int device, const poa_b200_engine_opts_t *opts, poa_b200_engine_t **out) {
+    if (!out) return set_err(POA_B200_EARG, "out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    CU(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return set_err(POA_B200_EARG, "no such CUDA device");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return set_err(POA_B200_ECUDA, "this library holds sm_100a code only; device is not Blackwell");
+    poa_b200_engine *e = new (std::nothrow) poa_b200_engine();
+    if (!e) return set_err(POA_B200_ENOMEM, "engine alloc");
+    e->device = device; e->n_sm = prop.multiProcessorCount; e->total_mem = prop.totalGlobalMem;
+    if (opts) e->opts = *opts;
+    CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    *out = e;
+    return POA_B200_OK;
+}
+
+void poa_b200_engine_destroy(poa_b200_engine_t *eng) {
+    if (!eng) return;
+    cudaSetDevice(eng->device);
+    if (eng->stream) cudaStreamDestroy(eng->stream);
+    delete eng;
+}
+
+int poa_b200_batch_upload(poa_b200_engine_t *eng, const poa_b200_params_t *params, int64_t n_blocks,
+                          const int64_t *block_seq_off, const int32_t *seq_len, const int64_t *seq_off,
+                          const uint8_t *bases, const int32_t *weight, poa_b200_batch_t **out) {
+    if (!eng || !params || !out || n_blocks < 0 || (n_blocks > 0 && (!block_seq_off || !seq_off)))
+        return set_err(POA_B200_EARG, "NULL argument");
+    *out = nullptr;
+    int rc = check_params(*params);
+    if (rc) return rc;
+    if (n_blocks > INT32_MAX / HDR_WORDS) return set_err(POA_B200_EARG, "too many blocks in one batch");
+    std::lock_guard<std::mutex> lk(eng->mu);
+    CU(cudaSetDevice(eng->device));
+    poa_b200_batch *b = new (std::nothrow) poa_b200_batch();
+    if (!b) return set_err(POA_B200_ENOMEM, "batch alloc");
+    b->eng = eng; b->params = *params; b->n_blocks = n_blocks;
+    build_params(*params, eng->opts, b->dp);
+    const int64_t n_seqs = n_blocks ? block_seq_off[n_blocks] : 0;
+    const int64_t n_bases = n_seqs ? seq_off[n_seqs] : 0;
+    b->n_seqs = n_seqs; b->n_bases = n_bases;
+    b->h_block_seq_off.assign(block_seq_off, block_seq_off + (n_blocks ? n_blocks + 1 : 0));
+    if (n_blocks == 0) b->h_block_seq_off.assign(1, 0);
+    b->h_block_bases.resize((size_t)n_blocks); b->h_block_maxlen.resize((size_t)n_blocks);
+    for (int64_t i = 0; i < n_blocks; ++i) {
+        int64_t s0 = block_seq_off[i], s1 = block_seq_off[i + 1];
+        if (s1 < s0) { delete b; return set_err(POA_B200_EARG, "block_seq_off not monotone"); }
+        int ml = 0;
+        for (int64_t s = s0; s < s1; ++s) {
+            if (seq_len[s] < 0 || seq_off[s + 1] - seq_off[s] != seq_len[s]) { delete b; return set_err(POA_B200_EARG, "seq_off/seq_len mismatch"); }
+            ml = std::max(ml, seq_len[s]);
+        }
+        b->h_block_bases[(size_t)i] = seq_off[s1] - seq_off[s0];
+        b->h_block_maxlen[(size_t)i] = ml;
+        if (b->h_block_bases[(size_t)i] > (1LL << 30)) { delete b; return set_err(POA_B200_EARG, "block too large"); }
+    }
+    auto fail = [&](int code) { free_batch_device(b); delete b; return code; };
+#define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(POA_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); return fail(POA_B200_ECUDA); } } while (0)
+    cudaStream_t st = eng->stream;
+    CUB(cudaEventCreate(&b->ev0)); CUB(cudaEventCreate(&b->ev1));
+    cudaEvent_t h0, h1;
+    CUB(cudaEventCreate(&h0)); CUB(cudaEventCreate(&h1));
+    CUB(cudaMalloc(&b->d_block_seq_off, sizeof(long long) * (size_t)(n_blocks + 1)));
+    CUB(cudaMalloc(&b->d_seq_off, sizeof(long long) * (size_t)(n_seqs + 1)));
+    CUB(cudaMalloc(&b->d_seq_len, sizeof(int) * (size_t)std::max<int64_t>(n_seqs, 1)));
+    CUB(cudaMalloc(&b->d_weight, sizeof(int) * (size_t)std::max<int64_t>(n_seqs, 1)));
+    CUB(cudaMalloc(&b->d_bases, (size_t)std::max<int64_t>(n_bases, 1)));
+    CUB(cudaMalloc(&b->d_order, sizeof(int) * (size_t)std::max<int64_t>(n_blocks, 1)));
+    CUB(cudaMalloc(&b->d_hdr, sizeof(int) * HDR_WORDS * (size_t)std::max<int64_t>(n_blocks, 1)));
+    CUB(cudaMalloc(&b->d_counter, sizeof(int)));
+    CUB(cudaMalloc(&b->d_arena_used, sizeof(unsigned long long)));
+    CUB(cudaMalloc(&b->d_phase, sizeof(unsigned long long) * PH_N));
+    CUB(cudaMemsetAsync(b->d_phase, 0, sizeof(unsigned long long) * PH_N, st));
+    CUB(cudaMemsetAsync(b->d_hdr, 0xff, sizeof(int) * HDR_WORDS * (size_t)std::max<int64_t>(n_blocks, 1), st));
+    CUB(cudaEventRecord(h0, st));
+    static const long long zero = 0;
+    CUB(cudaMemcpyAsync(b->d_block_seq_off, n_blocks ? (const void *)block_seq_off : (const void *)&zero, sizeof(long long) * (size_t)(n_blocks + 1), cudaMemcpyHostToDevice, st));
+    CUB(cudaMemcpyAsync(b->d_seq_off, n_seqs ? (const void *)seq_off : (const void *)&zero, sizeof(long long) * (size_t)(n_seqs + 1), cudaMemcpyHostToDevice, st));
+    if (n_seqs) {
+        CUB(cudaMemcpyAsync(b->d_seq_len, seq_len, sizeof(int) * (size_t)n_seqs, cudaMemcpyHostToDevice, st));
+        CUB(cudaMemcpyAsync(b->d_weight, weight, sizeof(int) * (size_t)n_seqs, cudaMemcpyHostToDevice, st));
+    }
+    if (n_bases) CUB(cudaMemcpyAsync(b->d_bases, bases, (size_t)n_bases, cudaMemcpyHostToDevice, st));
+    CUB(cudaEventRecord(h1, st));
+    CUB(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h0, h1);
+    cudaEventDestroy(h0); cudaEventDestroy(h1);
+    b->stats.h2d_ms = ms;
+    b->stats.h2d_bytes = (int64_t)(sizeof(long long) * (size_t)(n_blocks + 1 + n_seqs + 1) + 8 * (size_t)n_seqs + (size_t)n_bases);
+    b->h_hdr.assign((size_t)n_blocks * HDR_WORDS, -1);
+    b->arena_of.assign((size_t)n_blocks, -1);
+#undef CUB
+    *out = b;
+    return POA_B200_OK;
+}
+
+int poa_b200_batch_launch(poa_b200_batch_t *b, void *stream) {
+    if (!b) return set_err(POA_B200_EARG, "NULL batch");
+    std::lock_guard<std::mutex> lk(b->eng->mu);
+    CU(cudaSetDevice(b->eng->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : b->eng->stream;
+    // a re-launch of the same batch recomputes everything (used by benchmarks)
+    for (auto &a : b->arenas) cudaFree(a.d);
+    b->arenas.clear();
+    std::fill(b->arena_of.begin(), b->arena_of.end(), -1);
+    b->stats.kernel_launches = 0; b->stats.retried_blocks = 0;
+    CU(cudaMemsetAsync(b->d_phase, 0, sizeof(unsigned long long) * PH_N, st));
+    b->finished = false;
+    if (b->n_blocks == 0) { b->launched = true; b->finished = true; return POA_B200_OK; }
+    std::vector<int> blocks((size_t)b->n_blocks);
+    for (int64_t i = 0; i < b->n_blocks; ++i) blocks[(size_t)i] = (int)i;
+    int rc = run_launch(b, blocks, 0, st, true);
+    if (rc) return rc;
+    b->launched = true;
+    return POA_B200_OK;
+}
+
+int poa_b200_batch_finish(poa_b200_batch_t *b, void *stream) {
+    if (!b) return set_err(POA_B200_EARG, "NULL batch");
+    std::lock_guard<std::mutex> lk(b->eng->mu);
+    CU(cudaSetDevice(b->eng->device));
+    return finish_locked(b, stream ? (cudaStream_t)stream : b->eng->stream);
+}
+
+int poa_b200_batch_download(poa_b200_batch_t *b, void *stream, poa_b200_result_t **out) {
+    if (!b || !out) return set_err(POA_B200_EARG, "NULL argument");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(b->eng->mu);
+    CU(cudaSetDevice(b->eng->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : b->eng->stream;
+    int rc = finish_locked(b, st);
+    if (rc) return rc;
+    poa_b200_result *r = new (std::nothrow) poa_b200_result();
+    if (!r) return set_err(POA_B200_ENOMEM, "result alloc");
+    r->n_blocks = b->n_blocks; r->hdr = b->h_hdr; r->arena_of = b->arena_of; r->emit_cigar = b->dp.emit_cigar;
+    cudaEvent_t d0, d1;
+    CU(cudaEventCreate(&d0)); CU(cudaEventCreate(&d1));
+    CU(cudaEventRecord(d0, st));
+    int64_t bytes = (int64_t)b->h_hdr.size() * 4;
+    for (auto &a : b->arenas) {
+        int *h = nullptr;
+        size_t nbytes = (size_t)std::max<unsigned long long>(a.used, 1) * 4;
+        cudaError_t e = cudaMallocHost(&h, nbytes);
+        if (e != cudaSuccess) { poa_b200_result_free(r); return set_err(POA_B200_ENOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
+        r->arenas.push_back(h); r->arena_words.push_back(a.used);
+        if (a.used) CU(cudaMemcpyAsync(h, a.d, (size_t)a.used * 4, cudaMemcpyDeviceToHost, st));
+        bytes += (int64_t)a.used * 4;
+    }
+    CU(cudaEventRecord(d1, st));
+    CU(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, d0, d1);
+    cudaEventDestroy(d0); cudaEventDestroy(d1);
+    b->stats.d2h_ms = ms; b->stats.d2h_bytes = bytes;
+    r->stats = b->stats;
+    if (r->emit_cigar) r->cigar_cache.resize((size_t)r->n_blocks);
+    *out = r;
+    for (int64_t i = 0; i < r->n_blocks; ++i)
+        if (r->hdr[(size_t)i * HDR_WORDS + H_STATUS] != ST_OK) return set_err(POA_B200_EBLOCK, "one or more blocks failed; see per-block status");
+    return POA_B200_OK;
+}
+
+void poa_b200_batch_free(poa_b200_batch_t *b) {
+    if (!b) return;
+    {
+        std::lock_guard<std::mutex> lk(b->eng->mu);
+        cudaSetDevice(b->eng->device);
+        free_batch_device(b);
+    }
+    delete b;
+}
+
+int poa_b200_batch_stats(const poa_b200_batch_t *b, poa_b200_stats_t *s) {
+    if (!b || !s) return set_err(POA_B200_EARG, "NULL argument");
+    *s = b->stats;
+    return POA_B200_OK;
+}
+
+int poa_b200_run_batch(poa_b200_engine_t *eng, const poa_b200_params_t *params, int64_t n_blocks,
+                       const int64_t *block_seq_off, const int32_t *seq_len, const int64_t *seq_off,
+                       const uint8_t *bases, const int32_t *weight, poa_b200_result_t **result) {
+    if (!result) return set_err(POA_B200_EARG, "NULL result");
+    *result = nullptr;
+    poa_b200_batch_t *b = nullptr;
+    int rc = poa_b200_batch_upload(eng, params, n_blocks, block_seq_off, seq_len, seq_off, bases, weight, &b);
+    if (rc) return rc;
+    rc = poa_b200_batch_launch(b, nullptr);
+    if (rc == POA_B200_OK) rc = poa_b200_batch_download(b, nullptr, result);
+    poa_b200_batch_free(b);
+    return rc;
+}
+
+int poa_b200_poa_block(poa_b200_engine_t *eng, const poa_b200_params_t *params, int32_t n_seq,
+                       const uint8_t *const *seqs, const int32_t *seq_lens, const int32_t *weights,
+                       poa_b200_result_t **result) {
+    if (n_seq < 0 || (n_seq > 0 && (!seqs || !seq_lens || !weights))) return set_err(POA_B200_EARG, "bad block");
+    std::vector<int64_t> bso{0, n_seq}, so((size_t)n_seq + 1, 0);
+    for (int i = 0; i < n_seq; ++i) so[(size_t)i + 1] = so[(size_t)i] + seq_lens[i];
+    std::vector<uint8_t> cat((size_t)so[(size_t)n_seq]);
+    for (int i = 0; i < n_seq; ++i) if (seq_lens[i]) memcpy(cat.data() + so[(size_t)i], seqs[i], (size_t)seq_lens[i]);
+    return poa_b200_run_batch(eng, params, 1, bso.data(), seq_lens, so.data(), cat.data(), weights, result);
+}
+
+int64_t poa_b200_result_n_blocks(const poa_b200_result_t *res) { return res ? res->n_blocks : 0; }
+
+int poa_b200_result_block(const poa_b200_result_t *res, int64_t blk, poa_b200_block_view_t *v) {
+    if (!res || !v || blk < 0 || blk >= res->n_blocks) return set_err(POA_B200_EARG, "bad block index");
+    memset(v, 0, sizeof(*v));
+    const int *h = &res->hdr[(size_t)blk * HDR_WORDS];
+    v->status = h[H_STATUS];
+    v->n_seq = h[H_N_SEQ];
+    if (v->status != ST_OK) { v->cons_len = -1; v->msa_len = -1; return POA_B200_OK; }
+    const int ai = res->arena_of[(size_t)blk];
+    if (ai < 0 || ai >= (int)res->arenas.size()) return set_err(POA_B200_EARG, "block has no result body");
+    const unsigned long long off = (unsigned long long)(unsigned)h[H_OFF_LO] | ((unsigned long long)(unsigned)h[H_OFF_HI] << 32);
+    const int *o = res->arenas[(size_t)ai] + off;
+    const int n = h[H_N_NODE], ns = h[H_N_SEQ];
+    const long long in_tot = h[H_IN_TOT], out_tot = h[H_OUT_TOT], aln_tot = h[H_ALN_TOT], path_tot = h[H_PATH_TOT], cig_tot = h[H_CIG_TOT];
+    v->n_node = n; v->cons_len = h[H_CONS_LEN]; v->msa_len = h[H_MSA_LEN]; v->msa_rows = h[H_MSA_ROWS];
+    v->base = o; v->in_n = v->base + n; v->in_id = v->in_n + n; v->in_w = v->in_id + in_tot;
+    v->out_n = v->in_w + in_tot; v->out_id = v->out_n + n; v->out_w = v->out_id + out_tot;
+    v->aln_n = v->out_w + out_tot; v->aln_id = v->aln_n + n;
+    v->path_len = v->aln_id + aln_tot; v->path_node = v->path_len + ns; v->cons_node = v->path_node + path_tot;
+    v->best_score = v->cons_node + (v->cons_len > 0 ? v->cons_len : 0); v->n_cigar = v->best_score + ns;
+    const int *cig = v->n_cigar + ns;
+    v->msa = reinterpret_cast<const uint8_t *>(cig + 2 * cig_tot);
+    v->in_total = in_tot; v->out_total = out_tot; v->aln_total = aln_tot; v->path_total = path_tot; v->cigar_total = cig_tot;
+    v->inband_cells = (int64_t)((unsigned long long)(unsigned)h[H_INBAND_LO] | ((unsigned long long)(unsigned)h[H_INBAND_HI] << 32));
+    v->cigar = reinterpret_cast<const uint64_t *>(cig);  // lo word first: little-endian uint64, 4-byte aligned
+    return POA_B200_OK;
+}
+
+int poa_b200_result_stats(const poa_b200_result_t *res, poa_b200_stats_t *s) {
+    if (!res || !s) return set_err(POA_B200_EARG, "NULL argument");
+    *s = res->stats;
+    return POA_B200_OK;
+}
+
+void poa_b200_result_free(poa_b200_result_t *res) {
+    if (!res) return;
+    for (int *p : res->arenas) cudaFreeHost(p);
+    delete res;
+}
+
+}  // extern "C"

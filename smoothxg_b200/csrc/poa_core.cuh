@@ -1,0 +1,1088 @@
+// poa_core.cuh -- device code of the B200-native POA engine (one CUDA block per POA block).
+//
+// What it computes is abPOA v1.5.4's convex-gap partial order alignment exactly as smoothxg drives
+// it (reference citations relative to /root/reference):
+//   per-block driver loop          deps/abPOA/src/abpoa_align.c:304-344        -> poa_block()
+//   int16/int32 choice, inf_min    deps/abPOA/src/abpoa_align_simd.c:1286-1302 -> poa_block()
+//   first row / row recurrence     deps/abPOA/src/abpoa_align_simd.c:617-688, :935-1074 -> fill<>()
+//   adaptive band                  deps/abPOA/src/abpoa_align.h:34-35, abpoa_align_simd.c:1107-1130
+//   best cell                      deps/abPOA/src/abpoa_align_simd.c:1092-1105, :1208-1210
+//   backtrack                      deps/abPOA/src/abpoa_align_simd.c:309-458    -> backtrack<>()
+//   graph fusion                   deps/abPOA/src/abpoa_graph.c:688-773, :480-556, :573-592 -> fuse()
+//   topological sort               deps/abPOA/src/abpoa_graph.c:322-357 (:221-266, :192-219, :268-309)
+//   heaviest-bundle consensus      deps/abPOA/src/abpoa_output.c:468-536, :375-391
+//   MSA rank                       deps/abPOA/src/abpoa_graph.c:359-419
+//
+// How it computes it is not the reference's: the DP row is evaluated by all threads of the CUDA
+// block at once on 8-cell vectors in absolute column coordinates (so predecessor rows line up without
+// shifts), the horizontal gap recurrences F1/F2 are max-plus prefix scans (G[j] = F[j] + e*j turns
+// F[j] = max(F[j-1]-e, H[j-1]-oe) into a running maximum) done with warp shuffles, the row maximum /
+// arg-max for the adaptive band is a redux.sync reduction, rows are stored band-only, and the whole
+// per-block loop (align, traceback, fusion, topological sort, consensus, MSA) stays on the device.
+//
+// The file also compiles as plain C++ with -DPOA_HOST_EMU (one emulated thread, warp size 1).  That
+// build exists only so the serial logic can be unit-debugged on a machine without a GPU; it is never
+// built by __graft_entry__.build(), never shipped and never reachable from the C ABI.
+#pragma once
+#include <stdint.h>
+#include <limits.h>
+
+#ifdef POA_HOST_EMU
+#include <vector_types.h>
+#include <string.h>
+#define POA_D static inline
+#define POA_DN static
+#define POA_SM static inline
+#define POA_WARP 1
+static inline int poa_tid() { return 0; }
+static inline void poa_sync_block() {}
+static inline void poa_sync_warp() {}
+static inline int poa_shfl_up(int v, int) { return v; }
+static inline int poa_shfl(int v, int) { return v; }
+static inline int poa_redux_max(int v) { return v; }
+static inline int poa_redux_min(int v) { return v; }
+static inline long long poa_clock() { return 0; }
+static inline unsigned long long poa_atomic_add(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+static inline int poa_atomic_add(int *p, int v) { int o = *p; *p += v; return o; }
+static inline int4 poa_make_int4(int x, int y, int z, int w) { int4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+#else
+#define POA_D __device__ __forceinline__
+#define POA_DN __device__ __noinline__
+#define POA_SM __device__ __forceinline__ static
+#define POA_WARP 32
+POA_D int poa_tid() { return threadIdx.x; }
+POA_D void poa_sync_block() { __syncthreads(); }
+POA_D void poa_sync_warp() { __syncwarp(); }
+POA_D int poa_shfl_up(int v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+POA_D int poa_shfl(int v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+POA_D int poa_redux_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+POA_D int poa_redux_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
+POA_D long long poa_clock() { return clock64(); }
+POA_D unsigned long long poa_atomic_add(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
+POA_D int poa_atomic_add(int *p, int v) { return atomicAdd(p, v); }
+POA_D int4 poa_make_int4(int x, int y, int z, int w) { return make_int4(x, y, z, w); }
+#endif
+
+namespace poa {
+
+constexpr int SRC_ID = 0, SINK_ID = 1;
+constexpr int HDR_WORDS = 16;  // per-block result header, int32 words
+constexpr int NEG_INF32 = INT_MIN;
+constexpr int MAX_WARPS = 8;
+
+// per-block status (keep in sync with include/poa_b200.h)
+enum { ST_OK = 0, ST_ESLAB = 1, ST_EARENA = 2, ST_EINTERNAL = 3, ST_EUNSUP = 4 };
+// result header slots
+enum { H_STATUS = 0, H_N_NODE, H_N_SEQ, H_CONS_LEN, H_MSA_LEN, H_MSA_ROWS, H_IN_TOT, H_OUT_TOT, H_ALN_TOT,
+       H_PATH_TOT, H_CIG_TOT, H_OFF_LO, H_OFF_HI, H_INBAND_LO, H_INBAND_HI, H_WORDS };
+// phase cycle counters
+enum { PH_ROWS = 0, PH_FILL, PH_BT, PH_FUSE, PH_TOPO, PH_FINAL, PH_TOTAL, PH_SPARE, PH_N };
+
+// cigar ops (deps/abPOA/include/abpoa.h:18-24)
+constexpr int CMATCH = 0, CINS = 1, CDEL = 2;
+// backtrack state bits (deps/abPOA/src/abpoa_align.h:20-27)
+constexpr int OP_M = 0x1, OP_E1 = 0x2, OP_E2 = 0x4, OP_E = 0x6, OP_F1 = 0x8, OP_F2 = 0x10, OP_F = 0x18, OP_ALL = 0x1f;
+
+struct DevParams {
+    int mat[25];
+    int o1, e1, o2, e2, oe1, oe2;
+    int match, min_mis;
+    int local, wb;
+    float wf;
+    int out_cons, out_msa;
+    int pn16, pn32;  // lane counts of the reference build whose band-start rule we reproduce (AVX-512BW: 32/16)
+    int emit_cigar;
+};
+
+// Device-resident batch input (flat, same arrays as the C ABI takes).
+struct DevBatch {
+    const long long *block_seq_off;
+    const int *seq_len;
+    const long long *seq_off;
+    const uint8_t *bases;
+    const int *weight;
+    const int *order;  // processing order: block ids, most expensive first
+    int n_order;
+};
+
+// Byte offsets of the per-CTA workspace arrays (identical for all CTAs of a launch).
+struct WsLayout {
+    long long stride;  // bytes per CTA
+    long long o_base, o_aln_n, o_aln, o_in_off, o_in_n, o_out_off, o_out_n, o_pool_id, o_pool_w, o_pool_row;
+    long long o_idx2id, o_id2idx, o_remain, o_tmp0, o_tmp1, o_tmp2, o_tmp3;
+    long long o_rowinfo, o_rowmeta, o_rbase, o_rr, o_mplr, o_mprr;
+    long long o_cig, o_path, o_best, o_ncig, o_slab;
+    long long slab_bytes;
+    int nmax;      // node capacity
+    int pool_cap;  // edge pool capacity (entries)
+    int cig_cap;   // cigar words capacity per block (all sequences when emit_cigar, else one alignment)
+};
+
+struct DevOut {
+    int *hdr;                       // [n_blocks][HDR_WORDS]
+    int *arena;                     // result bodies, int32 words
+    unsigned long long *arena_used; // bump cursor (words)
+    unsigned long long arena_cap;   // words
+    unsigned long long *phase;      // [PH_N] summed cycles
+    int *counter;                   // next entry of DevBatch::order to take
+};
+
+struct Ws {
+    uint8_t *base, *aln_n, *rbase;
+    int *aln, *in_off, *in_n, *out_off, *out_n, *pool_id, *pool_w, *pool_row;
+    int *idx2id, *id2idx, *remain, *tmp0, *tmp1, *tmp2, *tmp3;
+    int4 *rowinfo, *rowmeta;
+    int *rr, *mplr, *mprr;
+    unsigned long long *cig;
+    int *path, *best, *ncig;
+    char *slab;
+};
+
+struct Shared {
+    Ws ws;
+    int blk;
+    int n_node;
+    int nmax, pool_cap;
+    int pool_used;
+    int err;
+    int n_cigar;       // cigar words of the current alignment
+    int cig_base;      // where the current alignment's cigar starts in ws.cig
+    int best_score, best_i, best_j;
+    long long inband;
+    int scan_x[2][2][MAX_WARPS];
+    int red_x[2][3][MAX_WARPS];
+    int bcast[4];
+};
+
+POA_D int imax(int a, int b) { return a > b ? a : b; }
+POA_D int imin(int a, int b) { return a < b ? a : b; }
+
+// ------------------------------------------------------------------------------------------------
+// graph primitives (single thread)
+// ------------------------------------------------------------------------------------------------
+// Edge lists live in one pool.  A node's in-list starts at 4*id and its out-list at 4*id+2 (two
+// entries each); a list that outgrows its slot moves to a fresh slot of twice the size taken from the
+// growth region behind 4*nmax.  The pool is sized for the worst case so it cannot run out.
+POA_D void edge_push(Shared &sh, int *off_arr, int *n_arr, int v, int id, int wt) {
+    Ws &w = sh.ws;
+    int n = n_arr[v], off = off_arr[v];
+    if (n >= 2 && (n & (n - 1)) == 0) {
+        int noff = sh.pool_used;
+        if (noff + 2 * n > sh.pool_cap) { sh.err = ST_ESLAB; return; }
+        sh.pool_used += 2 * n;
+        for (int t = 0; t < n; ++t) { w.pool_id[noff + t] = w.pool_id[off + t]; w.pool_w[noff + t] = w.pool_w[off + t]; }
+        off_arr[v] = noff; off = noff;
+    }
+    w.pool_id[off + n] = id; w.pool_w[off + n] = wt; n_arr[v] = n + 1;
+}
+
+POA_D int add_node(Shared &sh, int base) {  // abpoa_graph.c:471-478
+    Ws &w = sh.ws;
+    int v = sh.n_node++;
+    w.base[v] = (uint8_t)base; w.aln_n[v] = 0;
+    w.in_n[v] = 0; w.out_n[v] = 0; w.in_off[v] = 4 * v; w.out_off[v] = 4 * v + 2;
+    return v;
+}
+
+POA_D void add_edge(Shared &sh, int from, int to, int check_edge, int wt) {  // abpoa_graph.c:480-556
+    Ws &w = sh.ws;
+    int exist = 0;
+    if (check_edge) {
+        int n = w.in_n[to], off = w.in_off[to];
+        for (int i = 0; i < n; ++i) if (w.pool_id[off + i] == from) { w.pool_w[off + i] += wt; break; }
+        n = w.out_n[from]; off = w.out_off[from];
+        for (int i = 0; i < n; ++i) if (w.pool_id[off + i] == to) { w.pool_w[off + i] += wt; exist = 1; break; }
+    }
+    if (!exist) {
+        edge_push(sh, w.in_off, w.in_n, to, from, wt);
+        edge_push(sh, w.out_off, w.out_n, from, to, wt);
+    }
+}
+
+POA_D void add_aligned(Ws &w, int node_id, int new_id) {  // abpoa_graph.c:455-463
+    int n = w.aln_n[node_id];
+    for (int i = 0; i < n; ++i) {
+        int a = w.aln[4 * node_id + i];
+        w.aln[4 * a + w.aln_n[a]++] = new_id;
+        w.aln[4 * new_id + w.aln_n[new_id]++] = a;
+    }
+    w.aln[4 * node_id + w.aln_n[node_id]++] = new_id;
+    w.aln[4 * new_id + w.aln_n[new_id]++] = node_id;
+}
+
+POA_D int get_aligned_id(const Ws &w, int node_id, int base) {  // abpoa_graph.c:439-448
+    int n = w.aln_n[node_id];
+    for (int i = 0; i < n; ++i) {
+        int a = w.aln[4 * node_id + i];
+        if (w.base[a] == base) return a;
+    }
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-wide helpers
+// ------------------------------------------------------------------------------------------------
+template <int NW>
+POA_D void sync_block() {
+    if (NW == 1) poa_sync_warp(); else poa_sync_block();
+}
+
+// ------------------------------------------------------------------------------------------------
+// topological sort (abpoa_graph.c:322-357)
+// ------------------------------------------------------------------------------------------------
+template <int NW>
+POA_DN void toposort(Shared &sh, int banded) {
+    constexpr int NT = NW * POA_WARP;
+    Ws &w = sh.ws;
+    const int tid = poa_tid();
+    const int n = sh.n_node;
+    // in-degree copy
+    for (int v = tid; v < n; v += NT) w.tmp0[v] = w.in_n[v];
+    sync_block<NW>();
+    if (tid == 0) {  // abpoa_graph.c:221-266; the FIFO queue *is* index_to_node_id
+        int qh = 0, qt = 0;
+        w.idx2id[qt++] = SRC_ID;
+        while (qh < qt) {
+            int cur = w.idx2id[qh];
+            w.id2idx[cur] = qh++;
+            if (cur == SINK_ID) break;
+            int on = w.out_n[cur], ooff = w.out_off[cur];
+            for (int i = 0; i < on; ++i) {
+                int o = w.pool_id[ooff + i];
+                if (--w.tmp0[o] == 0) {
+                    int an = w.aln_n[o], ok = 1;
+                    for (int j = 0; j < an; ++j) if (w.tmp0[w.aln[4 * o + j]] != 0) { ok = 0; break; }
+                    if (!ok) continue;
+                    w.idx2id[qt++] = o;
+                    for (int j = 0; j < an; ++j) w.idx2id[qt++] = w.aln[4 * o + j];
+                }
+            }
+        }
+    }
+    sync_block<NW>();
+    // abpoa_graph.c:192-219: exchange sort by weight, strict <, not stable; one node per thread
+    for (int v = tid; v < n; v += NT) {
+        for (int side = 0; side < 2; ++side) {
+            int cnt = side ? w.out_n[v] : w.in_n[v];
+            int off = side ? w.out_off[v] : w.in_off[v];
+            for (int j = 0; j < cnt - 1; ++j)
+                for (int k = j + 1; k < cnt; ++k)
+                    if (w.pool_w[off + j] < w.pool_w[off + k]) {
+                        int t = w.pool_id[off + j]; w.pool_id[off + j] = w.pool_id[off + k]; w.pool_id[off + k] = t;
+                        t = w.pool_w[off + j]; w.pool_w[off + j] = w.pool_w[off + k]; w.pool_w[off + k] = t;
+                    }
+        }
+        if (banded) { w.tmp0[v] = w.out_n[v]; w.remain[v] = 0; }
+    }
+    sync_block<NW>();
+    if (banded && tid == 0) {  // abpoa_graph.c:268-309
+        int qh = 0, qt = 0;
+        int *q = w.tmp1;
+        q[qt++] = SINK_ID; w.remain[SINK_ID] = -1;
+        while (qh < qt) {
+            int cur = q[qh++];
+            if (cur != SINK_ID) {
+                int max_w = -1, max_id = -1;
+                int on = w.out_n[cur], ooff = w.out_off[cur];
+                for (int i = 0; i < on; ++i)
+                    if (w.pool_w[ooff + i] > max_w) { max_w = w.pool_w[ooff + i]; max_id = w.pool_id[ooff + i]; }
+                w.remain[cur] = w.remain[max_id] + 1;
+            }
+            if (cur == SRC_ID) break;
+            int in = w.in_n[cur], ioff = w.in_off[cur];
+            for (int i = 0; i < in; ++i) {
+                int p = w.pool_id[ioff + i];
+                if (--w.tmp0[p] == 0) q[qt++] = p;
+            }
+        }
+    }
+    sync_block<NW>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// first sequence (abpoa_graph.c:573-592): a chain src -> bases -> sink, built by all threads
+// ------------------------------------------------------------------------------------------------
+template <int NW>
+POA_DN void add_first_sequence(Shared &sh, const uint8_t *q, int qlen, int wt, int *path) {
+    constexpr int NT = NW * POA_WARP;
+    Ws &w = sh.ws;
+    const int tid = poa_tid();
+    // graph holds only src and sink here; sequential semantics: nodes 2..qlen+1 in order.
+    // (src/sink may already carry src->sink edges from earlier empty sequences.)
+    const int n0 = sh.n_node;
+    if (n0 + qlen > sh.nmax) { sync_block<NW>(); if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+    for (int t = tid; t < qlen; t += NT) {
+        int v = n0 + t;
+        w.base[v] = q[t]; w.aln_n[v] = 0;
+        w.in_off[v] = 4 * v; w.out_off[v] = 4 * v + 2;
+        w.in_n[v] = 1; w.out_n[v] = 1;
+        w.pool_id[4 * v] = (t == 0) ? SRC_ID : v - 1; w.pool_w[4 * v] = wt;
+        w.pool_id[4 * v + 2] = (t == qlen - 1) ? SINK_ID : v + 1; w.pool_w[4 * v + 2] = wt;
+        path[t] = v;
+    }
+    sync_block<NW>();
+    if (tid == 0) {
+        sh.n_node = n0 + qlen;
+        if (qlen > 0) {
+            edge_push(sh, w.out_off, w.out_n, SRC_ID, n0, wt);
+            edge_push(sh, w.in_off, w.in_n, SINK_ID, n0 + qlen - 1, wt);
+        } else {
+            add_edge(sh, SRC_ID, SINK_ID, 0, wt);
+        }
+    }
+    sync_block<NW>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-alignment row tables: everything the fill loop needs, indexed by row (= BFS index)
+// ------------------------------------------------------------------------------------------------
+template <int NW>
+POA_DN void build_rows(Shared &sh, int qlen, int banded) {
+    constexpr int NT = NW * POA_WARP;
+    Ws &w = sh.ws;
+    const int tid = poa_tid();
+    const int n = sh.n_node;
+    for (int i = tid; i < n; i += NT) {
+        int v = w.idx2id[i];
+        int in = w.in_n[v], ioff = w.in_off[v], on = w.out_n[v], ooff = w.out_off[v];
+        w.rowinfo[i] = poa_make_int4(ioff, in, ooff, on);
+        w.rbase[i] = w.base[v];
+        for (int k = 0; k < in; ++k) w.pool_row[ioff + k] = w.id2idx[w.pool_id[ioff + k]];
+        for (int k = 0; k < on; ++k) w.pool_row[ooff + k] = w.id2idx[w.pool_id[ooff + k]];
+        if (banded) {
+            w.rr[i] = qlen - w.remain[v];  // qlen - (remain[v] - remain[sink] - 1), remain[sink] = -1
+            w.mplr[i] = n; w.mprr[i] = 0;  // abpoa_graph.c:349-352
+        }
+    }
+    sync_block<NW>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// DP fill
+// ------------------------------------------------------------------------------------------------
+template <typename S> struct VecIO;
+template <> struct VecIO<short> {
+    POA_SM void load(const short *p, int v[8]) {
+        uint4 u = *reinterpret_cast<const uint4 *>(p);
+        v[0] = (short)(u.x & 0xffffu); v[1] = (short)(u.x >> 16); v[2] = (short)(u.y & 0xffffu); v[3] = (short)(u.y >> 16);
+        v[4] = (short)(u.z & 0xffffu); v[5] = (short)(u.z >> 16); v[6] = (short)(u.w & 0xffffu); v[7] = (short)(u.w >> 16);
+    }
+    POA_SM void store(short *p, const int v[8]) {
+        uint4 u;
+        u.x = ((unsigned)v[0] & 0xffffu) | ((unsigned)v[1] << 16); u.y = ((unsigned)v[2] & 0xffffu) | ((unsigned)v[3] << 16);
+        u.z = ((unsigned)v[4] & 0xffffu) | ((unsigned)v[5] << 16); u.w = ((unsigned)v[6] & 0xffffu) | ((unsigned)v[7] << 16);
+        *reinterpret_cast<uint4 *>(p) = u;
+    }
+};
+template <> struct VecIO<int> {
+    POA_SM void load(const int *p, int v[8]) {
+        int4 a = *reinterpret_cast<const int4 *>(p), b = *reinterpret_cast<const int4 *>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    POA_SM void store(int *p, const int v[8]) {
+        *reinterpret_cast<int4 *>(p) = poa_make_int4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<int4 *>(p + 4) = poa_make_int4(v[4], v[5], v[6], v[7]);
+    }
+};
+
+template <typename S>
+POA_D int inf_min_of(const DevParams &P) {  // abpoa_align_simd.c:1295 / :1299
+    long long bm = sizeof(S) == 2 ? (long long)INT16_MIN : (long long)INT32_MIN;
+    long long a = bm + P.min_mis, b = bm + P.oe1, c = bm + P.oe2;
+    long long m = a > b ? a : b; m = m > c ? m : c;
+    return (int)(m + 512 * (P.e1 > P.e2 ? P.e1 : P.e2));
+}
+
+// Row r of the current alignment is stored band-only: rowmeta[r] = {first vector index in the slab,
+// beg, end, 0}; five planes (H, E1, E2, F1, F2) of nv = (end>>3)-(beg>>3)+1 vectors each follow one
+// another.  Cells of those vectors that lie outside [beg,end] hold inf_min in every plane.
+template <typename S>
+POA_D const S *cell_ptr(const Ws &w, const int4 &pm, int plane, int j) {
+    int vb = pm.y >> 3, nv = (pm.z >> 3) - vb + 1;
+    return reinterpret_cast<const S *>(w.slab) + ((long long)pm.x + (long long)plane * nv) * 8 + (j - vb * 8);
+}
+
+template <int NW, typename S>
+POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, long long slab_vecs) {
+    constexpr int NT = NW * POA_WARP;
+    Ws &w = sh.ws;
+    const int tid = poa_tid();
+    const int lane = tid % POA_WARP, wid = tid / POA_WARP;
+    const int n_node = sh.n_node;
+    const int rows = n_node - 1;  // the sink row is never filled
+    const int inf_min = inf_min_of<S>(P);
+    const int pn = sizeof(S) == 2 ? P.pn16 : P.pn32;
+    const int local = P.local;
+    const int wb = local ? -1 : P.wb;  // abpoa_align.c:158
+#ifdef POA_HOST_EMU
+    const int bw = wb < 0 ? qlen : wb + (int)(P.wf * qlen);  // abpoa_align_simd.c:474
+#else
+    const int bw = wb < 0 ? qlen : wb + (int)__fmul_rn(P.wf, (float)qlen);
+#endif
+    const int e1 = P.e1, e2 = P.e2, oe1 = P.oe1, oe2 = P.oe2;
+    S *slab = reinterpret_cast<S *>(w.slab);
+    long long used = 0;  // vectors
+    long long inband = 0;
+    int xbuf = 0;        // parity of the cross-warp exchange buffers
+    (void)lane; (void)wid;
+
+    // ---- row 0 (abpoa_align_simd.c:617-688)
+    {
+        int end0;
+        if (wb >= 0) {
+            if (tid == 0) {
+                w.mplr[0] = 0; w.mprr[0] = 0;
+                int4 ri = w.rowinfo[0];
+                for (int k = 0; k < ri.w; ++k) { int o = w.pool_row[ri.z + k]; w.mplr[o] = 1; w.mprr[o] = 1; }
+            }
+            end0 = imin(qlen, imax(0, w.rr[0]) + bw);
+        } else end0 = qlen;
+        int nv = (end0 >> 3) + 1;
+        if (5LL * nv > slab_vecs) { if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+        if (tid == 0) w.rowmeta[0] = poa_make_int4(0, 0, end0, 0);
+        for (int vc = tid; vc < nv; vc += NT) {
+            int H[8], E1[8], E2[8], F1[8], F2[8];
+            for (int c = 0; c < 8; ++c) {
+                int j = vc * 8 + c;
+                if (j > end0) { H[c] = E1[c] = E2[c] = F1[c] = F2[c] = inf_min; }
+                else if (local) { H[c] = E1[c] = E2[c] = F1[c] = F2[c] = 0; }
+                else if (j == 0) { H[c] = 0; E1[c] = (S)(-oe1); E2[c] = (S)(-oe2); F1[c] = F2[c] = inf_min; }
+                else {
+                    F1[c] = (S)(-P.o1 - e1 * j); F2[c] = (S)(-P.o2 - e2 * j);
+                    H[c] = imax(F1[c], F2[c]); E1[c] = E2[c] = inf_min;
+                }
+            }
+            S *p = slab + (long long)vc * 8;
+            VecIO<S>::store(p, H); VecIO<S>::store(p + (long long)nv * 8, E1); VecIO<S>::store(p + 2LL * nv * 8, E2);
+            VecIO<S>::store(p + 3LL * nv * 8, F1); VecIO<S>::store(p + 4LL * nv * 8, F2);
+        }
+        used = 5LL * nv;
+        inband += end0 + 1;
+        sync_block<NW>();
+    }
+    int best_score = inf_min, best_i = 0, best_j = 0;
+    const int f0_1 = imax((int)(S)(inf_min - oe1), (int)(S)(inf_min - e1));
+    const int f0_2 = imax((int)(S)(inf_min - oe2), (int)(S)(inf_min - e2));
+
+    // ---- rows in index order (abpoa_align_simd.c:1205-1221)
+    for (int i = 1; i < rows; ++i) {
+        const int4 ri = w.rowinfo[i];  // {in_off, in_n, out_off, out_n}
+        const int *mrow = P.mat + 5 * w.rbase[i];
+        int beg, end;
+        if (wb < 0) { beg = 0; end = qlen; }
+        else {  // abpoa_align.h:34-35, abpoa_align_simd.c:946-960
+            int r = w.rr[i];
+            beg = imax(0, imin(w.mplr[i], r) - bw);
+            end = imin(qlen, imax(w.mprr[i], r) + bw);
+            int beg_sn = beg / pn, min_pre_beg = INT_MAX, min_pre_beg_sn = INT_MAX;
+            for (int k = 0; k < ri.y; ++k) {
+                int pb = w.rowmeta[w.pool_row[ri.x + k]].y;
+                if (min_pre_beg > pb) { min_pre_beg = pb; min_pre_beg_sn = pb / pn; }
+            }
+            if (beg_sn < min_pre_beg_sn) beg = min_pre_beg;
+        }
+        if (end < beg) end = beg;
+        const int vb = beg >> 3, ve = end >> 3, nv = ve - vb + 1;
+        if (used + 5LL * nv > slab_vecs) { if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+        const long long roff = used;
+        used += 5LL * nv;
+        inband += end - beg + 1;
+
+        int carry1 = f0_1 + e1 * beg, carry2 = f0_2 + e2 * beg;  // G[beg] of the two gap pieces
+        int mx = inf_min, left = -1, right = -1;
+        for (int vc0 = vb; vc0 <= ve; vc0 += NT) {
+            const int vc = vc0 + tid;
+            const bool act = vc <= ve;
+            const int j0 = vc * 8;
+            int M[8], E1[8], E2[8];
+            for (int c = 0; c < 8; ++c) { M[c] = inf_min; E1[c] = inf_min; E2[c] = inf_min; }
+            if (act) {
+                for (int k = 0; k < ri.y; ++k) {  // predecessors in in_id order (abpoa_align_simd.c:966-1029)
+                    const int4 pm = w.rowmeta[w.pool_row[ri.x + k]];
+                    const int pvb = pm.y >> 3, pve = pm.z >> 3, pnv = pve - pvb + 1;
+                    const S *pH = slab + (long long)pm.x * 8;
+                    if (vc >= pvb && vc <= pve) {
+                        int hv[8], ev[8];
+                        const S *ph = pH + (long long)(vc - pvb) * 8;
+                        VecIO<S>::load(ph, hv);
+                        for (int c = 0; c < 7; ++c) M[c + 1] = imax(M[c + 1], hv[c]);
+                        VecIO<S>::load(ph + (long long)pnv * 8, ev);
+                        for (int c = 0; c < 8; ++c) E1[c] = imax(E1[c], ev[c]);
+                        VecIO<S>::load(ph + 2LL * pnv * 8, ev);
+                        for (int c = 0; c < 8; ++c) E2[c] = imax(E2[c], ev[c]);
+                    }
+                    if (vc - 1 >= pvb && vc - 1 <= pve) M[0] = imax(M[0], (int)pH[(long long)(vc - 1 - pvb) * 8 + 7]);
+                }
+                if (local && vc == 0) M[0] = imax(M[0], 0);  // abpoa_align_simd.c:974 (`first` = 0)
+            }
+            // H = M + profile; Hh = max(H, E1, E2); scan inputs (abpoa_align_simd.c:1032-1059)
+            int Hh[8], c1[8], c2[8];
+            int t1 = NEG_INF32, t2 = NEG_INF32;
+            for (int c = 0; c < 8; ++c) {
+                const int j = j0 + c;
+                const bool inb = act && j >= beg && j <= end;
+                int hh = inf_min;
+                if (inb) {
+                    int s = j == 0 ? 0 : mrow[q[j - 1]];
+                    int hm = (S)(M[c] + s);
+                    hh = imax(imax(hm, E1[c]), E2[c]);
+                    // exclusive prefixes: value seen by cell j is the max over cells < j
+                    c1[c] = t1; c2[c] = t2;
+                    t1 = imax(t1, hh - oe1 + e1 * (j + 1));
+                    t2 = imax(t2, hh - oe2 + e2 * (j + 1));
+                } else { c1[c] = t1; c2[c] = t2; }
+                Hh[c] = hh;
+            }
+            // exclusive max-scan of the per-thread totals across the chunk
+            int i1 = t1, i2 = t2;
+            for (int d = 1; d < POA_WARP; d <<= 1) {
+                int u1 = poa_shfl_up(i1, d), u2 = poa_shfl_up(i2, d);
+                if (lane >= d) { i1 = imax(i1, u1); i2 = imax(i2, u2); }
+            }
+            int x1 = poa_shfl_up(i1, 1), x2 = poa_shfl_up(i2, 1);
+            if (lane == 0) { x1 = NEG_INF32; x2 = NEG_INF32; }
+            int tot1 = poa_shfl(i1, POA_WARP - 1), tot2 = poa_shfl(i2, POA_WARP - 1);
+            if (NW > 1) {
+                if (lane == POA_WARP - 1) { sh.scan_x[xbuf][0][wid] = i1; sh.scan_x[xbuf][1][wid] = i2; }
+                poa_sync_block();
+                int p1 = NEG_INF32, p2 = NEG_INF32, a1 = NEG_INF32, a2 = NEG_INF32;
+                for (int ww = 0; ww < NW; ++ww) {
+                    int v1 = sh.scan_x[xbuf][0][ww], v2 = sh.scan_x[xbuf][1][ww];
+                    if (ww < wid) { p1 = imax(p1, v1); p2 = imax(p2, v2); }
+                    a1 = imax(a1, v1); a2 = imax(a2, v2);
+                }
+                x1 = imax(x1, p1); x2 = imax(x2, p2); tot1 = a1; tot2 = a2;
+                xbuf ^= 1;
+            }
+            x1 = imax(x1, carry1); x2 = imax(x2, carry2);
+            carry1 = imax(carry1, tot1); carry2 = imax(carry2, tot2);
+            if (act) {
+                int H[8], F1[8], F2[8];
+                for (int c = 0; c < 8; ++c) {
+                    const int j = j0 + c;
+                    if (j >= beg && j <= end) {
+                        int f1 = (S)(imax(x1, c1[c]) - e1 * j);
+                        int f2 = (S)(imax(x2, c2[c]) - e2 * j);
+                        int h = imax(Hh[c], imax(f1, f2));
+                        if (local) h = imax(h, 0);
+                        int ne1 = imax((int)(S)(E1[c] - e1), (int)(S)(h - oe1));
+                        int ne2 = imax((int)(S)(E2[c] - e2), (int)(S)(h - oe2));
+                        if (local) { ne1 = imax(ne1, 0); ne2 = imax(ne2, 0); }
+                        H[c] = h; F1[c] = f1; F2[c] = f2; E1[c] = ne1; E2[c] = ne2;
+                        if (h > mx) { mx = h; left = right = j; } else if (h == mx) right = j;  // abpoa_align_simd.c:1107-1119
+                    } else { H[c] = E1[c] = E2[c] = F1[c] = F2[c] = inf_min; }
+                }
+                S *p = slab + (roff + (vc - vb)) * 8;
+                VecIO<S>::store(p, H); VecIO<S>::store(p + (long long)nv * 8, E1); VecIO<S>::store(p + 2LL * nv * 8, E2);
+                VecIO<S>::store(p + 3LL * nv * 8, F1); VecIO<S>::store(p + 4LL * nv * 8, F2);
+            }
+        }
+        if (tid == 0) w.rowmeta[i] = poa_make_int4((int)roff, beg, end, 0);
+        if (local || wb >= 0) {
+            int amx = poa_redux_max(mx);
+            int al = poa_redux_min((mx == amx && left >= 0) ? left : INT_MAX);
+            int ar = poa_redux_max(mx == amx ? right : -1);
+            if (NW > 1) {
+                if (lane == 0) { sh.red_x[xbuf][0][wid] = amx; sh.red_x[xbuf][1][wid] = al; sh.red_x[xbuf][2][wid] = ar; }
+                poa_sync_block();
+                int gm = sh.red_x[xbuf][0][0];
+                for (int ww = 1; ww < NW; ++ww) gm = imax(gm, sh.red_x[xbuf][0][ww]);
+                int gl = INT_MAX, gr = -1;
+                for (int ww = 0; ww < NW; ++ww) if (sh.red_x[xbuf][0][ww] == gm) {
+                    gl = imin(gl, sh.red_x[xbuf][1][ww]); gr = imax(gr, sh.red_x[xbuf][2][ww]);
+                }
+                amx = gm; al = gl; ar = gr;
+                xbuf ^= 1;
+            }
+            if (al == INT_MAX) al = -1;
+            if (local && amx > best_score) { best_score = amx; best_i = i; best_j = al; }  // abpoa_align_simd.c:1208-1210
+            if (wb >= 0) {  // abpoa_align_simd.c:1121-1130
+                for (int k = tid; k < ri.w; k += NT) {
+                    int o = w.pool_row[ri.z + k];
+                    if (ar + 1 > w.mprr[o]) w.mprr[o] = ar + 1;
+                    if (al + 1 < w.mplr[o]) w.mplr[o] = al + 1;
+                }
+            }
+        }
+        sync_block<NW>();
+    }
+    // ---- global best (abpoa_align_simd.c:1092-1105)
+    if (tid == 0) {
+        if (!local) {
+            const int4 ri = w.rowinfo[rows];  // sink row
+            for (int k = 0; k < ri.y; ++k) {
+                int pi = w.pool_row[ri.x + k];
+                const int4 pm = w.rowmeta[pi];
+                int e = qlen > pm.z ? pm.z : qlen;
+                int sc = *cell_ptr<S>(w, pm, 0, e);
+                if (sc > best_score) { best_score = sc; best_i = pi; best_j = e; }
+            }
+        }
+        sh.best_score = best_score; sh.best_i = best_i; sh.best_j = best_j;
+        sh.inband += inband;
+    }
+    sync_block<NW>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// backtrack (abpoa_align_simd.c:309-458), one thread
+// ------------------------------------------------------------------------------------------------
+POA_D void push_cigar(Shared &sh, int op, int len, int node_id, int query_id) {  // abpoa_align.h:54-73
+    unsigned long long *cig = sh.ws.cig + sh.cig_base;
+    unsigned long long l = (unsigned long long)len;
+    int n = sh.n_cigar;
+    if (n == 0 || op != CINS || op != (int)(cig[n - 1] & 0xf)) {
+        unsigned long long n_id = (unsigned long long)(long long)node_id, q_id = (unsigned long long)(long long)query_id;
+        if (op == CMATCH) cig[n] = n_id << 34 | q_id << 4 | (unsigned)op;
+        else if (op == CINS) cig[n] = q_id << 34 | l << 4 | (unsigned)op;
+        else cig[n] = n_id << 34 | l << 4 | (unsigned)op;
+        sh.n_cigar = n + 1;
+    } else cig[n - 1] += l << 4;
+}
+
+template <typename S>
+POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen) {
+    Ws &w = sh.ws;
+    const int inf_min = inf_min_of<S>(P);
+    const int local = P.local;
+    const int e1 = P.e1, e2 = P.e2, oe1 = P.oe1, oe2 = P.oe2;
+    int i = sh.best_i, j = sh.best_j;
+    int id = w.idx2id[i];
+    int cur_op = OP_ALL;
+    sh.n_cigar = 0;
+    if (j < qlen) push_cigar(sh, CINS, qlen - j, -1, qlen - 1);
+    while (i > 0 && j > 0) {
+        const int4 rm = w.rowmeta[i];
+        const int Hj = *cell_ptr<S>(w, rm, 0, j);
+        if (local && Hj == 0) break;
+        const int4 ri = w.rowinfo[i];
+        const int s = P.mat[5 * w.rbase[i] + q[j - 1]];
+        int hit = 0;
+        if (cur_op & OP_M) {
+            for (int k = 0; k < ri.y; ++k) {
+                int pi = w.pool_row[ri.x + k];
+                const int4 pm = w.rowmeta[pi];
+                if (j - 1 < pm.y || j - 1 > pm.z) continue;
+                if ((int)(S)(*cell_ptr<S>(w, pm, 0, j - 1) + s) == Hj) {
+                    push_cigar(sh, CMATCH, 1, id, j - 1);
+                    i = pi; --j; id = w.idx2id[i]; hit = 1; cur_op = OP_ALL;
+                    break;
+                }
+            }
+        }
+        if (hit == 0 && (cur_op & OP_E)) {
+            const int E1j = *cell_ptr<S>(w, rm, 1, j), E2j = *cell_ptr<S>(w, rm, 2, j);
+            for (int k = 0; k < ri.y; ++k) {
+                int pi = w.pool_row[ri.x + k];
+                const int4 pm = w.rowmeta[pi];
+                if (j < pm.y || j > pm.z) continue;
+                const int pH = *cell_ptr<S>(w, pm, 0, j);
+                if (cur_op & OP_E1) {
+                    const int pE1 = *cell_ptr<S>(w, pm, 1, j);
+                    bool cond = (cur_op & OP_M) ? (Hj == pE1) : (E1j == (int)(S)(pE1 - e1));
+                    if (cond) {
+                        cur_op = ((int)(S)(pH - oe1) == pE1) ? (OP_M | OP_F) : OP_E1;
+                        hit = 1; push_cigar(sh, CDEL, 1, id, j - 1);
+                        i = pi; id = w.idx2id[i];
+                        break;
+                    }
+                }
+                if (cur_op & OP_E2) {
+                    const int pE2 = *cell_ptr<S>(w, pm, 2, j);
+                    bool cond = (cur_op & OP_M) ? (Hj == pE2) : (E2j == (int)(S)(pE2 - e2));
+                    if (cond) {
+                        cur_op = ((int)(S)(pH - oe2) == pE2) ? (OP_M | OP_F) : OP_E2;
+                        hit = 1; push_cigar(sh, CDEL, 1, id, j - 1);
+                        i = pi; id = w.idx2id[i];
+                        break;
+                    }
+                }
+            }
+        }
+        if (hit == 0 && (cur_op & OP_F)) {
+            const bool inl = j - 1 >= rm.y;  // left neighbour inside this row's band?
+            const int hl = inl ? (int)*cell_ptr<S>(w, rm, 0, j - 1) : inf_min;
+            const int F1j = *cell_ptr<S>(w, rm, 3, j), F2j = *cell_ptr<S>(w, rm, 4, j);
+            if (cur_op & OP_F1) {
+                if (!(cur_op & OP_M) || Hj == F1j) {
+                    const int f1l = inl ? (int)*cell_ptr<S>(w, rm, 3, j - 1) : inf_min;
+                    if ((int)(S)(hl - oe1) == F1j) { cur_op = OP_M | OP_E; hit = 1; }
+                    else if ((int)(S)(f1l - e1) == F1j) { cur_op = OP_F1; hit = 1; }
+                }
+            }
+            if (hit == 0 && (cur_op & OP_F2)) {
+                if (!(cur_op & OP_M) || Hj == F2j) {
+                    const int f2l = inl ? (int)*cell_ptr<S>(w, rm, 4, j - 1) : inf_min;
+                    if ((int)(S)(hl - oe2) == F2j) { cur_op = OP_M | OP_E; hit = 1; }
+                    else if ((int)(S)(f2l - e2) == F2j) { cur_op = OP_F2; hit = 1; }
+                }
+            }
+            if (hit == 1) { push_cigar(sh, CINS, 1, id, j - 1); --j; }
+        }
+        if (hit == 0) { sh.err = ST_EINTERNAL; return; }
+    }
+    if (j > 0) push_cigar(sh, CINS, j, -1, j - 1);
+    unsigned long long *cig = w.cig + sh.cig_base;
+    int n = sh.n_cigar;
+    for (int k = 0; k < n >> 1; ++k) { unsigned long long t = cig[k]; cig[k] = cig[n - 1 - k]; cig[n - 1 - k] = t; }  // abpoa_align.h:88-96
+}
+
+// ------------------------------------------------------------------------------------------------
+// graph fusion (abpoa_graph.c:688-773), one thread.  path[qpos] = node id the base was placed on.
+// ------------------------------------------------------------------------------------------------
+POA_DN int fuse(Shared &sh, const uint8_t *seq, int seq_l, int wt, int *path) {
+    Ws &w = sh.ws;
+    const unsigned long long *cig = w.cig + sh.cig_base;
+    const int n_cigar = sh.n_cigar;
+    if (n_cigar == 0) return 0;  // abpoa_graph.c:706-708: the read is silently not added
+    if (sh.n_node + seq_l > sh.nmax) { sh.err = ST_ESLAB; return 0; }  // a read adds at most seq_l nodes
+    int query_id = -1, last_new = 0, last_id = SRC_ID;
+    for (int i = 0; i < n_cigar; ++i) {
+        int op = (int)(cig[i] & 0xf);
+        if (op == CMATCH) {
+            int node_id = (int)((cig[i] >> 34) & 0x3fffffff);
+            query_id++;
+            int b = seq[query_id];
+            if (w.base[node_id] != b) {
+                int aligned_id = get_aligned_id(w, node_id, b);
+                if (aligned_id != -1) {
+                    add_edge(sh, last_id, aligned_id, 1 - last_new, wt);
+                    last_id = aligned_id; last_new = 0;
+                } else {
+                    int new_id = add_node(sh, b);
+                    add_edge(sh, last_id, new_id, 0, wt);
+                    last_id = new_id; last_new = 1;
+                    add_aligned(w, node_id, new_id);
+                }
+            } else {
+                add_edge(sh, last_id, node_id, 1 - last_new, wt);
+                last_id = node_id; last_new = 0;
+            }
+            path[query_id] = last_id;
+        } else if (op == CINS) {
+            int len = (int)((cig[i] >> 4) & 0x3fffffff);
+            query_id += len;
+            for (int j = len - 1; j >= 0; --j) {
+                int new_id = add_node(sh, seq[query_id - j]);
+                add_edge(sh, last_id, new_id, 0, wt);
+                last_id = new_id; last_new = 1;
+                path[query_id - j] = last_id;
+            }
+        }
+    }
+    add_edge(sh, last_id, SINK_ID, 1 - last_new, wt);
+    return seq_l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// consensus (abpoa_output.c:468-536 + :375-391, one cluster) and MSA rank (abpoa_graph.c:359-410)
+// ------------------------------------------------------------------------------------------------
+POA_DN int heaviest_bundling(Shared &sh, int *cons) {  // one thread; uses tmp0..tmp3
+    Ws &w = sh.ws;
+    const int n = sh.n_node;
+    int *outdeg = w.tmp0, *score = w.tmp1, *max_out = w.tmp2, *q = w.tmp3;
+    for (int i = 0; i < n; ++i) { outdeg[i] = w.out_n[i]; max_out[i] = -1; score[i] = 0; }
+    int qh = 0, qt = 0;
+    q[qt++] = SINK_ID;
+    while (qh < qt) {
+        int cur = q[qh++];
+        if (cur == SINK_ID) { max_out[cur] = -1; score[cur] = 0; }
+        else {
+            int max_id = -1;
+            int on = w.out_n[cur], ooff = w.out_off[cur];
+            if (cur == SRC_ID) {
+                int path_score = -1, path_max_w = -1;
+                for (int i = 0; i < on; ++i) {
+                    int o = w.pool_id[ooff + i], ow = w.pool_w[ooff + i];
+                    if (ow > path_max_w || (ow == path_max_w && score[o] > path_score)) { max_id = o; path_score = score[o]; path_max_w = ow; }
+                }
+                max_out[cur] = max_id;
+                break;
+            } else {
+                int max_w = INT_MIN;
+                for (int i = 0; i < on; ++i) {
+                    int o = w.pool_id[ooff + i], ow = w.pool_w[ooff + i];
+                    if (max_w < ow) { max_w = ow; max_id = o; }
+                    else if (max_w == ow && score[max_id] <= score[o]) max_id = o;
+                }
+                score[cur] = max_w + score[max_id];
+                max_out[cur] = max_id;
+            }
+        }
+        int in = w.in_n[cur], ioff = w.in_off[cur];
+        for (int i = 0; i < in; ++i) { int p = w.pool_id[ioff + i]; if (--outdeg[p] == 0) q[qt++] = p; }
+    }
+    int len = 0, cur = max_out[SRC_ID];
+    while (cur != SINK_ID && cur >= 0) { cons[len++] = cur; cur = max_out[cur]; }
+    return len;
+}
+
+POA_DN void set_msa_rank(Shared &sh, int *rank) {  // one thread; uses tmp0 (in-degree), tmp1 (stack)
+    Ws &w = sh.ws;
+    const int n = sh.n_node;
+    int *indeg = w.tmp0, *st = w.tmp1;
+    int sp = 0, msa_rank = 0;
+    for (int i = 0; i < n; ++i) { indeg[i] = w.in_n[i]; rank[i] = -1; }
+    st[sp++] = SRC_ID;
+    while (sp > 0) {
+        int cur = st[--sp];
+        if (rank[cur] < 0) {
+            rank[cur] = msa_rank;
+            for (int i = 0; i < w.aln_n[cur]; ++i) rank[w.aln[4 * cur + i]] = msa_rank;
+            msa_rank++;
+        }
+        if (cur == SINK_ID) break;
+        int on = w.out_n[cur], ooff = w.out_off[cur];
+        for (int i = 0; i < on; ++i) {
+            int o = w.pool_id[ooff + i];
+            if (--indeg[o] == 0) {
+                int ok = 1, an = w.aln_n[o];
+                for (int j = 0; j < an; ++j) if (indeg[w.aln[4 * o + j]] != 0) { ok = 0; break; }
+                if (!ok) continue;
+                st[sp++] = o; rank[o] = -1;
+                for (int j = 0; j < an; ++j) { st[sp++] = w.aln[4 * o + j]; rank[w.aln[4 * o + j]] = -1; }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one POA block, start to finish
+// ------------------------------------------------------------------------------------------------
+POA_D void ws_bind(Ws &w, char *b, const WsLayout &L) {
+    w.base = (uint8_t *)(b + L.o_base); w.aln_n = (uint8_t *)(b + L.o_aln_n); w.aln = (int *)(b + L.o_aln);
+    w.in_off = (int *)(b + L.o_in_off); w.in_n = (int *)(b + L.o_in_n); w.out_off = (int *)(b + L.o_out_off); w.out_n = (int *)(b + L.o_out_n);
+    w.pool_id = (int *)(b + L.o_pool_id); w.pool_w = (int *)(b + L.o_pool_w); w.pool_row = (int *)(b + L.o_pool_row);
+    w.idx2id = (int *)(b + L.o_idx2id); w.id2idx = (int *)(b + L.o_id2idx); w.remain = (int *)(b + L.o_remain);
+    w.tmp0 = (int *)(b + L.o_tmp0); w.tmp1 = (int *)(b + L.o_tmp1); w.tmp2 = (int *)(b + L.o_tmp2); w.tmp3 = (int *)(b + L.o_tmp3);
+    w.rowinfo = (int4 *)(b + L.o_rowinfo); w.rowmeta = (int4 *)(b + L.o_rowmeta); w.rbase = (uint8_t *)(b + L.o_rbase);
+    w.rr = (int *)(b + L.o_rr); w.mplr = (int *)(b + L.o_mplr); w.mprr = (int *)(b + L.o_mprr);
+    w.cig = (unsigned long long *)(b + L.o_cig); w.path = (int *)(b + L.o_path); w.best = (int *)(b + L.o_best); w.ncig = (int *)(b + L.o_ncig);
+    w.slab = b + L.o_slab;
+}
+
+// block-wide sum of f(i), i in [0,n); result broadcast through sh.bcast[0..]
+template <int NW, typename F>
+POA_D long long block_sum(Shared &sh, int n, F f) {
+    constexpr int NT = NW * POA_WARP;
+    const int tid = poa_tid();
+    int s = 0;
+    for (int i = tid; i < n; i += NT) s += f(i);
+    sync_block<NW>();
+    if (tid == 0) sh.bcast[0] = 0;
+    sync_block<NW>();
+    if (s) poa_atomic_add(&sh.bcast[0], s);
+    sync_block<NW>();
+    int r = sh.bcast[0];
+    sync_block<NW>();
+    return r;
+}
+
+// exclusive prefix sum of src[0..n) into dst[0..n) (may alias), chunk per thread; returns total
+template <int NW>
+POA_D int block_excl_scan(Shared &sh, const int *src, int *dst, int n, int *scratch /* >= NT ints, global */) {
+    constexpr int NT = NW * POA_WARP;
+    const int tid = poa_tid();
+    const int per = (n + NT - 1) / NT;
+    const int lo = imin(n, tid * per), hi = imin(n, lo + per);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += src[i];
+    scratch[tid] = s;
+    sync_block<NW>();
+    int pre = 0, tot = 0;
+    for (int t = 0; t < NT; ++t) { int v = scratch[t]; if (t < tid) pre += v; tot += v; }
+    sync_block<NW>();
+    for (int i = lo; i < hi; ++i) { int v = src[i]; dst[i] = pre; pre += v; }
+    sync_block<NW>();
+    return tot;
+}
+
+template <int NW>
+POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const WsLayout &L, const DevOut &O, int b) {
+    constexpr int NT = NW * POA_WARP;
+    Ws &w = sh.ws;
+    const int tid = poa_tid();
+    const long long s0 = B.block_seq_off[b], s1 = B.block_seq_off[b + 1];
+    const int n_seq = (int)(s1 - s0);
+    const long long base0 = B.seq_off[s0];
+    const int banded = !P.local && P.wb >= 0;
+    long long t_ph[PH_N];
+    for (int k = 0; k < PH_N; ++k) t_ph[k] = 0;
+    long long t_start = poa_clock();
+
+    if (tid == 0) {
+        sh.n_node = 0; sh.err = ST_OK; sh.inband = 0; sh.cig_base = 0; sh.n_cigar = 0;
+        sh.nmax = L.nmax; sh.pool_cap = L.pool_cap;
+        sh.pool_used = 4 * L.nmax;
+        add_node(sh, 0); add_node(sh, 0);
+    }
+    sync_block<NW>();
+
+    int cig_tot = 0;
+    for (int k = 0; k < n_seq && sh.err == ST_OK; ++k) {
+        const int qlen = B.seq_len[s0 + k];
+        const long long qoff = B.seq_off[s0 + k] - base0;
+        const uint8_t *q = B.bases + B.seq_off[s0 + k];
+        const int wt = B.weight[s0 + k];
+        int *path = w.path + qoff;
+        int plen = 0;
+        if (tid == 0) { w.best[k] = 0; w.ncig[k] = 0; }
+        if (sh.n_node == 2) {  // abpoa_align.c:193-198 / abpoa_graph.c:699-702
+            long long t0 = poa_clock();
+            add_first_sequence<NW>(sh, q, qlen, wt, path);
+            plen = qlen;
+            t_ph[PH_FUSE] += poa_clock() - t0;
+        } else {
+            long long t0 = poa_clock();
+            build_rows<NW>(sh, qlen, banded);
+            long long t1 = poa_clock();
+            t_ph[PH_ROWS] += t1 - t0;
+            // abpoa_align_simd.c:1286-1302: int16 unless the score range needs 32 bits
+            const int gn = sh.n_node;
+            const int len = qlen > gn ? qlen : gn;
+            long long ms1 = (long long)qlen * P.match, ms2 = (long long)len * P.e1 + P.o1;
+            long long max_score = ms1 > ms2 ? ms1 : ms2;
+            const bool bits16 = max_score <= (long long)INT16_MAX - P.min_mis - P.oe1 - P.oe2;
+            if (bits16) fill<NW, short>(sh, P, q, qlen, L.slab_bytes / 16);
+            else fill<NW, int>(sh, P, q, qlen, L.slab_bytes / 32);
+            long long t2 = poa_clock();
+            t_ph[PH_FILL] += t2 - t1;
+            if (sh.err != ST_OK) break;
+            if (tid == 0) {
+                if (bits16) backtrack<short>(sh, P, q, qlen); else backtrack<int>(sh, P, q, qlen);
+            }
+            sync_block<NW>();
+            long long t3 = poa_clock();
+            t_ph[PH_BT] += t3 - t2;
+            if (sh.err != ST_OK) break;
+            if (tid == 0) {
+                w.best[k] = sh.best_score; w.ncig[k] = sh.n_cigar;
+                sh.bcast[1] = fuse(sh, q, qlen, wt, path);
+            }
+            sync_block<NW>();
+            plen = sh.bcast[1];
+            if (P.emit_cigar) cig_tot += sh.n_cigar;
+            t_ph[PH_FUSE] += poa_clock() - t3;
+            sync_block<NW>();
+            if (tid == 0 && P.emit_cigar) sh.cig_base += sh.n_cigar;
+        }
+        if (tid == 0) w.tmp3[k] = plen;  // path_len, parked until the output pass (tmp3 is free until then)
+        if (plen > 0 || sh.n_node == 2) {  // the reference re-sorts only when the read was added
+            long long t0 = poa_clock();
+            toposort<NW>(sh, banded);
+            t_ph[PH_TOPO] += poa_clock() - t0;
+        }
+        sync_block<NW>();
+    }
+    sync_block<NW>();
+
+    // ---- consensus, MSA rank, output
+    long long tf0 = poa_clock();
+    int *hdr = O.hdr + (long long)b * HDR_WORDS;
+    const int n = sh.n_node;
+    int status = sh.err;
+    if (status == ST_OK) {
+        // path lengths were parked in tmp3[0..n_seq); move them to w.ncig's neighbour array before tmp3 is reused
+        int *plen_arr = w.mplr;  // row tables are dead now; mplr/mprr/rr are free int[nmax] arrays (n_seq <= nmax)
+        for (int k = tid; k < n_seq; k += NT) plen_arr[k] = w.tmp3[k];
+        sync_block<NW>();
+        int cons_len = -1, msa_len = -1, msa_rows = 0;
+        int *cons = w.mprr;
+        int *rank = w.rr;
+        if (tid == 0) {
+            if (P.out_cons) cons_len = n > 2 ? heaviest_bundling(sh, cons) : 0;
+            if (P.out_msa) {
+                if (n > 2) {
+                    set_msa_rank(sh, rank);
+                    msa_len = rank[SINK_ID] - 1;
+                    msa_rows = n_seq + (P.out_cons ? 1 : 0);
+                    if (msa_len <= 0) { msa_len = 0; msa_rows = 0; }
+                } else { msa_len = 0; msa_rows = 0; }
+            }
+            sh.bcast[1] = cons_len; sh.bcast[2] = msa_len; sh.bcast[3] = msa_rows;
+        }
+        sync_block<NW>();
+        cons_len = sh.bcast[1]; msa_len = sh.bcast[2]; msa_rows = sh.bcast[3];
+        sync_block<NW>();
+        // section offsets
+        int *in_pre = w.tmp0, *out_pre = w.tmp1, *aln_pre = w.tmp2, *scr = w.tmp3;
+        const int in_tot = block_excl_scan<NW>(sh, w.in_n, in_pre, n, scr);
+        const int out_tot = block_excl_scan<NW>(sh, w.out_n, out_pre, n, scr);
+        for (int v = tid; v < n; v += NT) aln_pre[v] = w.aln_n[v];
+        sync_block<NW>();
+        const int aln_tot = block_excl_scan<NW>(sh, aln_pre, aln_pre, n, scr);
+        long long path_tot = 0;
+        for (int k = 0; k < n_seq; ++k) path_tot += plen_arr[k];
+        const long long msa_bytes = (long long)msa_rows * (msa_len > 0 ? msa_len : 0);
+        const long long words = 4LL * n + 2LL * in_tot + 2LL * out_tot + aln_tot + n_seq + path_tot + (cons_len > 0 ? cons_len : 0)
+                              + 2LL * n_seq + 2LL * cig_tot + (msa_bytes + 3) / 4;
+        if (tid == 0) {
+            unsigned long long off = poa_atomic_add(O.arena_used, (unsigned long long)words);
+            if (off + (unsigned long long)words > O.arena_cap) sh.err = ST_EARENA;
+            sh.bcast[0] = (int)(off & 0xffffffffull); sh.bcast[1] = (int)(off >> 32);
+        }
+        sync_block<NW>();
+        status = sh.err;
+        if (status == ST_OK) {
+            const unsigned long long off = (unsigned long long)(unsigned)sh.bcast[0] | ((unsigned long long)(unsigned)sh.bcast[1] << 32);
+            int *o = O.arena + off;
+            int *o_base = o, *o_in_n = o_base + n, *o_in_id = o_in_n + n, *o_in_w = o_in_id + in_tot;
+            int *o_out_n = o_in_w + in_tot, *o_out_id = o_out_n + n, *o_out_w = o_out_id + out_tot;
+            int *o_aln_n = o_out_w + out_tot, *o_aln_id = o_aln_n + n;
+            int *o_plen = o_aln_id + aln_tot, *o_path = o_plen + n_seq, *o_cons = o_path + path_tot;
+            int *o_best = o_cons + (cons_len > 0 ? cons_len : 0), *o_ncig = o_best + n_seq, *o_cig = o_ncig + n_seq;
+            uint8_t *o_msa = (uint8_t *)(o_cig + 2LL * cig_tot);
+            for (int v = tid; v < n; v += NT) {
+                o_base[v] = w.base[v];
+                int cn = w.in_n[v], off2 = w.in_off[v], dst = in_pre[v];
+                o_in_n[v] = cn;
+                for (int k = 0; k < cn; ++k) { o_in_id[dst + k] = w.pool_id[off2 + k]; o_in_w[dst + k] = w.pool_w[off2 + k]; }
+                cn = w.out_n[v]; off2 = w.out_off[v]; dst = out_pre[v];
+                o_out_n[v] = cn;
+                for (int k = 0; k < cn; ++k) { o_out_id[dst + k] = w.pool_id[off2 + k]; o_out_w[dst + k] = w.pool_w[off2 + k]; }
+                cn = w.aln_n[v]; dst = aln_pre[v];
+                o_aln_n[v] = cn;
+                for (int k = 0; k < cn; ++k) o_aln_id[dst + k] = w.aln[4 * v + k];
+            }
+            // per-read paths (only reads that were added have a path)
+            {
+                long long dst = 0;
+                for (int k = 0; k < n_seq; ++k) {
+                    const int pl = plen_arr[k];
+                    const int *src = w.path + (B.seq_off[s0 + k] - base0);
+                    for (int t = tid; t < pl; t += NT) o_path[dst + t] = src[t];
+                    dst += pl;
+                }
+                for (int k = tid; k < n_seq; k += NT) { o_plen[k] = plen_arr[k]; o_best[k] = w.best[k]; o_ncig[k] = P.emit_cigar ? w.ncig[k] : 0; }
+            }
+            for (int t = tid; t < cons_len; t += NT) o_cons[t] = cons[t];
+            for (int t = tid; t < cig_tot; t += NT) { unsigned long long c = w.cig[t]; o_cig[2 * t] = (int)(unsigned)(c & 0xffffffffull); o_cig[2 * t + 1] = (int)(unsigned)(c >> 32); }
+            if (msa_bytes > 0) {  // abpoa_output.c:149-192
+                for (long long t = tid; t < msa_bytes; t += NT) o_msa[t] = 5;
+                sync_block<NW>();
+                for (int k = 0; k < n_seq; ++k) {
+                    const int pl = plen_arr[k];
+                    const int *src = w.path + (B.seq_off[s0 + k] - base0);
+                    for (int t = tid; t < pl; t += NT) { int nd = src[t]; o_msa[(long long)k * msa_len + rank[nd] - 1] = w.base[nd]; }
+                }
+                if (P.out_cons) for (int t = tid; t < cons_len; t += NT) { int nd = cons[t]; o_msa[(long long)n_seq * msa_len + rank[nd] - 1] = w.base[nd]; }
+            }
+            if (tid == 0) {
+                hdr[H_N_NODE] = n; hdr[H_N_SEQ] = n_seq; hdr[H_CONS_LEN] = cons_len; hdr[H_MSA_LEN] = msa_len; hdr[H_MSA_ROWS] = msa_rows;
+                hdr[H_IN_TOT] = in_tot; hdr[H_OUT_TOT] = out_tot; hdr[H_ALN_TOT] = aln_tot; hdr[H_PATH_TOT] = (int)path_tot; hdr[H_CIG_TOT] = cig_tot;
+                hdr[H_OFF_LO] = sh.bcast[0]; hdr[H_OFF_HI] = sh.bcast[1];
+                hdr[H_INBAND_LO] = (int)(unsigned)(sh.inband & 0xffffffffll); hdr[H_INBAND_HI] = (int)(unsigned)((unsigned long long)sh.inband >> 32);
+            }
+        }
+    }
+    if (tid == 0) {
+        hdr[H_STATUS] = status;
+        if (status != ST_OK) { hdr[H_N_NODE] = 0; hdr[H_N_SEQ] = n_seq; }
+        long long t_end = poa_clock();
+        t_ph[PH_FINAL] = t_end - tf0; t_ph[PH_TOTAL] = t_end - t_start;
+        for (int k = 0; k < PH_N; ++k) if (t_ph[k]) poa_atomic_add(O.phase + k, (unsigned long long)t_ph[k]);
+    }
+    sync_block<NW>();
+}
+
+}  // namespace poa

@@ -1,0 +1,297 @@
+"""ctypes binding of the C ABI in include/poa_b200.h (libpoa_b200.so, hand-written sm_100a CUDA).
+
+Python is only the harness here (tests, bench, multi-GPU driver); the product is the shared library.
+The names mirror the reference's per-block call site: `PoaParams` carries what smooth_abpoa puts into
+abpoa_para_t (reference src/smooth.cpp:256-297), `PoaEngine.run_batch` stands where the OpenMP loop
+calls abpoa_poa (src/smooth.cpp:337, :1931), and `BlockView` exposes the abpoa_t fields that
+build_odgi_abPOA and the MAF code read afterwards (src/smooth.cpp:362-516, :2442-2574).
+
+There is deliberately no fallback: if the library is missing or no Blackwell GPU is present this
+module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libpoa_b200.so")
+
+# keep in sync with include/poa_b200.h
+OK, ESLAB, EARENA, EINTERNAL, EUNSUP, EBLOCK, ECUDA, EARG, ENOMEM = range(9)
+
+ABI_SYMBOLS = [
+    "poa_b200_abi_version", "poa_b200_strerror", "poa_b200_last_error",
+    "poa_b200_engine_create", "poa_b200_engine_destroy",
+    "poa_b200_run_batch", "poa_b200_poa_block",
+    "poa_b200_batch_upload", "poa_b200_batch_launch", "poa_b200_batch_download", "poa_b200_batch_finish",
+    "poa_b200_batch_free", "poa_b200_batch_stats",
+    "poa_b200_result_n_blocks", "poa_b200_result_block", "poa_b200_result_stats", "poa_b200_result_free",
+]
+
+
+class PoaParams(C.Structure):
+    """poa_b200_params_t; smoothxg defaults: scores 1,4,6,2,26,1 (src/main.cpp:322-327), wb=311, wf=0.03."""
+    _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open1", C.c_int32),
+                ("gap_ext1", C.c_int32), ("gap_open2", C.c_int32), ("gap_ext2", C.c_int32),
+                ("align_mode", C.c_int32), ("wb", C.c_int32), ("wf", C.c_float),
+                ("out_cons", C.c_int32), ("out_msa", C.c_int32)]
+
+
+def make_params(match=1, mismatch=4, gap_open1=6, gap_ext1=2, gap_open2=26, gap_ext2=1,
+                local=False, banded=True, out_cons=True, out_msa=False) -> PoaParams:
+    return PoaParams(match, mismatch, gap_open1, gap_ext1, gap_open2, gap_ext2,
+                     1 if local else 0, 311 if banded else -1, 0.03, int(out_cons), int(out_msa))
+
+
+class EngineOpts(C.Structure):
+    _fields_ = [("warps_per_block", C.c_int32), ("ctas_per_sm", C.c_int32), ("emit_cigar", C.c_int32),
+                ("reserved0", C.c_int32), ("slab_rows_factor", C.c_double), ("device_mem_budget", C.c_int64)]
+
+
+class _BlockView(C.Structure):
+    _fields_ = [("status", C.c_int32), ("n_node", C.c_int32), ("n_seq", C.c_int32), ("cons_len", C.c_int32),
+                ("msa_len", C.c_int32), ("msa_rows", C.c_int32),
+                ("base", C.POINTER(C.c_int32)), ("in_n", C.POINTER(C.c_int32)), ("in_id", C.POINTER(C.c_int32)),
+                ("in_w", C.POINTER(C.c_int32)), ("out_n", C.POINTER(C.c_int32)), ("out_id", C.POINTER(C.c_int32)),
+                ("out_w", C.POINTER(C.c_int32)), ("aln_n", C.POINTER(C.c_int32)), ("aln_id", C.POINTER(C.c_int32)),
+                ("path_len", C.POINTER(C.c_int32)), ("path_node", C.POINTER(C.c_int32)),
+                ("cons_node", C.POINTER(C.c_int32)), ("msa", C.POINTER(C.c_uint8)),
+                ("best_score", C.POINTER(C.c_int32)), ("n_cigar", C.POINTER(C.c_int32)),
+                ("cigar", C.POINTER(C.c_uint64)),
+                ("in_total", C.c_int64), ("out_total", C.c_int64), ("aln_total", C.c_int64),
+                ("path_total", C.c_int64), ("cigar_total", C.c_int64), ("inband_cells", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("inband_cells", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("kernel_launches", C.c_int32), ("retried_blocks", C.c_int32), ("n_ctas", C.c_int32),
+                ("warps_per_block", C.c_int32), ("workspace_bytes", C.c_int64), ("phase_cycles", C.c_int64 * 8)]
+
+    def as_dict(self):
+        names = ["rows", "fill", "backtrack", "fuse", "toposort", "finalize", "total", "spare"]
+        d = {f: getattr(self, f) for f, _ in self._fields_ if f != "phase_cycles"}
+        d["phase_cycles"] = {n: int(self.phase_cycles[i]) for i, n in enumerate(names)}
+        return d
+
+
+class PoaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"poa_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libpoa_b200.so; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(nvcc -gencode arch=compute_100a,code=sm_100a); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.poa_b200_abi_version.restype = C.c_int
+    lib.poa_b200_strerror.restype = C.c_char_p
+    lib.poa_b200_strerror.argtypes = [C.c_int]
+    lib.poa_b200_last_error.restype = C.c_char_p
+    lib.poa_b200_engine_create.argtypes = [C.c_int, C.POINTER(EngineOpts), C.POINTER(vp)]
+    lib.poa_b200_engine_destroy.argtypes = [vp]
+    lib.poa_b200_engine_destroy.restype = None
+    batch_args = [vp, C.POINTER(PoaParams), i64, vp, vp, vp, vp, vp, C.POINTER(vp)]
+    lib.poa_b200_run_batch.argtypes = batch_args
+    lib.poa_b200_batch_upload.argtypes = batch_args
+    lib.poa_b200_poa_block.argtypes = [vp, C.POINTER(PoaParams), i32, C.POINTER(C.c_void_p), vp, vp, C.POINTER(vp)]
+    lib.poa_b200_batch_launch.argtypes = [vp, vp]
+    lib.poa_b200_batch_download.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.poa_b200_batch_finish.argtypes = [vp, vp]
+    lib.poa_b200_batch_free.argtypes = [vp]
+    lib.poa_b200_batch_free.restype = None
+    lib.poa_b200_batch_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.poa_b200_result_n_blocks.argtypes = [vp]
+    lib.poa_b200_result_n_blocks.restype = i64
+    lib.poa_b200_result_block.argtypes = [vp, i64, C.POINTER(_BlockView)]
+    lib.poa_b200_result_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.poa_b200_result_free.argtypes = [vp]
+    lib.poa_b200_result_free.restype = None
+    _lib = lib
+    return lib
+
+
+def _check(lib, rc, allow=()):
+    if rc != OK and rc not in allow:
+        raise PoaError(rc, f"{lib.poa_b200_strerror(rc).decode()}: {lib.poa_b200_last_error().decode()}")
+    return rc
+
+
+def _arr(ptr, n, dtype=np.int32):
+    if n <= 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(int(n),)).copy()
+
+
+@dataclass
+class BlockView:
+    """One finished POA block (copies of the flat arrays of poa_b200_block_view_t)."""
+    status: int
+    n_node: int
+    n_seq: int
+    cons_len: int
+    msa_len: int
+    msa_rows: int
+    base: np.ndarray
+    in_n: np.ndarray
+    in_id: np.ndarray
+    in_w: np.ndarray
+    out_n: np.ndarray
+    out_id: np.ndarray
+    out_w: np.ndarray
+    aln_n: np.ndarray
+    aln_id: np.ndarray
+    path_len: np.ndarray
+    path_node: np.ndarray
+    cons_node: np.ndarray
+    msa: np.ndarray
+    best_score: np.ndarray
+    n_cigar: np.ndarray
+    cigar: np.ndarray
+    inband_cells: int
+
+    def consensus(self) -> str:
+        return "".join("ACGTN"[int(self.base[i])] for i in self.cons_node)
+
+
+class PoaResult:
+    def __init__(self, lib, handle):
+        self._lib, self._h = lib, handle
+
+    def __len__(self):
+        return int(self._lib.poa_b200_result_n_blocks(self._h))
+
+    def block(self, i: int) -> BlockView:
+        v = _BlockView()
+        _check(self._lib, self._lib.poa_b200_result_block(self._h, i, C.byref(v)))
+        if v.status != OK:
+            z = np.zeros(0, dtype=np.int32)
+            return BlockView(v.status, 0, v.n_seq, -1, -1, 0, z, z, z, z, z, z, z, z, z, z, z, z,
+                             np.zeros(0, np.uint8), z, z, np.zeros(0, np.uint64), 0)
+        n, s = v.n_node, v.n_seq
+        msa = _arr(v.msa, v.msa_rows * max(v.msa_len, 0), np.uint8)
+        cig = np.zeros(0, dtype=np.uint64)
+        if v.cigar_total > 0:
+            w = np.ctypeslib.as_array(C.cast(v.cigar, C.POINTER(C.c_uint32)), shape=(2 * int(v.cigar_total),)).copy()
+            cig = w[0::2].astype(np.uint64) | (w[1::2].astype(np.uint64) << np.uint64(32))
+        return BlockView(v.status, n, s, v.cons_len, v.msa_len, v.msa_rows,
+                         _arr(v.base, n), _arr(v.in_n, n), _arr(v.in_id, v.in_total), _arr(v.in_w, v.in_total),
+                         _arr(v.out_n, n), _arr(v.out_id, v.out_total), _arr(v.out_w, v.out_total),
+                         _arr(v.aln_n, n), _arr(v.aln_id, v.aln_total),
+                         _arr(v.path_len, s), _arr(v.path_node, v.path_total), _arr(v.cons_node, max(v.cons_len, 0)),
+                         msa, _arr(v.best_score, s), _arr(v.n_cigar, s), cig, int(v.inband_cells))
+
+    def stats(self) -> dict:
+        s = Stats()
+        _check(self._lib, self._lib.poa_b200_result_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def close(self):
+        if self._h:
+            self._lib.poa_b200_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+class DeviceBatch:
+    """A batch whose inputs are resident in HBM (staged API)."""
+
+    def __init__(self, lib, handle, keep):
+        self._lib, self._h, self._keep = lib, handle, keep
+
+    def launch(self, stream: int | None = None):
+        _check(self._lib, self._lib.poa_b200_batch_launch(self._h, C.c_void_p(stream or 0)))
+
+    def finish(self, stream: int | None = None):
+        _check(self._lib, self._lib.poa_b200_batch_finish(self._h, C.c_void_p(stream or 0)))
+
+    def download(self, stream: int | None = None, allow_block_errors=False) -> PoaResult:
+        r = C.c_void_p()
+        rc = self._lib.poa_b200_batch_download(self._h, C.c_void_p(stream or 0), C.byref(r))
+        _check(self._lib, rc, allow=(EBLOCK,) if allow_block_errors else ())
+        return PoaResult(self._lib, r)
+
+    def stats(self) -> dict:
+        s = Stats()
+        _check(self._lib, self._lib.poa_b200_batch_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def close(self):
+        if self._h:
+            self._lib.poa_b200_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class PoaEngine:
+    """One engine per GPU (one process per GPU in the multi-GPU driver)."""
+
+    def __init__(self, device: int = 0, warps_per_block: int = 0, ctas_per_sm: int = 0, emit_cigar: bool = False,
+                 slab_rows_factor: float = 0.0, device_mem_budget: int = 0):
+        self._h = None
+        self._lib = load_library()
+        opts = EngineOpts(warps_per_block, ctas_per_sm, int(emit_cigar), 0, slab_rows_factor, device_mem_budget)
+        h = C.c_void_p()
+        _check(self._lib, self._lib.poa_b200_engine_create(device, C.byref(opts), C.byref(h)))
+        self._h = h
+
+    def _args(self, batch):
+        bso = _c(batch.block_seq_off, np.int64); sl = _c(batch.seq_len, np.int32); so = _c(batch.seq_off, np.int64)
+        ba = _c(batch.bases, np.uint8); wt = _c(batch.weight, np.int32)
+        keep = (bso, sl, so, ba, wt)
+        return keep, (int(bso.shape[0] - 1), bso.ctypes.data, sl.ctypes.data, so.ctypes.data, ba.ctypes.data, wt.ctypes.data)
+
+    def run_batch(self, batch, params: PoaParams, allow_block_errors=False) -> PoaResult:
+        """Host buffers in, host result out: H2D, kernels, D2H (poa_b200_run_batch)."""
+        keep, a = self._args(batch)
+        r = C.c_void_p()
+        rc = self._lib.poa_b200_run_batch(self._h, C.byref(params), *a, C.byref(r))
+        _check(self._lib, rc, allow=(EBLOCK,) if allow_block_errors else ())
+        del keep
+        return PoaResult(self._lib, r)
+
+    def upload(self, batch, params: PoaParams) -> DeviceBatch:
+        keep, a = self._args(batch)
+        h = C.c_void_p()
+        _check(self._lib, self._lib.poa_b200_batch_upload(self._h, C.byref(params), *a, C.byref(h)))
+        return DeviceBatch(self._lib, h, keep)
+
+    def poa_block(self, seqs, weights, params: PoaParams) -> PoaResult:
+        """abpoa_poa-shaped convenience call for one block (poa_b200_poa_block)."""
+        seqs = [_c(s, np.uint8) for s in seqs]
+        n = len(seqs)
+        ptrs = (C.c_void_p * max(n, 1))(*[s.ctypes.data for s in seqs])
+        lens = _c([s.shape[0] for s in seqs], np.int32); wts = _c(weights, np.int32)
+        r = C.c_void_p()
+        _check(self._lib, self._lib.poa_b200_poa_block(self._h, C.byref(params), n, ptrs, lens.ctypes.data, wts.ctypes.data, C.byref(r)))
+        return PoaResult(self._lib, r)
+
+    def close(self):
+        if self._h:
+            self._lib.poa_b200_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()

@@ -1,0 +1,81 @@
+// TEST INFRASTRUCTURE ONLY -- debug harness, never built by __graft_entry__.build(), never shipped,
+// never loaded by the smoothxg_b200 package.
+//
+// Compiles smoothxg_b200/csrc/poa_core.cuh as plain C++ with -DPOA_HOST_EMU (one emulated thread,
+// warp size 1) and runs poa_block<1>() for one block on the host, so that the serial device logic
+// (vector indexing, band bookkeeping, traceback, fusion, topological sort, output packing) can be
+// checked against the oracle on a machine without a GPU.  The warp/block collectives degenerate to
+// identities here; they are only exercised by the -m gpu tests.
+//
+// Output: the canonical dump of oracle/poa_dump.h, so tests compare with np.array_equal.
+#define POA_HOST_EMU
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../smoothxg_b200/csrc/poa_host.hpp"
+#include "../../oracle/poa_dump.h"
+
+namespace poa {
+int set_err(int code, const std::string &msg) { fprintf(stderr, "[emu] %s\n", msg.c_str()); return code; }
+}
+using namespace poa;
+
+extern "C" void emu_free(void *p) { free(p); }
+
+extern "C" int32_t *emu_poa_block(const pd_params_t *pp, int n_seq, const int32_t *seq_len, const uint8_t *bases,
+                                  const int32_t *weight, int instrument, int64_t *n_out) {
+    *n_out = 0;
+    poa_b200_params_t p;
+    static_assert(sizeof(pd_params_t) == sizeof(poa_b200_params_t), "param structs must match");
+    memcpy(&p, pp, sizeof(p));
+    if (check_params(p)) return nullptr;
+    poa_b200_engine_opts_t opts; memset(&opts, 0, sizeof(opts));
+    opts.emit_cigar = instrument ? 1 : 0;
+    DevParams dp; build_params(p, opts, dp);
+    long long tot = 0, max_len = 1;
+    for (int i = 0; i < n_seq; ++i) { tot += seq_len[i]; if (seq_len[i] > max_len) max_len = seq_len[i]; }
+    const char *lvl = getenv("POA_EMU_TIGHT");
+    long long nmax = std::max<long long>(std::max<long long>(tot + 2, n_seq + 2), 1024);
+    long long slab = nmax * ((max_len + 1) / 8 + 2) * 5 * 32;
+    long long growth = 8 * (tot + n_seq) + 64;
+    if (lvl) { nmax = std::max<long long>(atoll(lvl), max_len + 2); slab = slab / 64; growth = 64; }
+    WsLayout L;
+    make_layout(L, nmax, std::max<long long>(tot, 1), max_len, std::max(n_seq, 1), growth, slab, dp.emit_cigar);
+    std::vector<char> ws((size_t)L.stride + 256);
+    char *wsp = (char *)(((uintptr_t)ws.data() + 255) & ~(uintptr_t)255);
+    std::vector<long long> bso{0, n_seq}, so((size_t)n_seq + 1, 0);
+    for (int i = 0; i < n_seq; ++i) so[(size_t)i + 1] = so[(size_t)i] + seq_len[i];
+    int order0 = 0;
+    DevBatch B; B.block_seq_off = bso.data(); B.seq_len = seq_len; B.seq_off = so.data(); B.bases = bases; B.weight = weight; B.order = &order0; B.n_order = 1;
+    std::vector<int> hdr(HDR_WORDS, -1);
+    long long cap = 16 * nmax + tot + 64 + (long long)(n_seq + 1) * nmax / 4 + 2 * (tot + (long long)n_seq * (nmax + max_len + 8));
+    std::vector<int> arena((size_t)cap);
+    unsigned long long used = 0, phase[PH_N] = {0};
+    int counter = 0;
+    DevOut O; O.hdr = hdr.data(); O.arena = arena.data(); O.arena_used = &used; O.arena_cap = (unsigned long long)cap; O.phase = phase; O.counter = &counter;
+    Shared sh; memset(&sh, 0, sizeof(sh));
+    ws_bind(sh.ws, wsp, L);
+    poa_block<1>(sh, dp, B, L, O, 0);
+    if (hdr[H_STATUS] != ST_OK) { fprintf(stderr, "[emu] block status %d\n", hdr[H_STATUS]); *n_out = -hdr[H_STATUS]; return nullptr; }
+    // wire format -> canonical dump
+    const int n = hdr[H_N_NODE], ns = hdr[H_N_SEQ];
+    const long long in_tot = hdr[H_IN_TOT], out_tot = hdr[H_OUT_TOT], aln_tot = hdr[H_ALN_TOT], path_tot = hdr[H_PATH_TOT], cig_tot = hdr[H_CIG_TOT];
+    const int cons_len = hdr[H_CONS_LEN], msa_len = hdr[H_MSA_LEN], msa_rows = hdr[H_MSA_ROWS];
+    const int *o = arena.data() + ((unsigned long long)(unsigned)hdr[H_OFF_LO] | ((unsigned long long)(unsigned)hdr[H_OFF_HI] << 32));
+    long long body = 4LL * n + 2 * in_tot + 2 * out_tot + aln_tot + ns + path_tot + (cons_len > 0 ? cons_len : 0);
+    const int *tail = o + body;  // best, ncig, cig
+    const uint8_t *msa = (const uint8_t *)(tail + 2LL * ns + 2 * cig_tot);
+    pd_buf_t b = {0, 0, 0};
+    for (int i = 0; i < PD_HEADER_LEN; ++i) pd_push(&b, 0);
+    for (long long i = 0; i < body; ++i) pd_push(&b, o[i]);
+    for (long long i = 0; i < (long long)msa_rows * (msa_len > 0 ? msa_len : 0); ++i) pd_push(&b, msa[i]);
+    for (long long i = 0; i < 2LL * ns + 2 * cig_tot; ++i) pd_push(&b, tail[i]);
+    b.d[PD_MAGIC] = POA_DUMP_MAGIC; b.d[PD_N_NODE] = n; b.d[PD_N_SEQ] = ns;
+    b.d[PD_CONS_LEN] = cons_len; b.d[PD_MSA_LEN] = msa_len; b.d[PD_MSA_ROWS] = msa_rows;
+    b.d[PD_N_IN_TOT] = (int)in_tot; b.d[PD_N_OUT_TOT] = (int)out_tot; b.d[PD_N_ALN_TOT] = (int)aln_tot;
+    b.d[PD_PATH_TOT] = (int)path_tot; b.d[PD_CIGAR_TOT] = (int)cig_tot;
+    b.d[PD_INBAND_LO] = hdr[H_INBAND_LO]; b.d[PD_INBAND_HI] = hdr[H_INBAND_HI];
+    *n_out = b.n;
+    return b.d;
+}
