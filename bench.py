@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- POA hot-path benchmark (BASELINE.json metric: POA DP Gcells/s and blocks/s).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3            # our arm, one B200
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                      # unmodified vendored abPOA on the host cores
+
+Workload (config.workload): BASELINE.json configs[2], the configuration the north star quotes the
+target on -- synthetic 10 000 blocks x 32 sequences x 2 kb, 2 % divergence, global alignment with
+abPOA's adaptive band (wb=311, wf=0.03), convex gaps 1,4,6,2,26,1 -- per GPU (weak scaling: every
+rank aligns its own 10 000-block shard, generated from a rank-specific seed).  A "step" is one pass
+of the whole per-block loop (DP fill, traceback, graph fusion, topological sort, consensus) over the
+shard.
+
+  value  = in-band DP cells of all ranks / max-over-ranks device time, inputs resident in HBM
+           (cells counted by the kernel; identical to the oracle's band, see tests).
+  e2e    = the same through the C ABI call poa_b200_run_batch(): pinned host buffers in, host result
+           out, H2D + kernels + D2H inside the timed region.
+  roofline = algorithmic HBM bytes (sizeof(score) x (5 + 3 p-bar) per in-band cell) /
+           kernel time, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline = oracle/_ref (unmodified abPOA, AVX-512/AVX2) on all host cores over a bounded
+           sample of the same shard (rank 0, N=1 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (n_blocks, n_seqs, length, divergence)
+    "10000x32x2kb": (10000, 32, 2000, 0.02),
+    "1000x16x1kb": (1000, 16, 1000, 0.02),
+}
+METRIC = "poa_dp_inband_gcells_per_s"
+UNIT = "Gcells/s"
+
+
+def gen_batch(workload: str, seed: int, n_blocks: int | None = None):
+    from smoothxg_b200 import synth
+    nb, ns, L, d = WORKLOADS[workload]
+    if n_blocks is not None:
+        nb = n_blocks
+    cache = os.path.join("/tmp", f"poa_bench_{workload}_{nb}_{seed}.npz")
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return synth.PoaBatch(z["bso"], z["sl"], z["so"], z["ba"], z["wt"])
+    b = synth.make_batch(n_blocks=nb, n_seqs=ns, length=L, divergence=d, seed=seed)
+    try:
+        np.savez(cache, bso=b.block_seq_off, sl=b.seq_len, so=b.seq_off, ba=b.bases, wt=b.weight)
+    except OSError:
+        pass
+    return b
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_per_launch(workload: str):
+    """DRAM bytes per launch of the POA kernel from the committed ncu --set full capture, if one matches."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            t = json.load(f)
+        if t.get("workload") == workload:
+            return t.get("dram_bytes_per_launch")
+    return None
+
+
+def cpu_reference(batch, params_kw, n_sample: int, threads: int):
+    """Unmodified vendored abPOA (oracle/_ref) over the first n_sample blocks, OpenMP dynamic loop over
+    blocks like reference src/smooth.cpp:1931.  Returns (seconds, kind, simd)."""
+    from oracle.oracle import RefAbpoa, Oracle, make_params, ref_available
+    sub = batch.select(range(min(n_sample, batch.n_blocks)))
+    p = make_params(**params_kw)
+    if ref_available():
+        ref = RefAbpoa()
+        ref.batch_timed(p, batch.select(range(min(threads, sub.n_blocks))), n_threads=threads)  # warm-up pass
+        secs = ref.batch_timed(p, sub, n_threads=threads)
+        return sub, secs, "reference", ref.simd
+    ora = Oracle()  # scalar port, single thread
+    t0 = time.perf_counter()
+    ora.poa_batch(p, sub, instrument=False)
+    return sub, time.perf_counter() - t0, "port", "scalar"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="10000x32x2kb", choices=sorted(WORKLOADS))
+    ap.add_argument("--blocks", type=int, default=None, help="override blocks per GPU (debug; invalidates the headline)")
+    ap.add_argument("--warps", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="blocks in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    nb, ns, L, div = WORKLOADS[args.workload]
+    if args.blocks:
+        nb = args.blocks
+    params_kw = dict(local=False, banded=True, out_cons=True, out_msa=False)
+    config = {"workload": f"synthetic {nb} blocks x {ns} seqs x {L} bp per GPU, {div:.0%} divergence, global, adaptive band wb=311 wf=0.03, "
+                          f"convex gaps 1,4,6,2,26,1 (BASELINE.json configs[2])" if args.workload == "10000x32x2kb" else
+                          f"synthetic {nb} blocks x {ns} seqs x {L} bp per GPU (BASELINE.json configs[1])",
+              "blocks_per_gpu": nb, "seqs_per_block": ns, "seq_len": L, "divergence": div,
+              "l2": "inputs + per-block workspaces are tens of GB per step, far larger than the 126 MB L2 (no flush needed)",
+              "sharding": "static, one 10k-block shard per rank, no data-path collective"}
+
+    # ---------------------------------------------------------------- reference arm (CPU abPOA)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        batch = gen_batch(args.workload, seed=1000, n_blocks=args.blocks)
+        n_sample = args.cpu_sample or max(threads, min(batch.n_blocks, 8 * threads))
+        from oracle.oracle import Oracle, make_params
+        times = []
+        sub = None
+        kind = simd = None
+        for it in range(args.warmup + args.steps):
+            sub, secs, kind, simd = cpu_reference(batch, params_kw, n_sample, threads)
+            if it >= args.warmup:
+                times.append(secs)
+        # in-band cells of the sample from the oracle restatement (identical to abPOA's band, tests/test_oracle_vs_ref.py)
+        ora = Oracle()
+        cells = sum(d.inband_cells for d in ora.poa_batch(make_params(**params_kw), sub.select(range(min(sub.n_blocks, 2 * threads)))))
+        cells = cells * sub.n_blocks / min(sub.n_blocks, 2 * threads)
+        t = sum(times) / len(times)
+        val = cells / t / 1e9
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int16", "data": "synthetic", "config": config, "blocks_per_s": sub.n_blocks / t,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
+                                 "sample": f"first {sub.n_blocks} blocks of the shard per step, abPOA v1.5.4 {simd}, OpenMP dynamic over blocks, "
+                                           f"cells extrapolated from the oracle's band on {min(sub.n_blocks, 2 * threads)} blocks"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    import torch.distributed as dist
+    from smoothxg_b200 import engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the POA engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    batch = gen_batch(args.workload, seed=1000 + rank, n_blocks=args.blocks)
+    eng = engine.PoaEngine(device=local_rank, warps_per_block=args.warps, ctas_per_sm=args.ctas_per_sm)
+    params = engine.make_params(**params_kw)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # --- device-resident leg
+    dev = eng.upload(batch, params)
+    for _ in range(args.warmup):
+        dev.launch(stream); dev.finish(stream)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, launches = 0.0, 0
+    e0.record()
+    for _ in range(args.steps):
+        dev.launch(stream); dev.finish(stream)
+        st = dev.stats()
+        kernel_ms += st["kernel_ms"]; launches += st["kernel_launches"]
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    st = dev.stats()
+    cells, edge_rows = st["inband_cells"], st["edge_row_cells"]
+    dev.close()
+
+    # --- end-to-end leg through poa_b200_run_batch with pinned host inputs
+    e2e_ms = None
+    last = None
+    h2d = d2h = 0
+    if not args.no_e2e:
+        import copy
+        pinned = copy.copy(batch)
+        keep = []
+        for name in ("block_seq_off", "seq_len", "seq_off", "bases", "weight"):
+            a = getattr(batch, name)
+            t = torch.from_numpy(a).pin_memory()
+            keep.append(t)
+            setattr(pinned, name, t.numpy())
+        r = eng.run_batch(pinned, params); r.close()  # warm the pinned/device pools
+        barrier()
+        t0 = time.perf_counter()
+        last = None
+        for _ in range(args.steps):
+            if last is not None:
+                last.close()
+            r = eng.run_batch(pinned, params)
+            s2 = r.stats(); h2d, d2h = s2["h2d_bytes"], s2["d2h_bytes"]
+            chk = r.block(0).n_node  # the step's result is read on the host
+            last = r
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        assert chk > 2
+
+    # --- max over ranks, sums over ranks
+    tot_cells, tot_blocks = float(cells), float(batch.n_blocks)
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms or 0.0, kernel_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_max, kernel_ms = t.tolist()
+        e2e_ms = e2e_max if e2e_ms is not None else None
+        c = torch.tensor([tot_cells, tot_blocks, float(edge_rows), float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        tot_cells, tot_blocks, edge_rows_all, launches_all = c.tolist()
+    else:
+        edge_rows_all, launches_all = float(edge_rows), float(launches)
+
+    if rank == 0:
+        K = args.steps
+        sec = ms / 1e3
+        value = tot_cells * K / sec / 1e9
+        pbar = edge_rows_all / max(tot_cells, 1.0)
+        bytes_per_cell = 2.0 * (5.0 + 3.0 * pbar)  # int16 convex: write 5 planes, read 3 per predecessor edge
+        peak, peak_src = peaks()
+        per_launch_s = (kernel_ms / 1e3) / max(K, 1)  # one POA kernel launch per step (plus rare retries), this rank
+        achieved = (float(cells) * bytes_per_cell) / per_launch_s / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int16", "data": "synthetic", "config": config,
+                "blocks_per_s": tot_blocks * K / sec, "inband_cells_per_step": tot_cells, "p_bar": pbar,
+                "clocks": clocks, "gpu_launches": int(launches_all),
+                "engine": {"n_ctas": st["n_ctas"], "warps_per_block": st["warps_per_block"], "workspace_gb": st["workspace_bytes"] / 1e9,
+                           "retried_blocks": st["retried_blocks"], "phase_cycles": st["phase_cycles"]},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic_per_launch(args.workload), "peak_source": peak_src,
+                             "kernel": "poa_b200_block_kernel", "algorithmic_bytes_per_cell": bytes_per_cell,
+                             "kernel_ms_per_launch": per_launch_s * 1e3}}
+        if e2e_ms is not None:
+            line["e2e"] = {"value": tot_cells * K / (e2e_ms / 1e3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                           "blocks_per_s": tot_blocks * K / (e2e_ms / 1e3), "ms_per_step": e2e_ms / K}
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            n_sample = args.cpu_sample or max(threads, min(batch.n_blocks, 12 * threads))
+            sub, secs, kind, simd = cpu_reference(batch, params_kw, n_sample, threads)
+            if last is not None:
+                sub_cells = float(sum(last.block(i).inband_cells for i in range(sub.n_blocks)))
+            else:
+                sub_cells = float(cells) * sub.n_blocks / batch.n_blocks
+            line["cpu_baseline"] = {"value": sub_cells / secs / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "blocks_per_s": sub.n_blocks / secs,
+                                    "sample": f"first {sub.n_blocks} blocks of the shard, abPOA v1.5.4 {simd} via oracle/_ref, OpenMP dynamic over blocks, {secs:.1f} s"}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

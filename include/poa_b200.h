@@ -107,6 +107,7 @@ typedef struct poa_b200_stats {
     double  kernel_ms;       /* device time of the POA kernel(s) of the last launch (CUDA events on the launch stream) */
     double  h2d_ms, d2h_ms;
     int64_t inband_cells;    /* summed over blocks */
+    int64_t edge_row_cells;  /* sum over evaluated rows of (predecessor count x band width): p-bar = this / inband_cells */
     int64_t h2d_bytes, d2h_bytes;
     int32_t kernel_launches; /* POA kernel launches, retries included */
     int32_t retried_blocks;

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -51,7 +52,67 @@ namespace {
             return set_err(POA_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
     } while (0)
 
+// Pinned host buffers are expensive to create (page-locking), so finished results hand theirs back
+// to a pool shared with the engine instead of freeing them.
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<std::pair<void *, size_t>> free_list;
+    void *take(size_t bytes, size_t *cap) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            size_t best = free_list.size();
+            for (size_t i = 0; i < free_list.size(); ++i)
+                if (free_list[i].second >= bytes && (best == free_list.size() || free_list[i].second < free_list[best].second)) best = i;
+            if (best != free_list.size()) {
+                void *p = free_list[best].first; *cap = free_list[best].second;
+                free_list.erase(free_list.begin() + (long)best);
+                return p;
+            }
+        }
+        void *p = nullptr;
+        size_t want = bytes + bytes / 8 + 4096;
+        if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        *cap = want;
+        return p;
+    }
+    void give(void *p, size_t cap) { std::lock_guard<std::mutex> lk(mu); free_list.emplace_back(p, cap); }
+    ~PinnedPool() { for (auto &e : free_list) cudaFreeHost(e.first); }
+};
+
+// Same idea for device memory: cudaMalloc/cudaFree of tens of GB per batch would sit inside every
+// end-to-end call, so workspaces and arenas are recycled through the engine.
+struct DevicePool {
+    std::mutex mu;
+    std::vector<std::pair<void *, size_t>> free_list;
+    void *take(size_t bytes, size_t *cap) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            size_t best = free_list.size();
+            for (size_t i = 0; i < free_list.size(); ++i)
+                if (free_list[i].second >= bytes && (best == free_list.size() || free_list[i].second < free_list[best].second)) best = i;
+            if (best != free_list.size() && free_list[best].second <= 2 * bytes + (64u << 20)) {
+                void *p = free_list[best].first; *cap = free_list[best].second;
+                free_list.erase(free_list.begin() + (long)best);
+                return p;
+            }
+        }
+        void *p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            trim();
+            if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        }
+        *cap = bytes;
+        return p;
+    }
+    void give(void *p, size_t cap) { if (p) { std::lock_guard<std::mutex> lk(mu); free_list.emplace_back(p, cap); } }
+    void trim() { std::lock_guard<std::mutex> lk(mu); for (auto &e : free_list) cudaFree(e.first); free_list.clear(); }
+    size_t pooled_bytes() { std::lock_guard<std::mutex> lk(mu); size_t s = 0; for (auto &e : free_list) s += e.second; return s; }
+    ~DevicePool() { for (auto &e : free_list) cudaFree(e.first); }
+};
+
 struct Arena {
+    size_t cap_bytes = 0;
     int *d = nullptr;
     unsigned long long cap = 0;   // words
     unsigned long long used = 0;  // words, filled after the launch
@@ -66,6 +127,8 @@ struct poa_b200_engine {
     poa_b200_engine_opts_t opts{};
     std::mutex mu;
     size_t total_mem = 0;
+    std::shared_ptr<PinnedPool> pinned = std::make_shared<PinnedPool>();
+    DevicePool dev_pool;
 };
 
 struct poa_b200_result {
@@ -73,6 +136,8 @@ struct poa_b200_result {
     std::vector<int> hdr;                 // n_blocks * HDR_WORDS
     std::vector<int> arena_of;            // per block: which arena holds its body
     std::vector<int *> arenas;            // pinned host copies
+    std::vector<size_t> arena_caps;       // bytes, for the pool
+    std::shared_ptr<PinnedPool> pinned;
     std::vector<unsigned long long> arena_words;
     poa_b200_stats_t stats{};
     int emit_cigar = 0;
@@ -129,8 +194,10 @@ cudaError_t launch_kernel(int nw, int n_ctas, cudaStream_t st, const DevParams &
 void free_batch_device(poa_b200_batch *b) {
     cudaFree(b->d_block_seq_off); cudaFree(b->d_seq_off); cudaFree(b->d_seq_len); cudaFree(b->d_weight);
     cudaFree(b->d_order); cudaFree(b->d_bases); cudaFree(b->d_hdr); cudaFree(b->d_counter);
-    cudaFree(b->d_arena_used); cudaFree(b->d_phase); cudaFree(b->d_ws);
-    for (auto &a : b->arenas) cudaFree(a.d);
+    cudaFree(b->d_arena_used); cudaFree(b->d_phase);
+    b->eng->dev_pool.give(b->d_ws, (size_t)b->ws_bytes); b->d_ws = nullptr;
+    for (auto &a : b->arenas) b->eng->dev_pool.give(a.d, a.cap_bytes);
+    b->arenas.clear();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
 }
@@ -192,14 +259,16 @@ int run_launch(poa_b200_batch *b, const std::vector<int> &blocks, int level, cud
     long long n_ctas = std::min<long long>((long long)blocks.size(), (long long)eng->n_sm * per_sm);
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    long long budget = eng->opts.device_mem_budget > 0 ? eng->opts.device_mem_budget : (long long)((double)(free_b + (size_t)b->ws_bytes) * 0.70);
+    long long budget = eng->opts.device_mem_budget > 0 ? eng->opts.device_mem_budget
+                     : (long long)((double)(free_b + (size_t)b->ws_bytes + eng->dev_pool.pooled_bytes()) * 0.70);
     n_ctas = std::max<long long>(1, std::min<long long>(n_ctas, budget / std::max<long long>(L.stride, 1)));
     const long long need = n_ctas * L.stride;
     if (need > b->ws_bytes) {
-        if (b->d_ws) { CU(cudaFree(b->d_ws)); b->d_ws = nullptr; b->ws_bytes = 0; }
-        cudaError_t e = cudaMalloc(&b->d_ws, (size_t)need);
-        if (e != cudaSuccess) return set_err(POA_B200_ENOMEM, std::string("workspace cudaMalloc failed: ") + cudaGetErrorString(e));
-        b->ws_bytes = need;
+        if (b->d_ws) { eng->dev_pool.give(b->d_ws, (size_t)b->ws_bytes); b->d_ws = nullptr; b->ws_bytes = 0; }
+        size_t cap = 0;
+        b->d_ws = (char *)eng->dev_pool.take((size_t)need, &cap);
+        if (!b->d_ws) return set_err(POA_B200_ENOMEM, "workspace cudaMalloc failed");
+        b->ws_bytes = (long long)cap;
     }
     b->layout = L; b->n_ctas = (int)n_ctas; b->nw = nw;
     // arena for this launch
@@ -215,10 +284,8 @@ int run_launch(poa_b200_batch *b, const std::vector<int> &blocks, int level, cud
     est_words = est_words + est_words / 4 + 1024;
     Arena ar;
     ar.cap = (unsigned long long)est_words;
-    {
-        cudaError_t e = cudaMalloc(&ar.d, (size_t)ar.cap * 4);
-        if (e != cudaSuccess) return set_err(POA_B200_ENOMEM, std::string("arena cudaMalloc failed: ") + cudaGetErrorString(e));
-    }
+    ar.d = (int *)eng->dev_pool.take((size_t)ar.cap * 4, &ar.cap_bytes);
+    if (!ar.d) return set_err(POA_B200_ENOMEM, "arena cudaMalloc failed");
     b->arenas.push_back(ar);
     // order: most expensive first
     std::vector<int> order(blocks);
@@ -297,12 +364,14 @@ int finish_locked(poa_b200_batch *b, cudaStream_t st) {
     unsigned long long ph[PH_N];
     CU(cudaMemcpy(ph, b->d_phase, sizeof(ph), cudaMemcpyDeviceToHost));
     for (int k = 0; k < 8; ++k) b->stats.phase_cycles[k] = (int64_t)ph[k];
-    long long cells = 0;
+    long long cells = 0, edges = 0;
     for (int64_t i = 0; i < b->n_blocks; ++i) {
         const int *h = &b->h_hdr[(size_t)i * HDR_WORDS];
-        if (h[H_STATUS] == ST_OK) cells += (long long)((unsigned long long)(unsigned)h[H_INBAND_LO] | ((unsigned long long)(unsigned)h[H_INBAND_HI] << 32));
+        if (h[H_STATUS] != ST_OK) continue;
+        cells += (long long)((unsigned long long)(unsigned)h[H_INBAND_LO] | ((unsigned long long)(unsigned)h[H_INBAND_HI] << 32));
+        edges += (long long)((unsigned long long)(unsigned)h[H_EDGE_LO] | ((unsigned long long)(unsigned)h[H_EDGE_HI] << 32));
     }
-    b->stats.inband_cells = cells;
+    b->stats.inband_cells = cells; b->stats.edge_row_cells = edges;
     b->finished = true;
     return POA_B200_OK;
 }
@@ -439,7 +508,7 @@ int poa_b200_batch_launch(poa_b200_batch_t *b, void *stream) {
     CU(cudaSetDevice(b->eng->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : b->eng->stream;
     // a re-launch of the same batch recomputes everything (used by benchmarks)
-    for (auto &a : b->arenas) cudaFree(a.d);
+    for (auto &a : b->arenas) b->eng->dev_pool.give(a.d, a.cap_bytes);
     b->arenas.clear();
     std::fill(b->arena_of.begin(), b->arena_of.end(), -1);
     b->stats.kernel_launches = 0; b->stats.retried_blocks = 0;
@@ -471,17 +540,17 @@ int poa_b200_batch_download(poa_b200_batch_t *b, void *stream, poa_b200_result_t
     if (rc) return rc;
     poa_b200_result *r = new (std::nothrow) poa_b200_result();
     if (!r) return set_err(POA_B200_ENOMEM, "result alloc");
+    r->pinned = b->eng->pinned;
     r->n_blocks = b->n_blocks; r->hdr = b->h_hdr; r->arena_of = b->arena_of; r->emit_cigar = b->dp.emit_cigar;
     cudaEvent_t d0, d1;
     CU(cudaEventCreate(&d0)); CU(cudaEventCreate(&d1));
     CU(cudaEventRecord(d0, st));
     int64_t bytes = (int64_t)b->h_hdr.size() * 4;
     for (auto &a : b->arenas) {
-        int *h = nullptr;
-        size_t nbytes = (size_t)std::max<unsigned long long>(a.used, 1) * 4;
-        cudaError_t e = cudaMallocHost(&h, nbytes);
-        if (e != cudaSuccess) { poa_b200_result_free(r); return set_err(POA_B200_ENOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
-        r->arenas.push_back(h); r->arena_words.push_back(a.used);
+        size_t nbytes = (size_t)std::max<unsigned long long>(a.used, 1) * 4, cap = 0;
+        int *h = (int *)r->pinned->take(nbytes, &cap);
+        if (!h) { poa_b200_result_free(r); return set_err(POA_B200_ENOMEM, "cudaMallocHost failed for the result buffer"); }
+        r->arenas.push_back(h); r->arena_caps.push_back(cap); r->arena_words.push_back(a.used);
         if (a.used) CU(cudaMemcpyAsync(h, a.d, (size_t)a.used * 4, cudaMemcpyDeviceToHost, st));
         bytes += (int64_t)a.used * 4;
     }
@@ -577,7 +646,7 @@ int poa_b200_result_stats(const poa_b200_result_t *res, poa_b200_stats_t *s) {
 
 void poa_b200_result_free(poa_b200_result_t *res) {
     if (!res) return;
-    for (int *p : res->arenas) cudaFreeHost(p);
+    for (size_t i = 0; i < res->arenas.size(); ++i) res->pinned->give(res->arenas[i], res->arena_caps[i]);
     delete res;
 }
 

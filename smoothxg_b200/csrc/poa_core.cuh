@@ -66,7 +66,7 @@ POA_D int4 poa_make_int4(int x, int y, int z, int w) { return make_int4(x, y, z,
 namespace poa {
 
 constexpr int SRC_ID = 0, SINK_ID = 1;
-constexpr int HDR_WORDS = 16;  // per-block result header, int32 words
+constexpr int HDR_WORDS = 20;  // per-block result header, int32 words
 constexpr int NEG_INF32 = INT_MIN;
 constexpr int MAX_WARPS = 8;
 
@@ -74,7 +74,7 @@ constexpr int MAX_WARPS = 8;
 enum { ST_OK = 0, ST_ESLAB = 1, ST_EARENA = 2, ST_EINTERNAL = 3, ST_EUNSUP = 4 };
 // result header slots
 enum { H_STATUS = 0, H_N_NODE, H_N_SEQ, H_CONS_LEN, H_MSA_LEN, H_MSA_ROWS, H_IN_TOT, H_OUT_TOT, H_ALN_TOT,
-       H_PATH_TOT, H_CIG_TOT, H_OFF_LO, H_OFF_HI, H_INBAND_LO, H_INBAND_HI, H_WORDS };
+       H_PATH_TOT, H_CIG_TOT, H_OFF_LO, H_OFF_HI, H_INBAND_LO, H_INBAND_HI, H_EDGE_LO, H_EDGE_HI, H_WORDS };
 // phase cycle counters
 enum { PH_ROWS = 0, PH_FILL, PH_BT, PH_FUSE, PH_TOPO, PH_FINAL, PH_TOTAL, PH_SPARE, PH_N };
 
@@ -148,7 +148,7 @@ struct Shared {
     int n_cigar;       // cigar words of the current alignment
     int cig_base;      // where the current alignment's cigar starts in ws.cig
     int best_score, best_i, best_j;
-    long long inband;
+    long long inband, edge_rows;
     int scan_x[2][2][MAX_WARPS];
     int red_x[2][3][MAX_WARPS];
     int bcast[4];
@@ -422,7 +422,7 @@ POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, lon
     const int e1 = P.e1, e2 = P.e2, oe1 = P.oe1, oe2 = P.oe2;
     S *slab = reinterpret_cast<S *>(w.slab);
     long long used = 0;  // vectors
-    long long inband = 0;
+    long long inband = 0, edge_rows = 0;
     int xbuf = 0;        // parity of the cross-warp exchange buffers
     (void)lane; (void)wid;
 
@@ -487,6 +487,7 @@ POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, lon
         const long long roff = used;
         used += 5LL * nv;
         inband += end - beg + 1;
+        edge_rows += (long long)ri.y * (end - beg + 1);
 
         int carry1 = f0_1 + e1 * beg, carry2 = f0_2 + e2 * beg;  // G[beg] of the two gap pieces
         int mx = inf_min, left = -1, right = -1;
@@ -619,7 +620,7 @@ POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, lon
             }
         }
         sh.best_score = best_score; sh.best_i = best_i; sh.best_j = best_j;
-        sh.inband += inband;
+        sh.inband += inband; sh.edge_rows += edge_rows;
     }
     sync_block<NW>();
 }
@@ -911,7 +912,7 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
     long long t_start = poa_clock();
 
     if (tid == 0) {
-        sh.n_node = 0; sh.err = ST_OK; sh.inband = 0; sh.cig_base = 0; sh.n_cigar = 0;
+        sh.n_node = 0; sh.err = ST_OK; sh.inband = 0; sh.edge_rows = 0; sh.cig_base = 0; sh.n_cigar = 0;
         sh.nmax = L.nmax; sh.pool_cap = L.pool_cap;
         sh.pool_used = 4 * L.nmax;
         add_node(sh, 0); add_node(sh, 0);
@@ -1072,6 +1073,7 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
                 hdr[H_IN_TOT] = in_tot; hdr[H_OUT_TOT] = out_tot; hdr[H_ALN_TOT] = aln_tot; hdr[H_PATH_TOT] = (int)path_tot; hdr[H_CIG_TOT] = cig_tot;
                 hdr[H_OFF_LO] = sh.bcast[0]; hdr[H_OFF_HI] = sh.bcast[1];
                 hdr[H_INBAND_LO] = (int)(unsigned)(sh.inband & 0xffffffffll); hdr[H_INBAND_HI] = (int)(unsigned)((unsigned long long)sh.inband >> 32);
+                hdr[H_EDGE_LO] = (int)(unsigned)(sh.edge_rows & 0xffffffffll); hdr[H_EDGE_HI] = (int)(unsigned)((unsigned long long)sh.edge_rows >> 32);
             }
         }
     }

@@ -68,7 +68,7 @@ class _BlockView(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
-                ("inband_cells", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("inband_cells", C.c_int64), ("edge_row_cells", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("kernel_launches", C.c_int32), ("retried_blocks", C.c_int32), ("n_ctas", C.c_int32),
                 ("warps_per_block", C.c_int32), ("workspace_bytes", C.c_int64), ("phase_cycles", C.c_int64 * 8)]
 

@@ -76,6 +76,7 @@ extern "C" int32_t *emu_poa_block(const pd_params_t *pp, int n_seq, const int32_
     b.d[PD_N_IN_TOT] = (int)in_tot; b.d[PD_N_OUT_TOT] = (int)out_tot; b.d[PD_N_ALN_TOT] = (int)aln_tot;
     b.d[PD_PATH_TOT] = (int)path_tot; b.d[PD_CIGAR_TOT] = (int)cig_tot;
     b.d[PD_INBAND_LO] = hdr[H_INBAND_LO]; b.d[PD_INBAND_HI] = hdr[H_INBAND_HI];
+    b.d[PD_EDGE_ROWS_LO] = hdr[H_EDGE_LO]; b.d[PD_EDGE_ROWS_HI] = hdr[H_EDGE_HI];
     *n_out = b.n;
     return b.d;
 }
