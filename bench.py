@@ -170,7 +170,7 @@ def main():
             return
         threads = os.cpu_count() or 1
         batch = gen_batch(args.workload, seed=1000, n_blocks=args.blocks)
-        n_sample = args.cpu_sample or max(threads, min(batch.n_blocks, 8 * threads))
+        n_sample = args.cpu_sample or max(threads, min(batch.n_blocks, 32 * threads))
         from oracle.oracle import Oracle, make_params
         times = []
         sub = None
@@ -303,7 +303,7 @@ def main():
                            "blocks_per_s": tot_blocks * K / (e2e_ms / 1e3), "ms_per_step": e2e_ms / K}
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            n_sample = args.cpu_sample or max(threads, min(batch.n_blocks, 12 * threads))
+            n_sample = args.cpu_sample or max(threads, min(batch.n_blocks, 64 * threads))
             sub, secs, kind, simd = cpu_reference(batch, params_kw, n_sample, threads)
             if last is not None:
                 sub_cells = float(sum(last.block(i).inband_cells for i in range(sub.n_blocks)))

@@ -36,6 +36,7 @@ extern "C" {
 #endif
 
 #define POA_B200_ABI_VERSION 1
+#define POA_B200_HDR_WORDS 20
 
 /* return / per-block status codes */
 enum {
@@ -148,6 +149,16 @@ int  poa_b200_batch_launch(poa_b200_batch_t *batch, void *stream);
 int  poa_b200_batch_download(poa_b200_batch_t *batch, void *stream, poa_b200_result_t **result);
 /* Wait for the launch and re-run overflowed blocks, results stay on the device (kernel-only timing). */
 int  poa_b200_batch_finish(poa_b200_batch_t *batch, void *stream);
+/* After poa_b200_batch_finish: the device-resident result, for a multi-GPU gather over NVLink without a
+ * host round trip.  *d_hdr = [n_blocks][POA_B200_HDR_WORDS] int32 block headers; arena `arena_idx`
+ * (0 <= arena_idx < *n_arenas; more than one only if blocks were re-run) holds *arena_words int32 words of
+ * block bodies; block_arena[b] (host array, n_blocks entries, owned by the batch) says which arena holds
+ * block b.  poa_b200_result_from_parts() turns gathered copies back into a result. */
+int  poa_b200_batch_device_result(poa_b200_batch_t *batch, int32_t arena_idx, const int32_t **d_hdr, const int32_t **d_arena,
+                                  int64_t *arena_words, int32_t *n_arenas, const int32_t **block_arena);
+/* Build a host result from header and arena words (copied) as produced on any GPU. */
+int  poa_b200_result_from_parts(int64_t n_blocks, const int32_t *hdr, const int32_t *arena, int64_t arena_words,
+                                poa_b200_result_t **result);
 void poa_b200_batch_free(poa_b200_batch_t *batch);
 int  poa_b200_batch_stats(const poa_b200_batch_t *batch, poa_b200_stats_t *stats);
 

@@ -136,7 +136,8 @@ struct poa_b200_result {
     std::vector<int> hdr;                 // n_blocks * HDR_WORDS
     std::vector<int> arena_of;            // per block: which arena holds its body
     std::vector<int *> arenas;            // pinned host copies
-    std::vector<size_t> arena_caps;       // bytes, for the pool
+    std::vector<size_t> arena_caps;       // bytes, for the pool (0 = not pooled)
+    std::vector<int> owned;               // storage of a result built by poa_b200_result_from_parts
     std::shared_ptr<PinnedPool> pinned;
     std::vector<unsigned long long> arena_words;
     poa_b200_stats_t stats{};
@@ -568,6 +569,46 @@ int poa_b200_batch_download(poa_b200_batch_t *b, void *stream, poa_b200_result_t
     return POA_B200_OK;
 }
 
+int poa_b200_batch_device_result(poa_b200_batch_t *b, int32_t arena_idx, const int32_t **d_hdr, const int32_t **d_arena,
+                                 int64_t *arena_words, int32_t *n_arenas, const int32_t **block_arena) {
+    if (!b || !b->finished) return set_err(POA_B200_EARG, "batch not finished");
+    if (n_arenas) *n_arenas = (int32_t)b->arenas.size();
+    if (d_hdr) *d_hdr = b->d_hdr;
+    if (block_arena) *block_arena = b->arena_of.data();
+    if (arena_idx < 0 || arena_idx >= (int)b->arenas.size()) {
+        if (d_arena) *d_arena = nullptr;
+        if (arena_words) *arena_words = 0;
+        return b->arenas.empty() ? POA_B200_OK : set_err(POA_B200_EARG, "bad arena index");
+    }
+    if (d_arena) *d_arena = b->arenas[(size_t)arena_idx].d;
+    if (arena_words) *arena_words = (int64_t)b->arenas[(size_t)arena_idx].used;
+    return POA_B200_OK;
+}
+
+int poa_b200_result_from_parts(int64_t n_blocks, const int32_t *hdr, const int32_t *arena, int64_t arena_words, poa_b200_result_t **out) {
+    if (!out || n_blocks < 0 || (n_blocks > 0 && !hdr) || arena_words < 0 || (arena_words > 0 && !arena)) return set_err(POA_B200_EARG, "bad argument");
+    static_assert(POA_B200_HDR_WORDS == HDR_WORDS, "header size mismatch");
+    poa_b200_result *r = new (std::nothrow) poa_b200_result();
+    if (!r) return set_err(POA_B200_ENOMEM, "result alloc");
+    r->n_blocks = n_blocks;
+    r->hdr.assign(hdr, hdr + n_blocks * HDR_WORDS);
+    r->arena_of.assign((size_t)n_blocks, 0);
+    r->owned.assign(arena, arena + arena_words);
+    r->arenas.push_back(r->owned.data()); r->arena_caps.push_back(0); r->arena_words.push_back((unsigned long long)arena_words);
+    // validate offsets so a corrupt gather cannot make the accessors read out of bounds
+    for (int64_t i = 0; i < n_blocks; ++i) {
+        const int *h = &r->hdr[(size_t)i * HDR_WORDS];
+        if (h[H_STATUS] != ST_OK) continue;
+        unsigned long long off = (unsigned long long)(unsigned)h[H_OFF_LO] | ((unsigned long long)(unsigned)h[H_OFF_HI] << 32);
+        unsigned long long words = 4ull * (unsigned)h[H_N_NODE] + 2ull * (unsigned)h[H_IN_TOT] + 2ull * (unsigned)h[H_OUT_TOT] + (unsigned)h[H_ALN_TOT]
+                                 + 3ull * (unsigned)h[H_N_SEQ] + (unsigned)h[H_PATH_TOT] + (unsigned)(h[H_CONS_LEN] > 0 ? h[H_CONS_LEN] : 0) + 2ull * (unsigned)h[H_CIG_TOT]
+                                 + ((unsigned long long)(unsigned)h[H_MSA_ROWS] * (unsigned)(h[H_MSA_LEN] > 0 ? h[H_MSA_LEN] : 0) + 3) / 4;
+        if (off + words > (unsigned long long)arena_words) { delete r; return set_err(POA_B200_EARG, "block body outside the arena"); }
+    }
+    *out = r;
+    return POA_B200_OK;
+}
+
 void poa_b200_batch_free(poa_b200_batch_t *b) {
     if (!b) return;
     {
@@ -646,7 +687,7 @@ int poa_b200_result_stats(const poa_b200_result_t *res, poa_b200_stats_t *s) {
 
 void poa_b200_result_free(poa_b200_result_t *res) {
     if (!res) return;
-    for (size_t i = 0; i < res->arenas.size(); ++i) res->pinned->give(res->arenas[i], res->arena_caps[i]);
+    for (size_t i = 0; i < res->arenas.size(); ++i) if (res->arena_caps[i]) res->pinned->give(res->arenas[i], res->arena_caps[i]);
     delete res;
 }
 

@@ -22,13 +22,15 @@ LIB_PATH = os.path.join(HERE, "lib", "libpoa_b200.so")
 
 # keep in sync with include/poa_b200.h
 OK, ESLAB, EARENA, EINTERNAL, EUNSUP, EBLOCK, ECUDA, EARG, ENOMEM = range(9)
+HDR_WORDS = 20  # POA_B200_HDR_WORDS
+H_OFF_LO, H_OFF_HI = 11, 12  # header slots holding a block body's word offset in its arena
 
 ABI_SYMBOLS = [
     "poa_b200_abi_version", "poa_b200_strerror", "poa_b200_last_error",
     "poa_b200_engine_create", "poa_b200_engine_destroy",
     "poa_b200_run_batch", "poa_b200_poa_block",
     "poa_b200_batch_upload", "poa_b200_batch_launch", "poa_b200_batch_download", "poa_b200_batch_finish",
-    "poa_b200_batch_free", "poa_b200_batch_stats",
+    "poa_b200_batch_free", "poa_b200_batch_stats", "poa_b200_batch_device_result", "poa_b200_result_from_parts",
     "poa_b200_result_n_blocks", "poa_b200_result_block", "poa_b200_result_stats", "poa_b200_result_free",
 ]
 
@@ -115,6 +117,8 @@ def load_library() -> C.CDLL:
     lib.poa_b200_batch_free.argtypes = [vp]
     lib.poa_b200_batch_free.restype = None
     lib.poa_b200_batch_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.poa_b200_batch_device_result.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i32), C.POINTER(vp)]
+    lib.poa_b200_result_from_parts.argtypes = [i64, vp, vp, i64, C.POINTER(vp)]
     lib.poa_b200_result_n_blocks.argtypes = [vp]
     lib.poa_b200_result_n_blocks.restype = i64
     lib.poa_b200_result_block.argtypes = [vp, i64, C.POINTER(_BlockView)]
@@ -209,6 +213,15 @@ class PoaResult:
         self.close()
 
 
+def result_from_parts(hdr: np.ndarray, arena: np.ndarray) -> PoaResult:
+    """Host result from gathered header / arena words (poa_b200_result_from_parts)."""
+    lib = load_library()
+    hdr = np.ascontiguousarray(hdr, dtype=np.int32); arena = np.ascontiguousarray(arena, dtype=np.int32)
+    r = C.c_void_p()
+    _check(lib, lib.poa_b200_result_from_parts(hdr.shape[0] // HDR_WORDS, hdr.ctypes.data, arena.ctypes.data, arena.shape[0], C.byref(r)))
+    return PoaResult(lib, r)
+
+
 class DeviceBatch:
     """A batch whose inputs are resident in HBM (staged API)."""
 
@@ -231,6 +244,19 @@ class DeviceBatch:
         s = Stats()
         _check(self._lib, self._lib.poa_b200_batch_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def device_result(self, n_blocks: int):
+        """(d_hdr_ptr, [(d_arena_ptr, words), ...], block_arena[n_blocks]) of a finished batch: raw device pointers
+        for the multi-GPU gather (smoothxg_b200/shard.py wraps them as torch tensors)."""
+        hdr, ar, bl = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        words, n_ar = C.c_int64(), C.c_int32()
+        _check(self._lib, self._lib.poa_b200_batch_device_result(self._h, 0, C.byref(hdr), C.byref(ar), C.byref(words), C.byref(n_ar), C.byref(bl)))
+        arenas = []
+        for i in range(n_ar.value):
+            _check(self._lib, self._lib.poa_b200_batch_device_result(self._h, i, None, C.byref(ar), C.byref(words), None, None))
+            arenas.append((ar.value, int(words.value)))
+        block_arena = np.ctypeslib.as_array(C.cast(bl, C.POINTER(C.c_int32)), shape=(n_blocks,)).copy() if n_blocks else np.zeros(0, np.int32)
+        return hdr.value, arenas, block_arena
 
     def close(self):
         if self._h:

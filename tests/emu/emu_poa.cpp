@@ -23,6 +23,19 @@ using namespace poa;
 
 extern "C" void emu_free(void *p) { free(p); }
 
+// Same run, but returns the product's wire format: HDR_WORDS header words followed by the arena words
+// (so the C ABI's result accessors and poa_b200_result_from_parts can be exercised without a GPU).
+static int g_want_wire = 0;
+extern "C" int32_t *emu_poa_block(const pd_params_t *pp, int n_seq, const int32_t *seq_len, const uint8_t *bases,
+                                  const int32_t *weight, int instrument, int64_t *n_out);
+extern "C" int32_t *emu_poa_block_wire(const pd_params_t *pp, int n_seq, const int32_t *seq_len, const uint8_t *bases,
+                                       const int32_t *weight, int instrument, int64_t *n_out) {
+    g_want_wire = 1;
+    int32_t *r = emu_poa_block(pp, n_seq, seq_len, bases, weight, instrument, n_out);
+    g_want_wire = 0;
+    return r;
+}
+
 extern "C" int32_t *emu_poa_block(const pd_params_t *pp, int n_seq, const int32_t *seq_len, const uint8_t *bases,
                                   const int32_t *weight, int instrument, int64_t *n_out) {
     *n_out = 0;
@@ -58,6 +71,13 @@ extern "C" int32_t *emu_poa_block(const pd_params_t *pp, int n_seq, const int32_
     ws_bind(sh.ws, wsp, L);
     poa_block<1>(sh, dp, B, L, O, 0);
     if (hdr[H_STATUS] != ST_OK) { fprintf(stderr, "[emu] block status %d\n", hdr[H_STATUS]); *n_out = -hdr[H_STATUS]; return nullptr; }
+    if (g_want_wire) {
+        int32_t *out = (int32_t *)malloc(sizeof(int32_t) * (HDR_WORDS + used + 1));
+        memcpy(out, hdr.data(), sizeof(int32_t) * HDR_WORDS);
+        memcpy(out + HDR_WORDS, arena.data(), sizeof(int32_t) * used);
+        *n_out = (int64_t)(HDR_WORDS + used);
+        return out;
+    }
     // wire format -> canonical dump
     const int n = hdr[H_N_NODE], ns = hdr[H_N_SEQ];
     const long long in_tot = hdr[H_IN_TOT], out_tot = hdr[H_OUT_TOT], aln_tot = hdr[H_ALN_TOT], path_tot = hdr[H_PATH_TOT], cig_tot = hdr[H_CIG_TOT];

@@ -1,0 +1,166 @@
+"""GPU (-m gpu): the CUDA path through the C ABI against (a) the committed golden vectors of the unmodified
+abPOA, (b) the oracle on fresh seeded inputs, (c) size-independent properties at BASELINE.json's full sizes.
+Bit-exact everywhere: integer DP, node ids, edge order, weights, paths, consensus, MSA, scores, cigars and the
+in-band cell count."""
+import numpy as np
+import pytest
+
+from oracle.oracle import make_params as oracle_params
+from smoothxg_b200 import engine as E
+from smoothxg_b200 import shard, synth
+from tests.golden_io import engine_params, load_cases, pd_params
+from tests.helpers import first_diff, view_to_dump
+
+pytestmark = pytest.mark.gpu
+CASES = load_cases()
+
+
+def _check_batch(eng, batch, eparams, want_dumps, label):
+    res = eng.run_batch(batch, eparams)
+    for b in range(batch.n_blocks):
+        got = view_to_dump(res.block(b))
+        assert np.array_equal(got.compare_part(), want_dumps[b].compare_part()), f"{label} block {b}: {first_diff(want_dumps[b], got)}"
+    st = res.stats()
+    res.close()
+    return st
+
+
+@pytest.mark.parametrize("warps", [1, 2, 4, 8])
+def test_golden_vectors(warps):
+    eng = E.PoaEngine(device=0, emit_cigar=True, warps_per_block=warps)
+    for name, batch, p, dumps in CASES:
+        _check_batch(eng, batch, engine_params(p), dumps, f"{name}/w{warps}")
+    eng.close()
+
+
+@pytest.mark.parametrize("kw,pk", [
+    (dict(n_blocks=24, n_seqs=16, length=1000, seed=201), dict()),
+    (dict(n_blocks=8, n_seqs=12, length=1500, seed=202, indel_prob=0.6, indel_len=(100, 700), dup_weights=True, n_frac=0.01), dict(out_msa=True)),
+    (dict(n_blocks=8, n_seqs=8, length=700, seed=203), dict(local=True, out_msa=True)),
+    (dict(n_blocks=8, n_seqs=8, length=500, seed=204, divergence=0.12), dict(banded=False)),
+    (dict(n_blocks=6, n_seqs=32, length=2000, seed=205), dict()),
+    (dict(n_blocks=4, n_seqs=10, length=800, seed=206, divergence=0.001), dict(out_msa=True)),
+])
+def test_fresh_inputs_vs_oracle(engine, oracle, kw, pk):
+    batch = synth.make_batch(**kw)
+    want = oracle.poa_batch(oracle_params(**pk), batch)
+    st = _check_batch(engine, batch, E.make_params(**pk), want, str(kw))
+    assert st["inband_cells"] == sum(d.inband_cells for d in want)
+    assert st["edge_row_cells"] == sum(d.edge_rows for d in want)
+
+
+def test_int32_scores_and_mid_block_switch(engine, oracle):
+    """max(qlen, rows) > 16361 switches abPOA to 32-bit scores (abpoa_align_simd.c:1293-1302), also mid-block."""
+    for kw in (dict(n_blocks=1, n_seqs=3, length=17000, seed=21), dict(n_blocks=1, n_seqs=6, length=8000, seed=22, divergence=0.3)):
+        batch = synth.make_batch(**kw)
+        want = oracle.poa_batch(oracle_params(), batch)
+        assert want[0].n_node > 16400
+        _check_batch(engine, batch, E.make_params(), want, str(kw))
+
+
+def test_workspace_retry_gives_identical_results(oracle):
+    """Blocks that exhaust the first-guess workspace are re-run with larger ones; results must not change."""
+    batch = synth.make_batch(n_blocks=6, n_seqs=8, length=600, seed=9, divergence=0.25)
+    want = oracle.poa_batch(oracle_params(), batch)
+    eng = E.PoaEngine(device=0, emit_cigar=True, slab_rows_factor=1.0)
+    st = _check_batch(eng, batch, E.make_params(), want, "retry")
+    assert st["retried_blocks"] > 0 and st["kernel_launches"] >= 2
+    eng.close()
+
+
+def test_poa_block_call_shape(engine, oracle):
+    """poa_b200_poa_block takes abpoa_poa's argument shapes (seqs[], seq_lens[], weights[])."""
+    batch = synth.make_batch(n_blocks=1, n_seqs=7, length=300, seed=31, dup_weights=True)
+    lens, bases, wts = batch.block(0)
+    res = engine.poa_block(batch.block_seqs(0), wts, E.make_params(out_msa=True))
+    want = oracle.poa_block(oracle_params(out_msa=True), lens, bases, wts)
+    assert np.array_equal(view_to_dump(res.block(0)).compare_part(), want.compare_part())
+
+
+def test_unsupported_gap_mode_is_refused(engine):
+    batch = synth.make_batch(n_blocks=1, n_seqs=2, length=50, seed=1)
+    with pytest.raises(E.PoaError) as e:
+        engine.run_batch(batch, E.make_params(gap_open2=0, gap_ext2=0))
+    assert e.value.code == E.EUNSUP
+
+
+def test_empty_batch(engine):
+    batch = synth.PoaBatch.from_blocks([])
+    res = engine.run_batch(batch, E.make_params())
+    assert len(res) == 0
+
+
+def _properties(batch, res, blocks):
+    """Size-independent invariants of a POA result (hold for any input): every read's path spells the read;
+    the source's out-weights and the sink's in-weights sum to the total read weight; every edge list is sorted by
+    weight (abpoa_graph.c:192-219); in- and out-lists describe the same edges; the consensus is a source-to-sink walk."""
+    for b in blocks:
+        v = res.block(b)
+        assert v.status == 0
+        lens, bases, wts = batch.block(b)
+        assert np.array_equal(v.path_len, lens)
+        assert np.array_equal(v.base[v.path_node].astype(np.uint8), bases)
+        out_off = np.concatenate([[0], np.cumsum(v.out_n)]); in_off = np.concatenate([[0], np.cumsum(v.in_n)])
+        assert v.out_w[out_off[0]:out_off[1]].sum() == wts.sum() == v.in_w[in_off[1]:in_off[2]].sum()
+        src = np.repeat(np.arange(v.n_node), v.out_n); dst = np.repeat(np.arange(v.n_node), v.in_n)
+        e_out = np.stack([src, v.out_id, v.out_w], 1); e_in = np.stack([v.in_id, dst, v.in_w], 1)
+        assert np.array_equal(e_out[np.lexsort(e_out.T[::-1])], e_in[np.lexsort(e_in.T[::-1])])
+        for off, w in ((out_off, v.out_w), (in_off, v.in_w)):
+            d = np.diff(w); brk = np.zeros(d.shape[0], bool); idx = off[1:-1] - 1
+            brk[idx[(idx >= 0) & (idx < d.shape[0])]] = True
+            assert np.all((d <= 0) | brk)
+        # total path weight through every node = its in-weight = its out-weight
+        win = np.add.reduceat(np.concatenate([v.in_w, [0]]), np.minimum(in_off[:-1], v.in_w.shape[0]))[2:]
+        wout = np.add.reduceat(np.concatenate([v.out_w, [0]]), np.minimum(out_off[:-1], v.out_w.shape[0]))[2:]
+        assert np.array_equal(win, wout)
+        if v.cons_len > 0:
+            c = v.cons_node
+            eset = set(zip(src.tolist(), v.out_id.tolist()))
+            assert (0, int(c[0])) in eset and (int(c[-1]), 1) in eset
+            assert all((int(a), int(b_)) in eset for a, b_ in zip(c[:-1], c[1:]))
+
+
+def test_full_size_config1_properties_and_determinism():
+    """BASELINE.json configs[1]: 1000 blocks x 16 seqs x 1 kb, int16.  Properties on every block; the result is
+    identical for 1 and 4 warps per block (scheduling-independent) -- checksum of checksums."""
+    batch = synth.make_batch(**synth.CONFIGS["config1_1000x16x1k"], seed=1000)
+    sums = []
+    for warps in (1, 4):
+        eng = E.PoaEngine(device=0, warps_per_block=warps)
+        res = eng.run_batch(batch, E.make_params())
+        if warps == 1:
+            _properties(batch, res, range(batch.n_blocks))
+        h = 0
+        for b in range(batch.n_blocks):
+            v = res.block(b)
+            h = hash((h, v.n_node, v.out_id.tobytes(), v.out_w.tobytes(), v.path_node.tobytes(), v.cons_node.tobytes(), v.inband_cells))
+        sums.append(h)
+        res.close(); eng.close()
+    assert sums[0] == sums[1]
+
+
+def test_full_size_config2_properties(oracle):
+    """BASELINE.json configs[2]: 10 000 blocks x 32 seqs x 2 kb, adaptive band: all blocks finish, invariants hold on a
+    sample, and a few blocks are compared with the oracle outright."""
+    batch = synth.make_batch(**synth.CONFIGS["config2_10000x32x2k"], seed=1000)
+    eng = E.PoaEngine(device=0)
+    res = eng.run_batch(batch, E.make_params())
+    st = res.stats()
+    assert st["retried_blocks"] == 0 or st["kernel_launches"] > 1
+    sample = list(range(0, batch.n_blocks, 97))
+    _properties(batch, res, sample)
+    for b in range(0, batch.n_blocks, 10):
+        assert res.block(b).status == 0
+    for b in (0, 4999, 9999):
+        want = oracle.poa_block(oracle_params(), *batch.block(b), instrument=False)
+        assert np.array_equal(view_to_dump(res.block(b)).result_part(), want.result_part())
+    res.close(); eng.close()
+
+
+def test_run_sharded_single_rank_equals_run_batch(engine):
+    batch = synth.make_batch(n_blocks=10, n_seqs=6, length=300, seed=41)
+    p = E.make_params(out_msa=True)
+    a = engine.run_batch(batch, p)
+    b = shard.run_sharded(engine, batch, p)
+    for i in range(batch.n_blocks):
+        assert np.array_equal(view_to_dump(a.block(i)).compare_part(), view_to_dump(b.block(i)).compare_part())

@@ -1,0 +1,36 @@
+"""CPU: the scalar restatement (oracle/poa_oracle.c) against the committed golden vectors produced by
+the unmodified vendored abPOA -- graph, read paths, consensus, MSA, scores, cigars, band cell counts."""
+import numpy as np
+import pytest
+
+from tests.golden_io import load_cases, pd_params
+
+CASES = load_cases()
+
+
+@pytest.mark.parametrize("name,batch,p,dumps", CASES, ids=[c[0] for c in CASES])
+def test_oracle_matches_golden(oracle, name, batch, p, dumps):
+    for b in range(batch.n_blocks):
+        got = oracle.poa_block(pd_params(p), *batch.block(b))
+        assert got is not None
+        assert np.array_equal(got.raw, dumps[b].raw), f"{name} block {b}"
+
+
+def test_oracle_lane_count_only_moves_junk(oracle):
+    """The reference's SIMD lane count only shifts the band start over -inf cells: results equal."""
+    name, batch, p, dumps = next(c for c in CASES if c[0] == "syn_indel")
+    try:
+        for pn16, pn32 in ((8, 4), (16, 8)):
+            oracle.set_lane_counts(pn16, pn32)
+            for b in range(batch.n_blocks):
+                got = oracle.poa_block(pd_params(p), *batch.block(b))
+                assert np.array_equal(got.result_part(), dumps[b].result_part())
+    finally:
+        oracle.set_lane_counts(32, 16)
+
+
+def test_affine_is_refused(oracle):
+    from oracle.oracle import make_params
+    p = make_params(gap_open2=0, gap_ext2=0)
+    name, batch, _, _ = CASES[0]
+    assert oracle.poa_block(p, *batch.block(0)) is None
