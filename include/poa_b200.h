@@ -122,6 +122,11 @@ int  poa_b200_abi_version(void);
 const char *poa_b200_strerror(int code);
 const char *poa_b200_last_error(void); /* thread-local text of the last CUDA/argument error */
 
+/* ASCII -> abPOA base codes, replacing the ab_char26_table loop at src/smooth.cpp:304-313 (table:
+ * deps/abPOA/src/abpoa_seq.c:15-32): A/a 0, C/c 1, G/g 2, T/t/U/u 3, bytes 0..3 map to themselves, everything
+ * else (N, IUPAC codes, '-') 4.  Pure host code; needs no GPU. */
+void poa_b200_encode_bases(const char *ascii, int64_t n, uint8_t *codes);
+
 int  poa_b200_engine_create(int device, const poa_b200_engine_opts_t *opts, poa_b200_engine_t **out);
 void poa_b200_engine_destroy(poa_b200_engine_t *eng);
 

@@ -403,6 +403,19 @@ const char *poa_b200_strerror(int code) {
 
 const char *poa_b200_last_error(void) { return g_last_error.c_str(); }
 
+void poa_b200_encode_bases(const char *ascii, int64_t n, uint8_t *codes) {
+    static const struct Table {
+        uint8_t t[256];
+        Table() {
+            for (int i = 0; i < 256; ++i) t[i] = 4;
+            t[0] = 0; t[1] = 1; t[2] = 2; t[3] = 3;
+            t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2;
+            t['T'] = t['t'] = t['U'] = t['u'] = 3;
+        }
+    } tab;
+    for (int64_t i = 0; i < n; ++i) codes[i] = tab.t[(unsigned char)ascii[i]];
+}
+
 int poa_b200_engine_create(int device, const poa_b200_engine_opts_t *opts, poa_b200_engine_t **out) {
     if (!out) return set_err(POA_B200_EARG, "out is NULL");
     *out = nullptr;

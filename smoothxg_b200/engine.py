@@ -27,7 +27,7 @@ H_OFF_LO, H_OFF_HI = 11, 12  # header slots holding a block body's word offset i
 
 ABI_SYMBOLS = [
     "poa_b200_abi_version", "poa_b200_strerror", "poa_b200_last_error",
-    "poa_b200_engine_create", "poa_b200_engine_destroy",
+    "poa_b200_encode_bases", "poa_b200_engine_create", "poa_b200_engine_destroy",
     "poa_b200_run_batch", "poa_b200_poa_block",
     "poa_b200_batch_upload", "poa_b200_batch_launch", "poa_b200_batch_download", "poa_b200_batch_finish",
     "poa_b200_batch_free", "poa_b200_batch_stats", "poa_b200_batch_device_result", "poa_b200_result_from_parts",
@@ -104,6 +104,8 @@ def load_library() -> C.CDLL:
     lib.poa_b200_strerror.restype = C.c_char_p
     lib.poa_b200_strerror.argtypes = [C.c_int]
     lib.poa_b200_last_error.restype = C.c_char_p
+    lib.poa_b200_encode_bases.argtypes = [C.c_char_p, i64, vp]
+    lib.poa_b200_encode_bases.restype = None
     lib.poa_b200_engine_create.argtypes = [C.c_int, C.POINTER(EngineOpts), C.POINTER(vp)]
     lib.poa_b200_engine_destroy.argtypes = [vp]
     lib.poa_b200_engine_destroy.restype = None
@@ -127,6 +129,15 @@ def load_library() -> C.CDLL:
     lib.poa_b200_result_free.restype = None
     _lib = lib
     return lib
+
+
+def encode_bases(ascii_seq: bytes | str) -> np.ndarray:
+    """ASCII -> abPOA codes through the library (poa_b200_encode_bases; reference src/smooth.cpp:304-313)."""
+    if isinstance(ascii_seq, str):
+        ascii_seq = ascii_seq.encode()
+    out = np.empty(len(ascii_seq), dtype=np.uint8)
+    load_library().poa_b200_encode_bases(ascii_seq, len(ascii_seq), out.ctypes.data)
+    return out
 
 
 def _check(lib, rc, allow=()):

@@ -20,7 +20,7 @@ def declared_symbols():
 def test_library_exports_every_declared_symbol():
     lib = engine.load_library()
     syms = declared_symbols()
-    assert len(syms) >= 19
+    assert len(syms) >= 20
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/poa_b200.h but not exported"
     assert sorted(engine.ABI_SYMBOLS) == syms
@@ -56,3 +56,13 @@ def test_product_never_imports_oracle():
                 code = [ln for ln in txt.splitlines() if re.match(r"\s*(import|from|#include)\b", ln)]
                 assert not any("oracle" in ln for ln in code), f
                 assert "libpoa_oracle" not in txt and "libabpoa_ref" not in txt and "CDLL(\"oracle" not in txt, f
+
+
+def test_encode_bases_matches_abpoa_table():
+    """poa_b200_encode_bases == ab_nt4_table (deps/abPOA/src/abpoa_seq.c:15-32), all 256 byte values."""
+    import numpy as np
+    from smoothxg_b200 import synth
+    allb = bytes(range(1, 256)) + b"ACGTNacgtnUu-RYKM"
+    got = engine.encode_bases(allb)
+    want = synth._ENC[np.frombuffer(allb, dtype=np.uint8)]
+    assert np.array_equal(got, want)
