@@ -238,7 +238,12 @@ Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int lev
     s.nmax = nmax; s.max_bases = max_bases; s.max_len = max_len; s.max_seq = max_seq;
     const long long edges = std::min<long long>(max_bases + max_seq, level >= 2 ? (1LL << 60) : 3 * nmax);
     s.pool_growth = 8 * edges + 64;
-    s.slab_bytes = rows * vecs_per_row * 5 * (may32 ? 32 : 16);
+    long long row_bytes = vecs_per_row * 5 * (may32 ? 32 : 16);
+    if (b->dp.p16_ok) {  // chunked rows of the packed 16-bit fill: whole 256-column chunks, 5 planes x 512 B each
+        const long long chunks = level >= 2 ? width / 256 + 2 : (width * 10 + 2559) / 2560 + 1;  // typical: one partial chunk extra
+        row_bytes = std::max(row_bytes, (level >= 1 ? width / 256 + 2 : chunks) * 2560);
+    }
+    s.slab_bytes = rows * row_bytes;
     return s;
 }
 

@@ -33,7 +33,11 @@
 #define POA_D static inline
 #define POA_DN static
 #define POA_SM static inline
-#define POA_WARP 1
+#ifndef POA_EMU_LANES
+#define POA_EMU_LANES 1
+#endif
+#define POA_WARP POA_EMU_LANES
+#if POA_EMU_LANES == 1
 static inline int poa_tid() { return 0; }
 static inline void poa_sync_block() {}
 static inline void poa_sync_warp() {}
@@ -41,6 +45,21 @@ static inline int poa_shfl_up(int v, int) { return v; }
 static inline int poa_shfl(int v, int) { return v; }
 static inline int poa_redux_max(int v) { return v; }
 static inline int poa_redux_min(int v) { return v; }
+static inline unsigned poa_ballot(int p) { return p ? 1u : 0u; }
+#else
+// 32 lock-step lanes emulated as fibers by the test harness (tests/emu/emu_simt.cpp): every collective is
+// an all-lanes exchange, so the warp-level logic (shuffle scans, reductions, lane-striped layouts) runs
+// on a machine without a GPU.  One warp per block only.
+namespace poa_emu { int lane(); void xchg(int v, int *all); }
+static inline int poa_tid() { return poa_emu::lane(); }
+static inline void poa_sync_warp() { int a[POA_EMU_LANES]; poa_emu::xchg(0, a); }
+static inline void poa_sync_block() { poa_sync_warp(); }
+static inline int poa_shfl_up(int v, int d) { int a[POA_EMU_LANES]; poa_emu::xchg(v, a); int l = poa_emu::lane(); return l >= d ? a[l - d] : v; }
+static inline int poa_shfl(int v, int l) { int a[POA_EMU_LANES]; poa_emu::xchg(v, a); return a[l & (POA_EMU_LANES - 1)]; }
+static inline int poa_redux_max(int v) { int a[POA_EMU_LANES]; poa_emu::xchg(v, a); int m = a[0]; for (int i = 1; i < POA_EMU_LANES; ++i) m = a[i] > m ? a[i] : m; return m; }
+static inline int poa_redux_min(int v) { int a[POA_EMU_LANES]; poa_emu::xchg(v, a); int m = a[0]; for (int i = 1; i < POA_EMU_LANES; ++i) m = a[i] < m ? a[i] : m; return m; }
+static inline unsigned poa_ballot(int p) { int a[POA_EMU_LANES]; poa_emu::xchg(p ? 1 : 0, a); unsigned m = 0; for (int i = 0; i < POA_EMU_LANES; ++i) if (a[i]) m |= 1u << i; return m; }
+#endif
 static inline long long poa_clock() { return 0; }
 static inline unsigned long long poa_atomic_add(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 static inline int poa_atomic_add(int *p, int v) { int o = *p; *p += v; return o; }
@@ -57,6 +76,7 @@ POA_D int poa_shfl_up(int v, int d) { return __shfl_up_sync(0xffffffffu, v, d); 
 POA_D int poa_shfl(int v, int l) { return __shfl_sync(0xffffffffu, v, l); }
 POA_D int poa_redux_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 POA_D int poa_redux_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
+POA_D unsigned poa_ballot(int p) { return __ballot_sync(0xffffffffu, p); }
 POA_D long long poa_clock() { return clock64(); }
 POA_D unsigned long long poa_atomic_add(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
 POA_D int poa_atomic_add(int *p, int v) { return atomicAdd(p, v); }
@@ -92,6 +112,7 @@ struct DevParams {
     int out_cons, out_msa;
     int pn16, pn32;  // lane counts of the reference build whose band-start rule we reproduce (AVX-512BW: 32/16)
     int emit_cigar;
+    int p16_ok;  // scoring parameters allow the packed 16-bit fill (poa_fill16.cuh)
 };
 
 // Device-resident batch input (flat, same arrays as the C ABI takes).
@@ -111,7 +132,7 @@ struct WsLayout {
     long long o_base, o_aln_n, o_aln, o_in_off, o_in_n, o_out_off, o_out_n, o_pool_id, o_pool_w, o_pool_row;
     long long o_idx2id, o_id2idx, o_remain, o_tmp0, o_tmp1, o_tmp2, o_tmp3;
     long long o_rowinfo, o_rowmeta, o_rbase, o_rr, o_mplr, o_mprr;
-    long long o_cig, o_path, o_best, o_ncig, o_slab;
+    long long o_cig, o_path, o_best, o_ncig, o_qp, o_slab;
     long long slab_bytes;
     int nmax;      // node capacity
     int pool_cap;  // edge pool capacity (entries)
@@ -135,6 +156,7 @@ struct Ws {
     int *rr, *mplr, *mprr;
     unsigned long long *cig;
     int *path, *best, *ncig;
+    char *qp;    // query profile of the alignment in flight, chunked layout (poa_fill16.cuh)
     char *slab;
 };
 
@@ -625,6 +647,8 @@ POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, lon
     sync_block<NW>();
 }
 
+#include "poa_fill16.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // backtrack (abpoa_align_simd.c:309-458), one thread
 // ------------------------------------------------------------------------------------------------
@@ -641,7 +665,16 @@ POA_D void push_cigar(Shared &sh, int op, int len, int node_id, int query_id) { 
     } else cig[n - 1] += l << 4;
 }
 
-template <typename S>
+// LAY16: rows are in the chunked layout of poa_fill16.cuh (S = short only)
+template <typename S, bool LAY16>
+POA_D const S *bt_cell(const Ws &w, const int4 &pm, int plane, int j) {
+#if POA_WARP == 32
+    if (LAY16) return reinterpret_cast<const S *>(cell_ptr16(w, pm, plane, j));
+#endif
+    return cell_ptr<S>(w, pm, plane, j);
+}
+
+template <typename S, bool LAY16>
 POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen) {
     Ws &w = sh.ws;
     const int inf_min = inf_min_of<S>(P);
@@ -654,7 +687,7 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
     if (j < qlen) push_cigar(sh, CINS, qlen - j, -1, qlen - 1);
     while (i > 0 && j > 0) {
         const int4 rm = w.rowmeta[i];
-        const int Hj = *cell_ptr<S>(w, rm, 0, j);
+        const int Hj = *bt_cell<S, LAY16>(w, rm, 0, j);
         if (local && Hj == 0) break;
         const int4 ri = w.rowinfo[i];
         const int s = P.mat[5 * w.rbase[i] + q[j - 1]];
@@ -664,7 +697,7 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
                 int pi = w.pool_row[ri.x + k];
                 const int4 pm = w.rowmeta[pi];
                 if (j - 1 < pm.y || j - 1 > pm.z) continue;
-                if ((int)(S)(*cell_ptr<S>(w, pm, 0, j - 1) + s) == Hj) {
+                if ((int)(S)(*bt_cell<S, LAY16>(w, pm, 0, j - 1) + s) == Hj) {
                     push_cigar(sh, CMATCH, 1, id, j - 1);
                     i = pi; --j; id = w.idx2id[i]; hit = 1; cur_op = OP_ALL;
                     break;
@@ -672,14 +705,14 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
             }
         }
         if (hit == 0 && (cur_op & OP_E)) {
-            const int E1j = *cell_ptr<S>(w, rm, 1, j), E2j = *cell_ptr<S>(w, rm, 2, j);
+            const int E1j = *bt_cell<S, LAY16>(w, rm, 1, j), E2j = *bt_cell<S, LAY16>(w, rm, 2, j);
             for (int k = 0; k < ri.y; ++k) {
                 int pi = w.pool_row[ri.x + k];
                 const int4 pm = w.rowmeta[pi];
                 if (j < pm.y || j > pm.z) continue;
-                const int pH = *cell_ptr<S>(w, pm, 0, j);
+                const int pH = *bt_cell<S, LAY16>(w, pm, 0, j);
                 if (cur_op & OP_E1) {
-                    const int pE1 = *cell_ptr<S>(w, pm, 1, j);
+                    const int pE1 = *bt_cell<S, LAY16>(w, pm, 1, j);
                     bool cond = (cur_op & OP_M) ? (Hj == pE1) : (E1j == (int)(S)(pE1 - e1));
                     if (cond) {
                         cur_op = ((int)(S)(pH - oe1) == pE1) ? (OP_M | OP_F) : OP_E1;
@@ -689,7 +722,7 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
                     }
                 }
                 if (cur_op & OP_E2) {
-                    const int pE2 = *cell_ptr<S>(w, pm, 2, j);
+                    const int pE2 = *bt_cell<S, LAY16>(w, pm, 2, j);
                     bool cond = (cur_op & OP_M) ? (Hj == pE2) : (E2j == (int)(S)(pE2 - e2));
                     if (cond) {
                         cur_op = ((int)(S)(pH - oe2) == pE2) ? (OP_M | OP_F) : OP_E2;
@@ -702,18 +735,18 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
         }
         if (hit == 0 && (cur_op & OP_F)) {
             const bool inl = j - 1 >= rm.y;  // left neighbour inside this row's band?
-            const int hl = inl ? (int)*cell_ptr<S>(w, rm, 0, j - 1) : inf_min;
-            const int F1j = *cell_ptr<S>(w, rm, 3, j), F2j = *cell_ptr<S>(w, rm, 4, j);
+            const int hl = inl ? (int)*bt_cell<S, LAY16>(w, rm, 0, j - 1) : inf_min;
+            const int F1j = *bt_cell<S, LAY16>(w, rm, 3, j), F2j = *bt_cell<S, LAY16>(w, rm, 4, j);
             if (cur_op & OP_F1) {
                 if (!(cur_op & OP_M) || Hj == F1j) {
-                    const int f1l = inl ? (int)*cell_ptr<S>(w, rm, 3, j - 1) : inf_min;
+                    const int f1l = inl ? (int)*bt_cell<S, LAY16>(w, rm, 3, j - 1) : inf_min;
                     if ((int)(S)(hl - oe1) == F1j) { cur_op = OP_M | OP_E; hit = 1; }
                     else if ((int)(S)(f1l - e1) == F1j) { cur_op = OP_F1; hit = 1; }
                 }
             }
             if (hit == 0 && (cur_op & OP_F2)) {
                 if (!(cur_op & OP_M) || Hj == F2j) {
-                    const int f2l = inl ? (int)*cell_ptr<S>(w, rm, 4, j - 1) : inf_min;
+                    const int f2l = inl ? (int)*bt_cell<S, LAY16>(w, rm, 4, j - 1) : inf_min;
                     if ((int)(S)(hl - oe2) == F2j) { cur_op = OP_M | OP_E; hit = 1; }
                     else if ((int)(S)(f2l - e2) == F2j) { cur_op = OP_F2; hit = 1; }
                 }
@@ -859,7 +892,7 @@ POA_D void ws_bind(Ws &w, char *b, const WsLayout &L) {
     w.rowinfo = (int4 *)(b + L.o_rowinfo); w.rowmeta = (int4 *)(b + L.o_rowmeta); w.rbase = (uint8_t *)(b + L.o_rbase);
     w.rr = (int *)(b + L.o_rr); w.mplr = (int *)(b + L.o_mplr); w.mprr = (int *)(b + L.o_mprr);
     w.cig = (unsigned long long *)(b + L.o_cig); w.path = (int *)(b + L.o_path); w.best = (int *)(b + L.o_best); w.ncig = (int *)(b + L.o_ncig);
-    w.slab = b + L.o_slab;
+    w.qp = b + L.o_qp; w.slab = b + L.o_slab;
 }
 
 // block-wide sum of f(i), i in [0,n); result broadcast through sh.bcast[0..]
@@ -944,13 +977,25 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
             long long ms1 = (long long)qlen * P.match, ms2 = (long long)len * P.e1 + P.o1;
             long long max_score = ms1 > ms2 ? ms1 : ms2;
             const bool bits16 = max_score <= (long long)INT16_MAX - P.min_mis - P.oe1 - P.oe2;
-            if (bits16) fill<NW, short>(sh, P, q, qlen, L.slab_bytes / 16);
+#if POA_WARP == 32
+            const bool p16 = NW == 1 && bits16 && p16_eligible(P, qlen);
+#else
+            const bool p16 = false;
+#endif
+            if (p16) {
+                t_ph[PH_SPARE] += 1;  // alignments that took the packed 16-bit fill
+#if POA_WARP == 32
+                fill_p16<NW>(sh, P, q, qlen, L.slab_bytes);
+#endif
+            } else if (bits16) fill<NW, short>(sh, P, q, qlen, L.slab_bytes / 16);
             else fill<NW, int>(sh, P, q, qlen, L.slab_bytes / 32);
             long long t2 = poa_clock();
             t_ph[PH_FILL] += t2 - t1;
             if (sh.err != ST_OK) break;
             if (tid == 0) {
-                if (bits16) backtrack<short>(sh, P, q, qlen); else backtrack<int>(sh, P, q, qlen);
+                if (p16) backtrack<short, true>(sh, P, q, qlen);
+                else if (bits16) backtrack<short, false>(sh, P, q, qlen);
+                else backtrack<int, false>(sh, P, q, qlen);
             }
             sync_block<NW>();
             long long t3 = poa_clock();

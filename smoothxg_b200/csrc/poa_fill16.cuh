@@ -1,0 +1,338 @@
+// poa_fill16.cuh -- packed-int16 DP fill (included by poa_core.cuh inside namespace poa).
+//
+// Same recurrence as fill<NW, short>() (abPOA's convex row kernel, deps/abPOA/src/abpoa_align_simd.c:935-1074,
+// first row :617-688, band :1107-1130), different machine mapping:
+//
+//  * two cells per 32-bit register, evaluated with Blackwell's packed 16-bit integer instructions
+//    (VIADD.16x2, VIMNMX.S16x2, VIMNMX3.S16x2, VIADDMNMX.S16x2 -- __vadd2/__vmaxs2/__vimax3_s16x2/__viaddmax_s16x2);
+//  * columns are processed in absolute 256-column chunks.  In a chunk, lane t holds columns
+//    c0 + 4t .. c0 + 4t+3 in the low halves of four registers and c0 + 128 + 4t .. +3 in the high halves, so
+//    the "previous column" operand of the match state is the neighbouring register (one shuffle per chunk
+//    for register 0) and both halves run the horizontal-gap recurrences at once;
+//  * F1/F2 are computed exactly: a 4-cell chain per lane, then a max-plus scan of the 64 lane-halves
+//    (G = F + e*position turns the decaying recurrence into a running maximum), then a per-cell fix-up;
+//  * a row is stored as [plane][chunk][lane][4 words] = 512-byte chunk-planes, so every predecessor read and
+//    every store is one fully coalesced 128-bit access per lane, and rows of different bands line up without
+//    shifts because chunks are in absolute column coordinates.
+//
+// Cells of a stored chunk that lie outside the row's band [beg,end] hold inf_min in the H, E1 and E2 planes
+// (what successors and the traceback may read); the F planes are only ever read inside the band.
+#if POA_WARP == 32
+
+#ifdef POA_HOST_EMU
+static inline unsigned p_pack(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+static inline int p_lo(unsigned x) { return (int)(short)(x & 0xffffu); }
+static inline int p_hi(unsigned x) { return (int)(short)(x >> 16); }
+static inline unsigned p_add(unsigned a, unsigned b) { return p_pack(p_lo(a) + p_lo(b), p_hi(a) + p_hi(b)); }
+static inline unsigned p_max(unsigned a, unsigned b) { return p_pack(imax(p_lo(a), p_lo(b)), imax(p_hi(a), p_hi(b))); }
+static inline unsigned p_min(unsigned a, unsigned b) { return p_pack(imin(p_lo(a), p_lo(b)), imin(p_hi(a), p_hi(b))); }
+static inline unsigned p_max3(unsigned a, unsigned b, unsigned c) { return p_max(p_max(a, b), c); }
+static inline unsigned p_addmax(unsigned a, unsigned b, unsigned c) { return p_max(p_add(a, b), c); }
+static inline unsigned p_signmask(unsigned d) { return (p_lo(d) < 0 ? 0xffffu : 0u) | (p_hi(d) < 0 ? 0xffff0000u : 0u); }
+static inline unsigned p_swap(unsigned x) { return (x >> 16) | (x << 16); }
+static inline unsigned p_lolo(unsigned a, unsigned b) { return (a & 0xffffu) | (b << 16); }  // (a.lo, b.lo)
+#else
+POA_D unsigned p_pack(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+POA_D int p_lo(unsigned x) { return (int)(short)(x & 0xffffu); }
+POA_D int p_hi(unsigned x) { return (int)x >> 16; }
+POA_D unsigned p_add(unsigned a, unsigned b) { return __vadd2(a, b); }
+POA_D unsigned p_max(unsigned a, unsigned b) { return __vmaxs2(a, b); }
+POA_D unsigned p_min(unsigned a, unsigned b) { return __vmins2(a, b); }
+POA_D unsigned p_max3(unsigned a, unsigned b, unsigned c) { return __vimax3_s16x2(a, b, c); }
+POA_D unsigned p_addmax(unsigned a, unsigned b, unsigned c) { return __viaddmax_s16x2(a, b, c); }
+POA_D unsigned p_signmask(unsigned d) { return __byte_perm(d, 0u, 0xbb99u); }  // PRMT sign-replicate: 0xffff per negative half
+POA_D unsigned p_swap(unsigned x) { return __byte_perm(x, 0u, 0x1032u); }
+POA_D unsigned p_lolo(unsigned a, unsigned b) { return __byte_perm(a, b, 0x5410u); }
+#endif
+
+constexpr int P16_CW = 256;          // columns per chunk
+constexpr int P16_CPB = 512;         // bytes per chunk-plane
+
+// address of cell (plane, j) of a row stored in the chunked layout; pm = {first chunk-plane of the row, beg, end, _}
+POA_D const short *cell_ptr16(const Ws &w, const int4 &pm, int plane, int j) {
+    const int cb = pm.y >> 8, nch = (pm.z >> 8) - cb + 1;
+    const int u = j & 255;
+    return reinterpret_cast<const short *>(w.slab) + ((long long)pm.x + (long long)plane * nch + ((j >> 8) - cb)) * 256 + ((u & 127) << 1) + (u >> 7);
+}
+
+POA_D uint4 p16_ld(const char *p) { return *reinterpret_cast<const uint4 *>(p); }
+POA_D void p16_st(char *p, unsigned a, unsigned b, unsigned c, unsigned d) {
+    uint4 u; u.x = a; u.y = b; u.z = c; u.w = d;
+    *reinterpret_cast<uint4 *>(p) = u;
+}
+
+// Can this alignment run in packed 16-bit arithmetic without any intermediate leaving the int16 range?
+// (scores <= qlen*match; the scan adds at most e*256 of position offset on top.)
+POA_D bool p16_eligible(const DevParams &P, int qlen) {
+    const int emax = imax(P.e1, P.e2);
+    return P.p16_ok && (long long)qlen * P.match + (long long)emax * (P16_CW + 8) + 64 <= 32767;
+}
+
+template <int NW>
+POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, long long slab_bytes) {
+    Ws &w = sh.ws;
+    const int lane = poa_tid();
+    const int n_node = sh.n_node;
+    const int rows = n_node - 1;  // the sink row is never filled
+    const int inf_min = inf_min_of<short>(P);
+    const int pn = P.pn16;
+    const int local = P.local;
+    const int wb = local ? -1 : P.wb;  // abpoa_align.c:158
+#ifdef POA_HOST_EMU
+    const int bw = wb < 0 ? qlen : wb + (int)(P.wf * qlen);  // abpoa_align_simd.c:474
+#else
+    const int bw = wb < 0 ? qlen : wb + (int)__fmul_rn(P.wf, (float)qlen);
+#endif
+    const int e1 = P.e1, e2 = P.e2, oe1 = P.oe1, oe2 = P.oe2;
+    // workspace pointers: read once from shared memory and told to be global so the hot loop uses LDG/STG
+    char *const slab = w.slab, *const qp = w.qp;
+    const int4 *const rowinfo = w.rowinfo;
+    int4 *const rowmeta = w.rowmeta;
+    const int *const pool_row = w.pool_row, *const rr = w.rr;
+    int *const mplr = w.mplr, *const mprr = w.mprr;
+    const uint8_t *const rbase = w.rbase;
+#ifndef POA_HOST_EMU
+    __builtin_assume(__isGlobal(slab)); __builtin_assume(__isGlobal(qp)); __builtin_assume(__isGlobal(rowinfo));
+    __builtin_assume(__isGlobal(rowmeta)); __builtin_assume(__isGlobal(pool_row)); __builtin_assume(__isGlobal(rr));
+    __builtin_assume(__isGlobal(mplr)); __builtin_assume(__isGlobal(mprr)); __builtin_assume(__isGlobal(rbase));
+    __builtin_assume(__isGlobal(q));
+#endif
+    const long long slab_units = slab_bytes / P16_CPB;
+    long long used = 0, inband = 0, edge_rows = 0;
+
+    // packed constants
+    const int emax = imax(e1, e2);
+    const int negl = -32768 + 8 * emax + 8;  // below every value a band cell can take, never wraps when used
+    const unsigned INFP = p_pack(inf_min, inf_min), NEGLP = p_pack(negl, negl), ZERO = 0u;
+    const unsigned NOE1 = p_pack(-oe1, -oe1), NOE2 = p_pack(-oe2, -oe2), NE1 = p_pack(-e1, -e1), NE2 = p_pack(-e2, -e2);
+    const unsigned NE1_2 = p_pack(-2 * e1, -2 * e1), NE1_3 = p_pack(-3 * e1, -3 * e1);
+    const unsigned NE2_2 = p_pack(-2 * e2, -2 * e2), NE2_3 = p_pack(-3 * e2, -3 * e2);
+    const unsigned OFF1 = p_pack(e1 * 4 * (lane + 1), e1 * 4 * (lane + 33)), NOFF1 = p_pack(-e1 * 4 * lane, -e1 * 4 * (lane + 32));
+    const unsigned OFF2 = p_pack(e2 * 4 * (lane + 1), e2 * 4 * (lane + 33)), NOFF2 = p_pack(-e2 * 4 * lane, -e2 * 4 * (lane + 32));
+    const unsigned NCW1 = p_pack(-e1 * P16_CW, -e1 * P16_CW), NCW2 = p_pack(-e2 * P16_CW, -e2 * P16_CW);
+    const int f0_1 = imax(inf_min - oe1, inf_min - e1), f0_2 = imax(inf_min - oe2, inf_min - e2);
+
+    // ---- query profile in the chunked layout: qp[base][chunk][lane] (abpoa_align_simd.c:531-546)
+    const int nchq = (qlen >> 8) + 1;
+    for (int b = 0; b < 5; ++b)
+        for (int c = 0; c < nchq; ++c) {
+            unsigned v[4];
+            for (int r = 0; r < 4; ++r) {
+                const int jl = c * P16_CW + lane * 4 + r, jh = jl + 128;
+                const int sl = (jl == 0 || jl > qlen) ? 0 : P.mat[b * 5 + q[jl - 1]];
+                const int s2 = jh > qlen ? 0 : P.mat[b * 5 + q[jh - 1]];
+                v[r] = p_pack(sl, s2);
+            }
+            p16_st(qp + ((long long)(b * nchq + c)) * P16_CPB + lane * 16, v[0], v[1], v[2], v[3]);
+        }
+
+    // ---- row 0 (abpoa_align_simd.c:617-688)
+    {
+        int end0;
+        if (wb >= 0) {
+            if (lane == 0) {
+                mplr[0] = 0; mprr[0] = 0;
+                const int4 ri = rowinfo[0];
+                for (int k = 0; k < ri.w; ++k) { int o = pool_row[ri.z + k]; mplr[o] = 1; mprr[o] = 1; }
+            }
+            end0 = imin(qlen, imax(0, rr[0]) + bw);
+        } else end0 = qlen;
+        const int nch = (end0 >> 8) + 1;
+        if (5LL * nch > slab_units) { if (lane == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+        if (lane == 0) rowmeta[0] = poa_make_int4(0, 0, end0, 0);
+        for (int c = 0; c < nch; ++c) {
+            unsigned v[5][4];
+            for (int r = 0; r < 4; ++r) {
+                int x[2][5];
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int j = c * P16_CW + hf * 128 + lane * 4 + r;
+                    int *y = x[hf];
+                    if (j > end0) { y[0] = y[1] = y[2] = y[3] = y[4] = inf_min; }
+                    else if (local) { y[0] = y[1] = y[2] = y[3] = y[4] = 0; }
+                    else if (j == 0) { y[0] = 0; y[1] = -oe1; y[2] = -oe2; y[3] = y[4] = inf_min; }
+                    else { y[3] = -P.o1 - e1 * j; y[4] = -P.o2 - e2 * j; y[0] = imax((int)(short)y[3], (int)(short)y[4]); y[1] = y[2] = inf_min; }
+                }
+                for (int p = 0; p < 5; ++p) v[p][r] = p_pack(x[0][p], x[1][p]);
+            }
+            for (int p = 0; p < 5; ++p)
+                p16_st(slab + ((long long)p * nch + c) * P16_CPB + lane * 16, v[p][0], v[p][1], v[p][2], v[p][3]);
+        }
+        used = 5LL * nch;
+        inband += end0 + 1;
+        sync_block<NW>();
+    }
+    int best_score = inf_min, best_i = 0, best_j = 0;
+
+    // ---- rows in index order (abpoa_align_simd.c:1205-1221)
+    for (int i = 1; i < rows; ++i) {
+        const int4 ri = rowinfo[i];  // {in_off, in_n, out_off, out_n}
+        const int rb = rbase[i];
+        int beg, end;
+        if (wb < 0) { beg = 0; end = qlen; }
+        else {  // abpoa_align.h:34-35, abpoa_align_simd.c:946-960
+            const int r = rr[i];
+            beg = imax(0, imin(mplr[i], r) - bw);
+            end = imin(qlen, imax(mprr[i], r) + bw);
+            const int beg_sn = beg / pn;
+            int min_pre_beg = INT_MAX, min_pre_beg_sn = INT_MAX;
+            for (int k = 0; k < ri.y; ++k) {
+                const int pb = rowmeta[pool_row[ri.x + k]].y;
+                if (min_pre_beg > pb) { min_pre_beg = pb; min_pre_beg_sn = pb / pn; }
+            }
+            if (beg_sn < min_pre_beg_sn) beg = min_pre_beg;
+        }
+        if (end < beg) end = beg;
+        const int cb = beg >> 8, ce = end >> 8, nch = ce - cb + 1;
+        if (used + 5LL * nch > slab_units) { if (lane == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+        const long long roff = used;
+        used += 5LL * nch;
+        inband += end - beg + 1;
+        edge_rows += (long long)ri.y * (end - beg + 1);
+
+        // F entering column cb*256 such that F[beg] comes out as f0 (cells left of beg are masked to inf_min)
+        unsigned carry1 = p_pack(f0_1 + e1 * (beg - cb * P16_CW), f0_1 + e1 * (beg - cb * P16_CW));
+        unsigned carry2 = p_pack(f0_2 + e2 * (beg - cb * P16_CW), f0_2 + e2 * (beg - cb * P16_CW));
+        int rmx = INT_MIN, left = -1, right = -1;
+        const char *qrow = qp + (long long)rb * nchq * P16_CPB + lane * 16;
+
+        for (int c = cb; c <= ce; ++c) {
+            const int c0 = c * P16_CW;
+            unsigned M0 = INFP, M1 = INFP, M2 = INFP, M3 = INFP;
+            unsigned A0 = INFP, A1 = INFP, A2 = INFP, A3 = INFP;  // E1 in
+            unsigned B0 = INFP, B1 = INFP, B2 = INFP, B3 = INFP;  // E2 in
+            for (int k = 0; k < ri.y; ++k) {  // predecessors in in_id order (abpoa_align_simd.c:966-1029)
+                const int4 pm = rowmeta[pool_row[ri.x + k]];
+                const int pcb = pm.y >> 8, pce = pm.z >> 8;
+                if (c < pcb || c > pce + 1) continue;
+                const long long pnb = (long long)(pce - pcb + 1) * P16_CPB;
+                const char *ph = slab + ((long long)pm.x + (c - pcb)) * P16_CPB;
+                int prevlast = inf_min;  // H_p[c0 - 1]: the last halfword of the previous chunk-plane
+                if (c > pcb) prevlast = *reinterpret_cast<const short *>(ph - 2);
+                if (c <= pce) {
+                    const uint4 h = p16_ld(ph + lane * 16), a = p16_ld(ph + pnb + lane * 16), b = p16_ld(ph + 2 * pnb + lane * 16);
+                    const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
+                    const unsigned s0 = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot;
+                    M0 = p_max(M0, s0); M1 = p_max(M1, h.x); M2 = p_max(M2, h.y); M3 = p_max(M3, h.z);
+                    A0 = p_max(A0, a.x); A1 = p_max(A1, a.y); A2 = p_max(A2, a.z); A3 = p_max(A3, a.w);
+                    B0 = p_max(B0, b.x); B1 = p_max(B1, b.y); B2 = p_max(B2, b.z); B3 = p_max(B3, b.w);
+                } else if (lane == 0) {
+                    M0 = p_max(M0, p_pack(prevlast, inf_min));
+                }
+            }
+            if (local && c == 0 && lane == 0) M0 = p_max(M0, p_pack(0, inf_min));  // abpoa_align_simd.c:974 (`first` = 0)
+            // H~ = max(M + profile, E1, E2) (abpoa_align_simd.c:1032-1050)
+            const uint4 qv = p16_ld(qrow + (long long)c * P16_CPB);
+            unsigned H0 = p_max3(p_add(M0, qv.x), A0, B0), H1 = p_max3(p_add(M1, qv.y), A1, B1);
+            unsigned H2 = p_max3(p_add(M2, qv.z), A2, B2), H3 = p_max3(p_add(M3, qv.w), A3, B3);
+            // cells of this chunk outside [beg,end]
+            const bool bnd = (c == cb && beg > c0) || (c == ce && end < c0 + P16_CW - 1);
+            unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+            if (bnd) {
+                const int brel = imax(beg - c0, 0), erel = imin(end - c0, P16_CW - 1);
+                const unsigned da = p_pack(lane * 4 - brel, 128 + lane * 4 - brel), db = p_pack(erel - lane * 4, erel - 128 - lane * 4);
+                m0 = p_signmask(p_min(da, db));
+                m1 = p_signmask(p_min(p_add(da, 0x00010001u), p_add(db, 0xffffffffu)));
+                m2 = p_signmask(p_min(p_add(da, 0x00020002u), p_add(db, 0xfffefffeu)));
+                m3 = p_signmask(p_min(p_add(da, 0x00030003u), p_add(db, 0xfffdfffdu)));
+                H0 = (H0 & ~m0) | (INFP & m0); H1 = (H1 & ~m1) | (INFP & m1);
+                H2 = (H2 & ~m2) | (INFP & m2); H3 = (H3 & ~m3) | (INFP & m3);
+            }
+            // horizontal gaps (abpoa_align_simd.c:1052-1059): per-lane chains, lane-half scan, fix-up
+            unsigned F10, F11, F12, F13, F20, F21, F22, F23;
+            {
+                const unsigned l1 = p_add(H0, NOE1), l2 = p_addmax(l1, NE1, p_add(H1, NOE1)), l3 = p_addmax(l2, NE1, p_add(H2, NOE1));
+                const unsigned lout = p_addmax(l3, NE1, p_add(H3, NOE1));
+                const unsigned k1 = p_add(H0, NOE2), k2 = p_addmax(k1, NE2, p_add(H1, NOE2)), k3 = p_addmax(k2, NE2, p_add(H2, NOE2));
+                const unsigned kout = p_addmax(k3, NE2, p_add(H3, NOE2));
+                unsigned g1 = p_add(lout, OFF1), g2 = p_add(kout, OFF2);
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned u1 = (unsigned)poa_shfl_up((int)g1, d), u2 = (unsigned)poa_shfl_up((int)g2, d);
+                    g1 = p_max(g1, u1); g2 = p_max(g2, u2);  // lanes < d get their own value back: a no-op
+                }
+                unsigned x1 = (unsigned)poa_shfl_up((int)g1, 1), x2 = (unsigned)poa_shfl_up((int)g2, 1);
+                const unsigned t1 = (unsigned)poa_shfl((int)g1, 31), t2 = (unsigned)poa_shfl((int)g2, 31);
+                if (lane == 0) { x1 = NEGLP; x2 = NEGLP; }
+                x1 = p_max3(x1, p_lolo(NEGLP, t1), carry1);  // high halves continue after all low halves
+                x2 = p_max3(x2, p_lolo(NEGLP, t2), carry2);
+                const unsigned fin1 = p_add(x1, NOFF1), fin2 = p_add(x2, NOFF2);
+                carry1 = p_add(p_max3(t1, p_swap(t1), carry1), NCW1);
+                carry2 = p_add(p_max3(t2, p_swap(t2), carry2), NCW2);
+                F10 = fin1; F11 = p_addmax(fin1, NE1, l1); F12 = p_addmax(fin1, NE1_2, l2); F13 = p_addmax(fin1, NE1_3, l3);
+                F20 = fin2; F21 = p_addmax(fin2, NE2, k1); F22 = p_addmax(fin2, NE2_2, k2); F23 = p_addmax(fin2, NE2_3, k3);
+            }
+            // H, new E (abpoa_align_simd.c:1060-1071)
+            H0 = p_max3(H0, F10, F20); H1 = p_max3(H1, F11, F21); H2 = p_max3(H2, F12, F22); H3 = p_max3(H3, F13, F23);
+            if (local) { H0 = p_max(H0, ZERO); H1 = p_max(H1, ZERO); H2 = p_max(H2, ZERO); H3 = p_max(H3, ZERO); }
+            A0 = p_addmax(A0, NE1, p_add(H0, NOE1)); A1 = p_addmax(A1, NE1, p_add(H1, NOE1));
+            A2 = p_addmax(A2, NE1, p_add(H2, NOE1)); A3 = p_addmax(A3, NE1, p_add(H3, NOE1));
+            B0 = p_addmax(B0, NE2, p_add(H0, NOE2)); B1 = p_addmax(B1, NE2, p_add(H1, NOE2));
+            B2 = p_addmax(B2, NE2, p_add(H2, NOE2)); B3 = p_addmax(B3, NE2, p_add(H3, NOE2));
+            if (local) {
+                A0 = p_max(A0, ZERO); A1 = p_max(A1, ZERO); A2 = p_max(A2, ZERO); A3 = p_max(A3, ZERO);
+                B0 = p_max(B0, ZERO); B1 = p_max(B1, ZERO); B2 = p_max(B2, ZERO); B3 = p_max(B3, ZERO);
+            }
+            if (bnd) {
+                H0 = (H0 & ~m0) | (INFP & m0); H1 = (H1 & ~m1) | (INFP & m1); H2 = (H2 & ~m2) | (INFP & m2); H3 = (H3 & ~m3) | (INFP & m3);
+                A0 = (A0 & ~m0) | (INFP & m0); A1 = (A1 & ~m1) | (INFP & m1); A2 = (A2 & ~m2) | (INFP & m2); A3 = (A3 & ~m3) | (INFP & m3);
+                B0 = (B0 & ~m0) | (INFP & m0); B1 = (B1 & ~m1) | (INFP & m1); B2 = (B2 & ~m2) | (INFP & m2); B3 = (B3 & ~m3) | (INFP & m3);
+            }
+            char *dst = slab + (roff + (c - cb)) * P16_CPB + lane * 16;
+            const long long pstride = (long long)nch * P16_CPB;
+            p16_st(dst, H0, H1, H2, H3); p16_st(dst + pstride, A0, A1, A2, A3); p16_st(dst + 2 * pstride, B0, B1, B2, B3);
+            p16_st(dst + 3 * pstride, F10, F11, F12, F13); p16_st(dst + 4 * pstride, F20, F21, F22, F23);
+            // row maximum with first / last arg-max (abpoa_align_simd.c:1107-1119)
+            if (local || wb >= 0) {
+                const unsigned cm = p_max(p_max3(H0, H1, H2), H3);
+                const int cmx = poa_redux_max(imax(p_lo(cm), p_hi(cm)));
+                if (cmx >= rmx) {  // uniform
+                    const unsigned pat = p_pack(cmx, cmx);
+                    const int jl = c0 + lane * 4, jh = jl + 128;
+                    const unsigned x0 = H0 ^ pat, x1 = H1 ^ pat, x2 = H2 ^ pat, x3 = H3 ^ pat;
+                    int first = INT_MAX, last = -1;
+                    // lowest column first: low halves 0..3, then high halves 0..3
+                    if ((x0 & 0xffffu) == 0) first = jl; else if ((x1 & 0xffffu) == 0) first = jl + 1;
+                    else if ((x2 & 0xffffu) == 0) first = jl + 2; else if ((x3 & 0xffffu) == 0) first = jl + 3;
+                    else if ((x0 >> 16) == 0) first = jh; else if ((x1 >> 16) == 0) first = jh + 1;
+                    else if ((x2 >> 16) == 0) first = jh + 2; else if ((x3 >> 16) == 0) first = jh + 3;
+                    // highest column first: high halves 3..0, then low halves 3..0
+                    if ((x3 >> 16) == 0) last = jh + 3; else if ((x2 >> 16) == 0) last = jh + 2;
+                    else if ((x1 >> 16) == 0) last = jh + 1; else if ((x0 >> 16) == 0) last = jh;
+                    else if ((x3 & 0xffffu) == 0) last = jl + 3; else if ((x2 & 0xffffu) == 0) last = jl + 2;
+                    else if ((x1 & 0xffffu) == 0) last = jl + 1; else if ((x0 & 0xffffu) == 0) last = jl;
+                    const int gl = poa_redux_min(first), gr = poa_redux_max(last);
+                    if (cmx > rmx) { rmx = cmx; left = gl; right = gr; } else right = gr;
+                }
+            }
+        }
+        if (lane == 0) rowmeta[i] = poa_make_int4((int)roff, beg, end, 0);
+        if (local || wb >= 0) {
+            if (local && rmx > best_score) { best_score = rmx; best_i = i; best_j = left; }  // abpoa_align_simd.c:1208-1210
+            if (wb >= 0) {  // abpoa_align_simd.c:1121-1130
+                for (int k = lane; k < ri.w; k += POA_WARP) {
+                    const int o = pool_row[ri.z + k];
+                    if (right + 1 > mprr[o]) mprr[o] = right + 1;
+                    if (left + 1 < mplr[o]) mplr[o] = left + 1;
+                }
+            }
+        }
+        sync_block<NW>();
+    }
+    // ---- global best (abpoa_align_simd.c:1092-1105)
+    if (lane == 0) {
+        if (!local) {
+            const int4 ri = rowinfo[rows];  // sink row
+            for (int k = 0; k < ri.y; ++k) {
+                const int pi = pool_row[ri.x + k];
+                const int4 pm = rowmeta[pi];
+                const int e = qlen > pm.z ? pm.z : qlen;
+                const int sc = *cell_ptr16(w, pm, 0, e);
+                if (sc > best_score) { best_score = sc; best_i = pi; best_j = e; }
+            }
+        }
+        sh.best_score = best_score; sh.best_i = best_i; sh.best_j = best_j;
+        sh.inband += inband; sh.edge_rows += edge_rows;
+    }
+    sync_block<NW>();
+}
+
+#endif  // POA_WARP == 32

@@ -30,6 +30,12 @@ inline void build_params(const poa_b200_params_t &p, const poa_b200_engine_opts_
     d.out_cons = p.out_cons ? 1 : 0; d.out_msa = p.out_msa ? 1 : 0;
     d.pn16 = 32; d.pn32 = 16;
     d.emit_cigar = o.emit_cigar ? 1 : 0;
+    // packed 16-bit fill (poa_fill16.cuh): every intermediate must stay inside int16, i.e. the slack abPOA
+    // builds into inf_min (512 * max(e1,e2), abpoa_align_simd.c:1295) must cover one mismatch, one gap open
+    // and the scan's position offsets
+    const long long emax = std::max(d.e1, d.e2);
+    d.p16_ok = (o.flags & 1) == 0 && emax >= 1 && emax <= 100 && 240 * emax >= (long long)d.min_mis + std::max(d.oe1, d.oe2) + 64
+               && d.oe1 > d.e1 && d.oe2 > d.e2;
 }
 
 inline int check_params(const poa_b200_params_t &p) {
@@ -71,7 +77,8 @@ inline void make_layout(WsLayout &L, long long nmax, long long max_bases, long l
     L.o_cig = take(8LL * L.cig_cap);
     L.o_path = take(4 * std::max<long long>(max_bases, 1));
     L.o_best = take(4 * std::max<long long>(max_seq, 1)); L.o_ncig = take(4 * std::max<long long>(max_seq, 1));
-    L.slab_bytes = align_up(slab_bytes, 256);
+    L.o_qp = take(5 * ((max_len >> 8) + 2) * 512);
+    L.slab_bytes = align_up(slab_bytes, 512);
     L.o_slab = take(L.slab_bytes);
     L.stride = o;
 }

@@ -51,7 +51,7 @@ def make_params(match=1, mismatch=4, gap_open1=6, gap_ext1=2, gap_open2=26, gap_
 
 class EngineOpts(C.Structure):
     _fields_ = [("warps_per_block", C.c_int32), ("ctas_per_sm", C.c_int32), ("emit_cigar", C.c_int32),
-                ("reserved0", C.c_int32), ("slab_rows_factor", C.c_double), ("device_mem_budget", C.c_int64)]
+                ("flags", C.c_int32), ("slab_rows_factor", C.c_double), ("device_mem_budget", C.c_int64)]
 
 
 class _BlockView(C.Structure):
@@ -286,10 +286,10 @@ class PoaEngine:
     """One engine per GPU (one process per GPU in the multi-GPU driver)."""
 
     def __init__(self, device: int = 0, warps_per_block: int = 0, ctas_per_sm: int = 0, emit_cigar: bool = False,
-                 slab_rows_factor: float = 0.0, device_mem_budget: int = 0):
+                 slab_rows_factor: float = 0.0, device_mem_budget: int = 0, flags: int = 0):
         self._h = None
         self._lib = load_library()
-        opts = EngineOpts(warps_per_block, ctas_per_sm, int(emit_cigar), 0, slab_rows_factor, device_mem_budget)
+        opts = EngineOpts(warps_per_block, ctas_per_sm, int(emit_cigar), flags, slab_rows_factor, device_mem_budget)
         h = C.c_void_p()
         _check(self._lib, self._lib.poa_b200_engine_create(device, C.byref(opts), C.byref(h)))
         self._h = h

@@ -21,6 +21,52 @@ int set_err(int code, const std::string &msg) { fprintf(stderr, "[emu] %s\n", ms
 }
 using namespace poa;
 
+#if POA_EMU_LANES > 1
+// ---- 32 lock-step lanes as fibers: a collective publishes the lane's value and yields until all lanes arrived.
+#include <ucontext.h>
+#include <functional>
+namespace poa_emu {
+static const int NL = POA_EMU_LANES;
+static ucontext_t g_main, g_ctx[NL];
+static int g_cur = 0, g_done[NL];
+static long long g_gen[NL], g_arrivals = 0;
+static int g_buf[2][NL];
+static std::function<void()> g_body;
+int lane() { return g_cur; }
+static void yield_to_main() { swapcontext(&g_ctx[g_cur], &g_main); }
+void xchg(int v, int *all) {
+    const int me = g_cur;
+    const long long gen = g_gen[me]++;
+    g_buf[gen & 1][me] = v;
+    ++g_arrivals;
+    while (g_arrivals < (long long)NL * (gen + 1)) yield_to_main();
+    for (int i = 0; i < NL; ++i) all[i] = g_buf[gen & 1][i];
+}
+static void trampoline() { g_body(); g_done[g_cur] = 1; yield_to_main(); }
+static void run_warp(std::function<void()> body) {
+    static std::vector<char> stacks;
+    const size_t SS = 1 << 20;
+    stacks.assign(SS * NL, 0);
+    g_body = body; g_arrivals = 0;
+    for (int i = 0; i < NL; ++i) {
+        g_done[i] = 0; g_gen[i] = 0;
+        getcontext(&g_ctx[i]);
+        g_ctx[i].uc_stack.ss_sp = stacks.data() + SS * i; g_ctx[i].uc_stack.ss_size = SS; g_ctx[i].uc_link = &g_main;
+        makecontext(&g_ctx[i], trampoline, 0);
+    }
+    for (;;) {
+        int alive = 0;
+        long long before = g_arrivals;
+        int finished_before = 0; for (int i = 0; i < NL; ++i) finished_before += g_done[i];
+        for (int i = 0; i < NL; ++i) if (!g_done[i]) { ++alive; g_cur = i; swapcontext(&g_main, &g_ctx[i]); }
+        if (!alive) break;
+        int finished_after = 0; for (int i = 0; i < NL; ++i) finished_after += g_done[i];
+        if (g_arrivals == before && finished_after == finished_before) { fprintf(stderr, "[emu] divergent collective: lanes deadlocked\n"); abort(); }
+    }
+}
+}  // namespace poa_emu
+#endif
+
 extern "C" void emu_free(void *p) { free(p); }
 
 // Same run, but returns the product's wire format: HDR_WORDS header words followed by the arena words
@@ -45,12 +91,13 @@ extern "C" int32_t *emu_poa_block(const pd_params_t *pp, int n_seq, const int32_
     if (check_params(p)) return nullptr;
     poa_b200_engine_opts_t opts; memset(&opts, 0, sizeof(opts));
     opts.emit_cigar = instrument ? 1 : 0;
+    if (getenv("POA_EMU_NO_P16")) opts.flags = 1;
     DevParams dp; build_params(p, opts, dp);
     long long tot = 0, max_len = 1;
     for (int i = 0; i < n_seq; ++i) { tot += seq_len[i]; if (seq_len[i] > max_len) max_len = seq_len[i]; }
     const char *lvl = getenv("POA_EMU_TIGHT");
     long long nmax = std::max<long long>(std::max<long long>(tot + 2, n_seq + 2), 1024);
-    long long slab = nmax * ((max_len + 1) / 8 + 2) * 5 * 32;
+    long long slab = nmax * std::max<long long>(((max_len + 1) / 8 + 2) * 5 * 32, ((max_len + 1) / 256 + 2) * 2560);
     long long growth = 8 * (tot + n_seq) + 64;
     if (lvl) { nmax = std::max<long long>(atoll(lvl), max_len + 2); slab = slab / 64; growth = 64; }
     WsLayout L;
@@ -69,7 +116,12 @@ extern "C" int32_t *emu_poa_block(const pd_params_t *pp, int n_seq, const int32_
     DevOut O; O.hdr = hdr.data(); O.arena = arena.data(); O.arena_used = &used; O.arena_cap = (unsigned long long)cap; O.phase = phase; O.counter = &counter;
     Shared sh; memset(&sh, 0, sizeof(sh));
     ws_bind(sh.ws, wsp, L);
+#if POA_EMU_LANES > 1
+    poa_emu::run_warp([&]() { poa_block<1>(sh, dp, B, L, O, 0); });
+#else
     poa_block<1>(sh, dp, B, L, O, 0);
+#endif
+    if (getenv("POA_EMU_VERBOSE")) fprintf(stderr, "[emu] packed-16 alignments: %llu of %d\n", phase[PH_SPARE], n_seq > 0 ? n_seq - 1 : 0);
     if (hdr[H_STATUS] != ST_OK) { fprintf(stderr, "[emu] block status %d\n", hdr[H_STATUS]); *n_out = -hdr[H_STATUS]; return nullptr; }
     if (g_want_wire) {
         int32_t *out = (int32_t *)malloc(sizeof(int32_t) * (HDR_WORDS + used + 1));

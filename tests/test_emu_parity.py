@@ -24,7 +24,7 @@ CASES = load_cases()
 @pytest.fixture(scope="module")
 def emu():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    deps = [SRC, os.path.join(HERE, "..", "smoothxg_b200", "csrc", "poa_core.cuh"), os.path.join(HERE, "..", "smoothxg_b200", "csrc", "poa_host.hpp")]
+    deps = [SRC] + [os.path.join(HERE, "..", "smoothxg_b200", "csrc", f) for f in ("poa_core.cuh", "poa_fill16.cuh", "poa_host.hpp")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         inc = "/usr/local/cuda/include"
         subprocess.check_call(["/usr/bin/g++", "-O1", "-fPIC", "-shared", "-std=c++17", f"-I{inc}", "-o", OUT, SRC])
@@ -32,6 +32,36 @@ def emu():
     chk = _Checker(lib, "emu_poa_block", "emu_free")
     wire = _Checker(lib, "emu_poa_block_wire", "emu_free")
     return chk, wire
+
+
+OUT32 = os.path.join(HERE, "emu", "_build", "libpoa_emu32.so")
+# cases the 32-lane emulation runs in the default CPU suite (the rest: POA_EMU32_ALL=1)
+FAST32 = {"abpoa_seq_fa_global", "abpoa_seq_fa_local", "abpoa_test_fa", "abpoa_example_c", "edge_shapes", "edge_shapes_local",
+          "syn_local", "syn_unbanded", "syn_presets", "syn_divergent"}
+
+
+@pytest.fixture(scope="module")
+def emu32():
+    """The same device code with 32 lock-step lanes emulated as fibers (-DPOA_EMU_LANES=32): exercises the
+    warp-level logic -- shuffle scans, reductions, the lane-striped packed 16-bit fill of poa_fill16.cuh."""
+    os.makedirs(os.path.dirname(OUT32), exist_ok=True)
+    csrc = os.path.join(HERE, "..", "smoothxg_b200", "csrc")
+    deps = [SRC] + [os.path.join(csrc, f) for f in ("poa_core.cuh", "poa_fill16.cuh", "poa_host.hpp")]
+    if not os.path.exists(OUT32) or any(os.path.getmtime(d) > os.path.getmtime(OUT32) for d in deps):
+        subprocess.check_call(["/usr/bin/g++", "-O1", "-fPIC", "-shared", "-std=c++17", "-DPOA_EMU_LANES=32",
+                               "-I/usr/local/cuda/include", "-o", OUT32, SRC])
+    return _Checker(C.CDLL(OUT32), "emu_poa_block", "emu_free")
+
+
+@pytest.mark.parametrize("name,batch,p,dumps", CASES, ids=[c[0] for c in CASES])
+def test_emulated_warp_logic_matches_golden(emu32, name, batch, p, dumps):
+    if name not in FAST32 and not os.environ.get("POA_EMU32_ALL"):
+        pytest.skip("slow under the fiber emulation; set POA_EMU32_ALL=1")
+    for b in range(batch.n_blocks):
+        got = emu32.poa_block(pd_params(p), *batch.block(b))
+        assert got is not None
+        assert np.array_equal(got.compare_part(), dumps[b].compare_part()), f"{name} block {b}"
+        assert got.edge_rows == dumps[b].edge_rows
 
 
 @pytest.mark.parametrize("name,batch,p,dumps", CASES, ids=[c[0] for c in CASES])
