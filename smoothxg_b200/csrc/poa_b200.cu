@@ -24,8 +24,11 @@ using namespace poa;
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
+#ifndef POA_MIN_BLOCKS
+#define POA_MIN_BLOCKS 12  // resident single-warp POA blocks per SM the register budget is sized for
+#endif
 template <int NW>
-__global__ void __launch_bounds__(NW * 32) poa_b200_block_kernel(DevParams P, DevBatch B, WsLayout L, char *ws_base, DevOut O) {
+__global__ void __launch_bounds__(NW * 32, POA_MIN_BLOCKS / NW) poa_b200_block_kernel(DevParams P, DevBatch B, WsLayout L, char *ws_base, DevOut O) {
     __shared__ Shared sh;
     if (threadIdx.x == 0) ws_bind(sh.ws, ws_base + (long long)blockIdx.x * L.stride, L);
     for (;;) {

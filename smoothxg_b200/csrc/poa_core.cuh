@@ -132,7 +132,7 @@ struct WsLayout {
     long long o_base, o_aln_n, o_aln, o_in_off, o_in_n, o_out_off, o_out_n, o_pool_id, o_pool_w, o_pool_row;
     long long o_idx2id, o_id2idx, o_remain, o_tmp0, o_tmp1, o_tmp2, o_tmp3;
     long long o_rowinfo, o_rowmeta, o_rbase, o_rr, o_mplr, o_mprr;
-    long long o_cig, o_path, o_best, o_ncig, o_qp, o_slab;
+    long long o_cig, o_path, o_best, o_ncig, o_plen, o_qp, o_slab;
     long long slab_bytes;
     int nmax;      // node capacity
     int pool_cap;  // edge pool capacity (entries)
@@ -155,7 +155,7 @@ struct Ws {
     int4 *rowinfo, *rowmeta;
     int *rr, *mplr, *mprr;
     unsigned long long *cig;
-    int *path, *best, *ncig;
+    int *path, *best, *ncig, *plen;
     char *qp;    // query profile of the alignment in flight, chunked layout (poa_fill16.cuh)
     char *slab;
 };
@@ -176,6 +176,11 @@ struct Shared {
     int bcast[4];
 };
 
+#ifdef POA_HOST_EMU
+static inline int p_ctz32(unsigned x) { return __builtin_ctz(x); }
+#else
+POA_D int p_ctz32(unsigned x) { return __ffs((int)x) - 1; }
+#endif
 POA_D int imax(int a, int b) { return a > b ? a : b; }
 POA_D int imin(int a, int b) { return a < b ? a : b; }
 
@@ -322,6 +327,102 @@ POA_DN void toposort(Shared &sh, int banded) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Global alignment: row order maintained incrementally instead of re-running the BFS.
+//
+// abpoa_topological_sort (abpoa_graph.c:322-357) recomputes a BFS order of the whole graph after every
+// read; a single-thread pointer chase that is pure latency on a GPU.  In global mode the DP result does
+// not depend on WHICH topological order the rows are evaluated in: band limits are min/max
+// accumulations over predecessors (abpoa_align_simd.c:1121-1130), `remain` is a property of the graph,
+// the best cell and the traceback walk edge lists in in_id order, never row order.  (Local mode breaks
+// score ties by BFS index, abpoa_align_simd.c:1208-1210, so it keeps the exact BFS.)  So the order is kept
+// as an invariant: topological, aligned groups contiguous.  A fused read visits old nodes in increasing
+// order; a node it creates is placed right behind the aligned group of the old node it follows (insertion)
+// or is aligned with (mismatch) -- fuse() records that old node in anc[].  New positions are old position +
+// number of insertions in front: one histogram, one block-wide prefix sum, no serial walk.
+// `remain` (abpoa_graph.c:268-309: edges to the sink along heaviest out-edges) is pointer jumping.
+// ------------------------------------------------------------------------------------------------
+template <int NW>
+POA_D int block_any(Shared &sh, int pred) {
+    unsigned b = poa_ballot(pred);
+    if (NW == 1) return b != 0;
+    const int tid = poa_tid();
+    sync_block<NW>();
+    if (tid == 0) sh.bcast[0] = 0;
+    sync_block<NW>();
+    if (b != 0 && (tid % POA_WARP) == 0) poa_atomic_add(&sh.bcast[0], 1);
+    sync_block<NW>();
+    const int r = sh.bcast[0];
+    sync_block<NW>();
+    return r != 0;
+}
+
+template <int NW> POA_D int block_excl_scan(Shared &sh, const int *src, int *dst, int n, int *scratch);
+
+template <int NW>
+POA_DN void toposort_incr(Shared &sh, int banded, int n_old) {
+    constexpr int NT = NW * POA_WARP;
+    Ws &w = sh.ws;
+    const int tid = poa_tid();
+    const int n = sh.n_node, n_new = n - n_old;
+    // abpoa_graph.c:192-219: exchange sort by weight, strict <, not stable; one node per thread
+    for (int v = tid; v < n; v += NT) {
+        for (int side = 0; side < 2; ++side) {
+            int cnt = side ? w.out_n[v] : w.in_n[v];
+            int off = side ? w.out_off[v] : w.in_off[v];
+            for (int j = 0; j < cnt - 1; ++j)
+                for (int k = j + 1; k < cnt; ++k)
+                    if (w.pool_w[off + j] < w.pool_w[off + k]) {
+                        int t = w.pool_id[off + j]; w.pool_id[off + j] = w.pool_id[off + k]; w.pool_id[off + k] = t;
+                        t = w.pool_w[off + j]; w.pool_w[off + j] = w.pool_w[off + k]; w.pool_w[off + k] = t;
+                    }
+        }
+    }
+    if (n_new > 0) {
+        int *hist = w.tmp0, *anc = w.tmp2, *apos = w.tmp3;
+        for (int i = tid; i < n_old; i += NT) hist[i] = 0;
+        sync_block<NW>();
+        for (int k = tid; k < n_new; k += NT) {  // position of the last member of the followed group, old order
+            const int x = anc[k];
+            int ge = w.id2idx[x];
+            const int an = w.aln_n[x];
+            for (int j = 0; j < an; ++j) { const int m = w.aln[4 * x + j]; if (m < n_old) ge = imax(ge, w.id2idx[m]); }
+            apos[k] = ge;
+            poa_atomic_add(&hist[ge], 1);
+        }
+        sync_block<NW>();
+        block_excl_scan<NW>(sh, hist, hist, n_old, w.tmp1);  // hist[i] = nodes inserted in front of old position i
+        for (int i = tid; i < n_old; i += NT) w.id2idx[w.idx2id[i]] = i + hist[i];
+        for (int k = tid; k < n_new; k += NT) w.id2idx[n_old + k] = apos[k] + 1 + k;  // creation order = path order
+        sync_block<NW>();
+        for (int v = tid; v < n; v += NT) w.idx2id[w.id2idx[v]] = v;
+    }
+    sync_block<NW>();
+    if (banded) {
+        int *d0 = w.tmp0, *d1 = w.tmp1, *t0 = w.tmp2, *t1 = w.tmp3;
+        for (int v = tid; v < n; v += NT) {
+            const bool sink = v == SINK_ID;
+            d0[v] = sink ? 0 : 1;
+            t0[v] = sink ? SINK_ID : w.pool_id[w.out_off[v]];  // heaviest out-edge: first after the weight sort
+        }
+        sync_block<NW>();
+        for (;;) {
+            int busy = 0;
+            for (int v = tid; v < n; v += NT) {
+                const int t = t0[v];
+                const int tt = t0[t];
+                d1[v] = d0[v] + d0[t]; t1[v] = tt;
+                busy |= tt != SINK_ID;
+            }
+            int *x = d0; d0 = d1; d1 = x; x = t0; t0 = t1; t1 = x;
+            sync_block<NW>();
+            if (!block_any<NW>(sh, busy)) break;
+        }
+        for (int v = tid; v < n; v += NT) w.remain[v] = d0[v] - 1;  // remain[sink] = -1 (abpoa_graph.c:281)
+    }
+    sync_block<NW>();
+}
+
+// ------------------------------------------------------------------------------------------------
 // first sequence (abpoa_graph.c:573-592): a chain src -> bases -> sink, built by all threads
 // ------------------------------------------------------------------------------------------------
 template <int NW>
@@ -341,6 +442,7 @@ POA_DN void add_first_sequence(Shared &sh, const uint8_t *q, int qlen, int wt, i
         w.pool_id[4 * v] = (t == 0) ? SRC_ID : v - 1; w.pool_w[4 * v] = wt;
         w.pool_id[4 * v + 2] = (t == qlen - 1) ? SINK_ID : v + 1; w.pool_w[4 * v + 2] = wt;
         path[t] = v;
+        w.tmp2[t] = SRC_ID;  // toposort_incr(): the chain goes right behind the source
     }
     sync_block<NW>();
     if (tid == 0) {
@@ -369,6 +471,7 @@ POA_DN void build_rows(Shared &sh, int qlen, int banded) {
         int in = w.in_n[v], ioff = w.in_off[v], on = w.out_n[v], ooff = w.out_off[v];
         w.rowinfo[i] = poa_make_int4(ioff, in, ooff, on);
         w.rbase[i] = w.base[v];
+        w.tmp0[i] = in > 0 ? w.id2idx[w.pool_id[ioff]] : 0;  // backtrack(): row of the first predecessor
         for (int k = 0; k < in; ++k) w.pool_row[ioff + k] = w.id2idx[w.pool_id[ioff + k]];
         for (int k = 0; k < on; ++k) w.pool_row[ooff + k] = w.id2idx[w.pool_id[ooff + k]];
         if (banded) {
@@ -674,21 +777,17 @@ POA_D const S *bt_cell(const Ws &w, const int4 &pm, int plane, int j) {
     return cell_ptr<S>(w, pm, plane, j);
 }
 
+// one iteration of the reference's traceback loop at cell (i, j) in state cur_op; 0 = moved, 1 = local alignment
+// ends here (H == 0), 2 = dead end
 template <typename S, bool LAY16>
-POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen) {
+POA_D int bt_step(Shared &sh, const DevParams &P, const uint8_t *q, int &i, int &j, int &id, int &cur_op) {
     Ws &w = sh.ws;
     const int inf_min = inf_min_of<S>(P);
     const int local = P.local;
     const int e1 = P.e1, e2 = P.e2, oe1 = P.oe1, oe2 = P.oe2;
-    int i = sh.best_i, j = sh.best_j;
-    int id = w.idx2id[i];
-    int cur_op = OP_ALL;
-    sh.n_cigar = 0;
-    if (j < qlen) push_cigar(sh, CINS, qlen - j, -1, qlen - 1);
-    while (i > 0 && j > 0) {
         const int4 rm = w.rowmeta[i];
         const int Hj = *bt_cell<S, LAY16>(w, rm, 0, j);
-        if (local && Hj == 0) break;
+        if (local && Hj == 0) return 1;
         const int4 ri = w.rowinfo[i];
         const int s = P.mat[5 * w.rbase[i] + q[j - 1]];
         int hit = 0;
@@ -753,12 +852,80 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
             }
             if (hit == 1) { push_cigar(sh, CINS, 1, id, j - 1); --j; }
         }
-        if (hit == 0) { sh.err = ST_EINTERNAL; return; }
-    }
-    if (j > 0) push_cigar(sh, CINS, j, -1, j - 1);
-    unsigned long long *cig = w.cig + sh.cig_base;
+        if (hit == 0) { sh.err = ST_EINTERNAL; return 2; }
+    return 0;
+}
+
+// Traceback by one warp.  The walk itself is sequential, but its dominant pattern is not: long diagonal runs
+// of MATCH steps, each to the row's FIRST predecessor (the heaviest in-edge).  With cur_op = ALL the reference
+// tries exactly that predecessor first (abpoa_align_simd.c:321-337), so lane t speculatively checks step t of
+// such a run -- rows come from chasing the first-predecessor table fp[] -- and the leading run of successful
+// lanes is committed at once; the first failing step falls back to bt_step() on lane 0.
+template <typename S, bool LAY16>
+POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen) {
+    Ws &w = sh.ws;
+    const int lane = poa_tid() % POA_WARP;
+    const int local = P.local;
+    const int *fp = w.tmp0;  // build_rows(): row of the first predecessor
+    int i = sh.best_i, j = sh.best_j;
+    int id = w.idx2id[i];
+    int cur_op = OP_ALL;
+    if (lane == 0) { sh.n_cigar = 0; if (j < qlen) push_cigar(sh, CINS, qlen - j, -1, qlen - 1); }
+    poa_sync_warp();
     int n = sh.n_cigar;
-    for (int k = 0; k < n >> 1; ++k) { unsigned long long t = cig[k]; cig[k] = cig[n - 1 - k]; cig[n - 1 - k] = t; }  // abpoa_align.h:88-96
+    while (i > 0 && j > 0) {
+        if (POA_WARP > 1 && cur_op == OP_ALL) {
+            int ia = 0, ib = 0, r = i;
+            for (int s = 0; s < POA_WARP; ++s) {
+                const int nx = r > 0 ? fp[r] : 0;
+                if (s == lane) { ia = r; ib = nx; }
+                r = nx;
+            }
+            const int jt = j - lane;
+            int ok = 0;
+            if (ia > 0 && jt > 0) {
+                const int4 rm = w.rowmeta[ia], pm = w.rowmeta[ib];
+                const int Hj = *bt_cell<S, LAY16>(w, rm, 0, jt);
+                if (jt - 1 >= pm.y && jt - 1 <= pm.z && !(local && Hj == 0)) {
+                    const int sc = P.mat[5 * w.rbase[ia] + q[jt - 1]];
+                    ok = (int)(S)(*bt_cell<S, LAY16>(w, pm, 0, jt - 1) + sc) == Hj;
+                }
+            }
+            const unsigned okm = poa_ballot(ok);
+            const int nok = okm == 0xffffffffu ? 32 : p_ctz32(~okm);
+            if (nok > 0) {
+                if (lane < nok)  // abpoa_align.h:54-73: a MATCH always opens a new cigar word
+                    (w.cig + sh.cig_base)[n + lane] = (unsigned long long)(long long)w.idx2id[ia] << 34 | (unsigned long long)(long long)(jt - 1) << 4 | (unsigned)CMATCH;
+                n += nok;
+                const int src = nok < POA_WARP ? nok : POA_WARP - 1;
+                const int ni = poa_shfl(nok < POA_WARP ? ia : ib, src);
+                i = ni; j -= nok; id = w.idx2id[i]; cur_op = OP_ALL;
+                continue;
+            }
+        }
+        if (lane == 0) {
+            sh.n_cigar = n;
+            int ti = i, tj = j, tid_ = id, top = cur_op;
+            const int rc = bt_step<S, LAY16>(sh, P, q, ti, tj, tid_, top);
+            sh.bcast[0] = ti; sh.bcast[1] = tj; sh.bcast[2] = top; sh.bcast[3] = rc;
+        }
+        poa_sync_warp();
+        const int rc = sh.bcast[3];
+        i = sh.bcast[0]; j = sh.bcast[1]; cur_op = sh.bcast[2]; n = sh.n_cigar;
+        poa_sync_warp();
+        if (rc == 2) return;
+        if (rc == 1) break;
+        id = w.idx2id[i];
+    }
+    if (lane == 0) {
+        sh.n_cigar = n;
+        if (j > 0) push_cigar(sh, CINS, j, -1, j - 1);
+    }
+    poa_sync_warp();
+    n = sh.n_cigar;
+    unsigned long long *cig = w.cig + sh.cig_base;
+    for (int k = lane; k < n >> 1; k += POA_WARP) { unsigned long long t = cig[k]; cig[k] = cig[n - 1 - k]; cig[n - 1 - k] = t; }  // abpoa_align.h:88-96
+    poa_sync_warp();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -771,6 +938,9 @@ POA_DN int fuse(Shared &sh, const uint8_t *seq, int seq_l, int wt, int *path) {
     if (n_cigar == 0) return 0;  // abpoa_graph.c:706-708: the read is silently not added
     if (sh.n_node + seq_l > sh.nmax) { sh.err = ST_ESLAB; return 0; }  // a read adds at most seq_l nodes
     int query_id = -1, last_new = 0, last_id = SRC_ID;
+    const int n_old = sh.n_node;
+    int *anc = w.tmp2;       // anc[new_id - n_old]: see toposort_incr()
+    int anc_ref = SRC_ID;    // last pre-existing node on (or aligned with) the path so far
     for (int i = 0; i < n_cigar; ++i) {
         int op = (int)(cig[i] & 0xf);
         if (op == CMATCH) {
@@ -787,11 +957,13 @@ POA_DN int fuse(Shared &sh, const uint8_t *seq, int seq_l, int wt, int *path) {
                     add_edge(sh, last_id, new_id, 0, wt);
                     last_id = new_id; last_new = 1;
                     add_aligned(w, node_id, new_id);
+                    anc[new_id - n_old] = node_id;
                 }
             } else {
                 add_edge(sh, last_id, node_id, 1 - last_new, wt);
                 last_id = node_id; last_new = 0;
             }
+            anc_ref = node_id;
             path[query_id] = last_id;
         } else if (op == CINS) {
             int len = (int)((cig[i] >> 4) & 0x3fffffff);
@@ -801,10 +973,111 @@ POA_DN int fuse(Shared &sh, const uint8_t *seq, int seq_l, int wt, int *path) {
                 add_edge(sh, last_id, new_id, 0, wt);
                 last_id = new_id; last_new = 1;
                 path[query_id - j] = last_id;
+                anc[new_id - n_old] = anc_ref;
             }
         }
     }
     add_edge(sh, last_id, SINK_ID, 1 - last_new, wt);
+    return seq_l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// graph fusion, all threads.  Same result as fuse(): the read's path visits every graph node at most once,
+// so each (node, edge list) pair is touched by exactly one query position and the positions can be
+// processed independently once node ids are known; ids of created nodes are handed out in query order by
+// a prefix sum, which is the order fuse() creates them in.
+// ------------------------------------------------------------------------------------------------
+POA_D void edge_push_par(Shared &sh, int *off_arr, int *n_arr, int v, int id, int wt) {
+    Ws &w = sh.ws;
+    int n = n_arr[v], off = off_arr[v];
+    if (n >= 2 && (n & (n - 1)) == 0) {
+        int noff = poa_atomic_add(&sh.pool_used, 2 * n);
+        if (noff + 2 * n > sh.pool_cap) { sh.err = ST_ESLAB; return; }
+        for (int t = 0; t < n; ++t) { w.pool_id[noff + t] = w.pool_id[off + t]; w.pool_w[noff + t] = w.pool_w[off + t]; }
+        off_arr[v] = noff; off = noff;
+    }
+    w.pool_id[off + n] = id; w.pool_w[off + n] = wt; n_arr[v] = n + 1;
+}
+
+template <int NW>
+POA_D void block_incl_maxscan(Shared &sh, int *a, int n, int *scratch /* >= NT ints, global */) {
+    constexpr int NT = NW * POA_WARP;
+    const int tid = poa_tid();
+    const int per = (n + NT - 1) / NT;
+    const int lo = imin(n, tid * per), hi = imin(n, lo + per);
+    int m = INT_MIN;
+    for (int i = lo; i < hi; ++i) m = imax(m, a[i]);
+    scratch[tid] = m;
+    sync_block<NW>();
+    int pre = INT_MIN;
+    for (int t = 0; t < tid; ++t) pre = imax(pre, scratch[t]);
+    sync_block<NW>();
+    for (int i = lo; i < hi; ++i) { pre = imax(pre, a[i]); a[i] = pre; }
+    sync_block<NW>();
+}
+
+template <int NW>
+POA_DN int fuse_par(Shared &sh, const uint8_t *seq, int seq_l, int wt, int *path) {
+    constexpr int NT = NW * POA_WARP;
+    Ws &w = sh.ws;
+    const int tid = poa_tid();
+    const unsigned long long *cig = w.cig + sh.cig_base;
+    const int n_cigar = sh.n_cigar;
+    if (n_cigar == 0) return 0;  // abpoa_graph.c:706-708: the read is silently not added
+    const int n_old = sh.n_node;
+    if (n_old + seq_l > sh.nmax) { sync_block<NW>(); if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return 0; }
+    int *flag = w.tmp0, *lastm = w.tmp1, *anc = w.tmp2, *cnode = w.tmp3, *scratch = w.rr;
+    // cigar -> per query position: the graph node it is matched with, or -1 for an inserted base.  A MATCH op
+    // carries its query index; an INS op carries the index of its last base and its length (abpoa_align.h:54-73).
+    for (int i = tid; i < n_cigar; i += NT) {
+        const unsigned long long c = cig[i];
+        const int op = (int)(c & 0xf);
+        if (op == CMATCH) cnode[(int)((c >> 4) & 0x3fffffff)] = (int)((c >> 34) & 0x3fffffff);
+        else if (op == CINS) {
+            const int qid = (int)((c >> 34) & 0x3fffffff), len = (int)((c >> 4) & 0x3fffffff);
+            for (int j = 0; j < len; ++j) cnode[qid - j] = -1;
+        }
+    }
+    sync_block<NW>();
+    for (int t = tid; t < seq_l; t += NT) {
+        const int x = cnode[t], b = seq[t];
+        int node = -1;
+        if (x >= 0) {
+            if (w.base[x] == b) node = x; else node = get_aligned_id(w, x, b);
+        }
+        path[t] = node;              // existing node the base lands on, or -1: a node must be created
+        flag[t] = node < 0;
+        lastm[t] = x >= 0 ? t : -1;
+    }
+    sync_block<NW>();
+    const int n_new = block_excl_scan<NW>(sh, flag, flag, seq_l, scratch);  // flag[t] = rank among created nodes
+    block_incl_maxscan<NW>(sh, lastm, seq_l, scratch);                      // last matched position <= t
+    for (int t = tid; t < seq_l; t += NT) {
+        if (path[t] >= 0) continue;
+        const int id = n_old + flag[t], x = cnode[t];
+        w.base[id] = seq[t]; w.aln_n[id] = 0;
+        w.in_n[id] = 0; w.out_n[id] = 0; w.in_off[id] = 4 * id; w.out_off[id] = 4 * id + 2;
+        if (x >= 0) { add_aligned(w, x, id); anc[flag[t]] = x; }
+        else anc[flag[t]] = lastm[t] >= 0 ? cnode[lastm[t]] : SRC_ID;
+        path[t] = id;
+    }
+    sync_block<NW>();
+    if (tid == 0) sh.n_node = n_old + n_new;
+    for (int t = tid; t <= seq_l; t += NT) {  // abpoa_graph.c:480-556
+        const int from = t == 0 ? SRC_ID : path[t - 1], to = t == seq_l ? SINK_ID : path[t];
+        int exist = 0;
+        if (from < n_old && to < n_old) {
+            int n = w.in_n[to], off = w.in_off[to];
+            for (int i = 0; i < n; ++i) if (w.pool_id[off + i] == from) { w.pool_w[off + i] += wt; break; }
+            n = w.out_n[from]; off = w.out_off[from];
+            for (int i = 0; i < n; ++i) if (w.pool_id[off + i] == to) { w.pool_w[off + i] += wt; exist = 1; break; }
+        }
+        if (!exist) {
+            edge_push_par(sh, w.in_off, w.in_n, to, from, wt);
+            edge_push_par(sh, w.out_off, w.out_n, from, to, wt);
+        }
+    }
+    sync_block<NW>();
     return seq_l;
 }
 
@@ -891,7 +1164,7 @@ POA_D void ws_bind(Ws &w, char *b, const WsLayout &L) {
     w.tmp0 = (int *)(b + L.o_tmp0); w.tmp1 = (int *)(b + L.o_tmp1); w.tmp2 = (int *)(b + L.o_tmp2); w.tmp3 = (int *)(b + L.o_tmp3);
     w.rowinfo = (int4 *)(b + L.o_rowinfo); w.rowmeta = (int4 *)(b + L.o_rowmeta); w.rbase = (uint8_t *)(b + L.o_rbase);
     w.rr = (int *)(b + L.o_rr); w.mplr = (int *)(b + L.o_mplr); w.mprr = (int *)(b + L.o_mprr);
-    w.cig = (unsigned long long *)(b + L.o_cig); w.path = (int *)(b + L.o_path); w.best = (int *)(b + L.o_best); w.ncig = (int *)(b + L.o_ncig);
+    w.cig = (unsigned long long *)(b + L.o_cig); w.path = (int *)(b + L.o_path); w.best = (int *)(b + L.o_best); w.ncig = (int *)(b + L.o_ncig); w.plen = (int *)(b + L.o_plen);
     w.qp = b + L.o_qp; w.slab = b + L.o_slab;
 }
 
@@ -949,6 +1222,7 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
         sh.nmax = L.nmax; sh.pool_cap = L.pool_cap;
         sh.pool_used = 4 * L.nmax;
         add_node(sh, 0); add_node(sh, 0);
+        w.idx2id[0] = SRC_ID; w.idx2id[1] = SINK_ID; w.id2idx[SRC_ID] = 0; w.id2idx[SINK_ID] = 1;
     }
     sync_block<NW>();
 
@@ -960,6 +1234,7 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
         const int wt = B.weight[s0 + k];
         int *path = w.path + qoff;
         int plen = 0;
+        const int n_before = sh.n_node;
         if (tid == 0) { w.best[k] = 0; w.ncig[k] = 0; }
         if (sh.n_node == 2) {  // abpoa_align.c:193-198 / abpoa_graph.c:699-702
             long long t0 = poa_clock();
@@ -992,7 +1267,7 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
             long long t2 = poa_clock();
             t_ph[PH_FILL] += t2 - t1;
             if (sh.err != ST_OK) break;
-            if (tid == 0) {
+            if (tid < POA_WARP) {
                 if (p16) backtrack<short, true>(sh, P, q, qlen);
                 else if (bits16) backtrack<short, false>(sh, P, q, qlen);
                 else backtrack<int, false>(sh, P, q, qlen);
@@ -1001,21 +1276,17 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
             long long t3 = poa_clock();
             t_ph[PH_BT] += t3 - t2;
             if (sh.err != ST_OK) break;
-            if (tid == 0) {
-                w.best[k] = sh.best_score; w.ncig[k] = sh.n_cigar;
-                sh.bcast[1] = fuse(sh, q, qlen, wt, path);
-            }
-            sync_block<NW>();
-            plen = sh.bcast[1];
+            if (tid == 0) { w.best[k] = sh.best_score; w.ncig[k] = sh.n_cigar; }
+            plen = fuse_par<NW>(sh, q, qlen, wt, path);
             if (P.emit_cigar) cig_tot += sh.n_cigar;
             t_ph[PH_FUSE] += poa_clock() - t3;
             sync_block<NW>();
             if (tid == 0 && P.emit_cigar) sh.cig_base += sh.n_cigar;
         }
-        if (tid == 0) w.tmp3[k] = plen;  // path_len, parked until the output pass (tmp3 is free until then)
+        if (tid == 0) w.plen[k] = plen;
         if (plen > 0 || sh.n_node == 2) {  // the reference re-sorts only when the read was added
             long long t0 = poa_clock();
-            toposort<NW>(sh, banded);
+            if (P.local) toposort<NW>(sh, banded); else toposort_incr<NW>(sh, banded, n_before);
             t_ph[PH_TOPO] += poa_clock() - t0;
         }
         sync_block<NW>();
@@ -1028,10 +1299,7 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
     const int n = sh.n_node;
     int status = sh.err;
     if (status == ST_OK) {
-        // path lengths were parked in tmp3[0..n_seq); move them to w.ncig's neighbour array before tmp3 is reused
-        int *plen_arr = w.mplr;  // row tables are dead now; mplr/mprr/rr are free int[nmax] arrays (n_seq <= nmax)
-        for (int k = tid; k < n_seq; k += NT) plen_arr[k] = w.tmp3[k];
-        sync_block<NW>();
+        int *plen_arr = w.plen;
         int cons_len = -1, msa_len = -1, msa_rows = 0;
         int *cons = w.mprr;
         int *rank = w.rr;

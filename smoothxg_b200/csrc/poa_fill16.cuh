@@ -27,9 +27,12 @@ static inline unsigned p_add(unsigned a, unsigned b) { return p_pack(p_lo(a) + p
 static inline unsigned p_max(unsigned a, unsigned b) { return p_pack(imax(p_lo(a), p_lo(b)), imax(p_hi(a), p_hi(b))); }
 static inline unsigned p_min(unsigned a, unsigned b) { return p_pack(imin(p_lo(a), p_lo(b)), imin(p_hi(a), p_hi(b))); }
 static inline unsigned p_max3(unsigned a, unsigned b, unsigned c) { return p_max(p_max(a, b), c); }
+static inline unsigned p_minu(unsigned a, unsigned b) { unsigned lo = (a & 0xffffu) < (b & 0xffffu) ? (a & 0xffffu) : (b & 0xffffu), hi = (a >> 16) < (b >> 16) ? (a >> 16) : (b >> 16); return lo | (hi << 16); }
 static inline unsigned p_addmax(unsigned a, unsigned b, unsigned c) { return p_max(p_add(a, b), c); }
 static inline unsigned p_signmask(unsigned d) { return (p_lo(d) < 0 ? 0xffffu : 0u) | (p_hi(d) < 0 ? 0xffff0000u : 0u); }
 static inline unsigned p_swap(unsigned x) { return (x >> 16) | (x << 16); }
+static inline int p_ctz(unsigned x) { return __builtin_ctz(x); }
+static inline int p_clz(unsigned x) { return __builtin_clz(x); }
 static inline unsigned p_lolo(unsigned a, unsigned b) { return (a & 0xffffu) | (b << 16); }  // (a.lo, b.lo)
 #else
 POA_D unsigned p_pack(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
@@ -39,9 +42,12 @@ POA_D unsigned p_add(unsigned a, unsigned b) { return __vadd2(a, b); }
 POA_D unsigned p_max(unsigned a, unsigned b) { return __vmaxs2(a, b); }
 POA_D unsigned p_min(unsigned a, unsigned b) { return __vmins2(a, b); }
 POA_D unsigned p_max3(unsigned a, unsigned b, unsigned c) { return __vimax3_s16x2(a, b, c); }
+POA_D unsigned p_minu(unsigned a, unsigned b) { return __vminu2(a, b); }
 POA_D unsigned p_addmax(unsigned a, unsigned b, unsigned c) { return __viaddmax_s16x2(a, b, c); }
 POA_D unsigned p_signmask(unsigned d) { return __byte_perm(d, 0u, 0xbb99u); }  // PRMT sign-replicate: 0xffff per negative half
 POA_D unsigned p_swap(unsigned x) { return __byte_perm(x, 0u, 0x1032u); }
+POA_D int p_ctz(unsigned x) { return __ffs((int)x) - 1; }
+POA_D int p_clz(unsigned x) { return __clz((int)x); }
 POA_D unsigned p_lolo(unsigned a, unsigned b) { return __byte_perm(a, b, 0x5410u); }
 #endif
 
@@ -162,29 +168,32 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
         sync_block<NW>();
     }
     int best_score = inf_min, best_i = 0, best_j = 0;
+    const int pshift = 31 - p_clz((unsigned)pn);  // pn is the reference build's lane count, a power of two
+    char *const slab_lane = slab + lane * 16;
+    const bool track = local || wb >= 0;
+    int4 prev_meta = rowmeta[0];  // {chunk-plane index, beg, end} of the row evaluated last
 
     // ---- rows in index order (abpoa_align_simd.c:1205-1221)
     for (int i = 1; i < rows; ++i) {
         const int4 ri = rowinfo[i];  // {in_off, in_n, out_off, out_n}
         const int rb = rbase[i];
+        // first predecessor's row descriptor: from registers when it is the row just evaluated (the common case)
+        const int p0 = pool_row[ri.x];
+        const int4 pm0 = p0 == i - 1 ? prev_meta : rowmeta[p0];
         int beg, end;
         if (wb < 0) { beg = 0; end = qlen; }
         else {  // abpoa_align.h:34-35, abpoa_align_simd.c:946-960
             const int r = rr[i];
             beg = imax(0, imin(mplr[i], r) - bw);
             end = imin(qlen, imax(mprr[i], r) + bw);
-            const int beg_sn = beg / pn;
-            int min_pre_beg = INT_MAX, min_pre_beg_sn = INT_MAX;
-            for (int k = 0; k < ri.y; ++k) {
-                const int pb = rowmeta[pool_row[ri.x + k]].y;
-                if (min_pre_beg > pb) { min_pre_beg = pb; min_pre_beg_sn = pb / pn; }
-            }
-            if (beg_sn < min_pre_beg_sn) beg = min_pre_beg;
+            int min_pre_beg = pm0.y;
+            for (int k = 1; k < ri.y; ++k) min_pre_beg = imin(min_pre_beg, rowmeta[pool_row[ri.x + k]].y);
+            if ((beg >> pshift) < (min_pre_beg >> pshift)) beg = min_pre_beg;
         }
         if (end < beg) end = beg;
         const int cb = beg >> 8, ce = end >> 8, nch = ce - cb + 1;
         if (used + 5LL * nch > slab_units) { if (lane == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
-        const long long roff = used;
+        const unsigned roff = (unsigned)used;
         used += 5LL * nch;
         inband += end - beg + 1;
         edge_rows += (long long)ri.y * (end - beg + 1);
@@ -192,36 +201,42 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
         // F entering column cb*256 such that F[beg] comes out as f0 (cells left of beg are masked to inf_min)
         unsigned carry1 = p_pack(f0_1 + e1 * (beg - cb * P16_CW), f0_1 + e1 * (beg - cb * P16_CW));
         unsigned carry2 = p_pack(f0_2 + e2 * (beg - cb * P16_CW), f0_2 + e2 * (beg - cb * P16_CW));
-        int rmx = INT_MIN, left = -1, right = -1;
-        const char *qrow = qp + (long long)rb * nchq * P16_CPB + lane * 16;
+        int rmx = INT_MIN, fc = cb, lc = cb;  // row maximum, first / last chunk attaining it, and those chunks' H
+        unsigned fh0 = 0, fh1 = 0, fh2 = 0, fh3 = 0, lh0 = 0, lh1 = 0, lh2 = 0, lh3 = 0;
+        const char *qrow = qp + (size_t)(unsigned)(rb * nchq) * P16_CPB + lane * 16;
 
+#pragma unroll 1
         for (int c = cb; c <= ce; ++c) {
             const int c0 = c * P16_CW;
+            const uint4 qv = p16_ld(qrow + (size_t)(unsigned)c * P16_CPB);
             unsigned M0 = INFP, M1 = INFP, M2 = INFP, M3 = INFP;
             unsigned A0 = INFP, A1 = INFP, A2 = INFP, A3 = INFP;  // E1 in
             unsigned B0 = INFP, B1 = INFP, B2 = INFP, B3 = INFP;  // E2 in
+#pragma unroll 1
             for (int k = 0; k < ri.y; ++k) {  // predecessors in in_id order (abpoa_align_simd.c:966-1029)
-                const int4 pm = rowmeta[pool_row[ri.x + k]];
+                int4 pm = pm0;
+                if (k > 0) pm = rowmeta[pool_row[ri.x + k]];
                 const int pcb = pm.y >> 8, pce = pm.z >> 8;
-                if (c < pcb || c > pce + 1) continue;
-                const long long pnb = (long long)(pce - pcb + 1) * P16_CPB;
-                const char *ph = slab + ((long long)pm.x + (c - pcb)) * P16_CPB;
-                int prevlast = inf_min;  // H_p[c0 - 1]: the last halfword of the previous chunk-plane
-                if (c > pcb) prevlast = *reinterpret_cast<const short *>(ph - 2);
-                if (c <= pce) {
-                    const uint4 h = p16_ld(ph + lane * 16), a = p16_ld(ph + pnb + lane * 16), b = p16_ld(ph + 2 * pnb + lane * 16);
-                    const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
-                    const unsigned s0 = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot;
-                    M0 = p_max(M0, s0); M1 = p_max(M1, h.x); M2 = p_max(M2, h.y); M3 = p_max(M3, h.z);
-                    A0 = p_max(A0, a.x); A1 = p_max(A1, a.y); A2 = p_max(A2, a.z); A3 = p_max(A3, a.w);
-                    B0 = p_max(B0, b.x); B1 = p_max(B1, b.y); B2 = p_max(B2, b.z); B3 = p_max(B3, b.w);
-                } else if (lane == 0) {
-                    M0 = p_max(M0, p_pack(prevlast, inf_min));
+                if (c >= pcb && c <= pce + 1) {
+                    const unsigned pn_ = (unsigned)(pce - pcb + 1), idx = (unsigned)pm.x + (unsigned)(c - pcb);
+                    int prevlast = inf_min;  // H_p[c0 - 1]: the last halfword of the previous chunk-plane
+                    if (c > pcb) prevlast = *reinterpret_cast<const short *>(slab + (size_t)idx * P16_CPB - 2);
+                    if (c <= pce) {
+                        const uint4 h = p16_ld(slab_lane + (size_t)idx * P16_CPB);
+                        const uint4 a = p16_ld(slab_lane + (size_t)(idx + pn_) * P16_CPB);
+                        const uint4 b = p16_ld(slab_lane + (size_t)(idx + 2 * pn_) * P16_CPB);
+                        const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
+                        const unsigned s0 = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot;
+                        M0 = p_max(M0, s0); M1 = p_max(M1, h.x); M2 = p_max(M2, h.y); M3 = p_max(M3, h.z);
+                        A0 = p_max(A0, a.x); A1 = p_max(A1, a.y); A2 = p_max(A2, a.z); A3 = p_max(A3, a.w);
+                        B0 = p_max(B0, b.x); B1 = p_max(B1, b.y); B2 = p_max(B2, b.z); B3 = p_max(B3, b.w);
+                    } else if (lane == 0) {
+                        M0 = p_max(M0, p_pack(prevlast, inf_min));
+                    }
                 }
             }
             if (local && c == 0 && lane == 0) M0 = p_max(M0, p_pack(0, inf_min));  // abpoa_align_simd.c:974 (`first` = 0)
             // H~ = max(M + profile, E1, E2) (abpoa_align_simd.c:1032-1050)
-            const uint4 qv = p16_ld(qrow + (long long)c * P16_CPB);
             unsigned H0 = p_max3(p_add(M0, qv.x), A0, B0), H1 = p_max3(p_add(M1, qv.y), A1, B1);
             unsigned H2 = p_max3(p_add(M2, qv.z), A2, B2), H3 = p_max3(p_add(M3, qv.w), A3, B3);
             // cells of this chunk outside [beg,end]
@@ -245,6 +260,7 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
                 const unsigned k1 = p_add(H0, NOE2), k2 = p_addmax(k1, NE2, p_add(H1, NOE2)), k3 = p_addmax(k2, NE2, p_add(H2, NOE2));
                 const unsigned kout = p_addmax(k3, NE2, p_add(H3, NOE2));
                 unsigned g1 = p_add(lout, OFF1), g2 = p_add(kout, OFF2);
+#pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const unsigned u1 = (unsigned)poa_shfl_up((int)g1, d), u2 = (unsigned)poa_shfl_up((int)g2, d);
                     g1 = p_max(g1, u1); g2 = p_max(g2, u2);  // lanes < d get their own value back: a no-op
@@ -276,36 +292,36 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
                 A0 = (A0 & ~m0) | (INFP & m0); A1 = (A1 & ~m1) | (INFP & m1); A2 = (A2 & ~m2) | (INFP & m2); A3 = (A3 & ~m3) | (INFP & m3);
                 B0 = (B0 & ~m0) | (INFP & m0); B1 = (B1 & ~m1) | (INFP & m1); B2 = (B2 & ~m2) | (INFP & m2); B3 = (B3 & ~m3) | (INFP & m3);
             }
-            char *dst = slab + (roff + (c - cb)) * P16_CPB + lane * 16;
-            const long long pstride = (long long)nch * P16_CPB;
-            p16_st(dst, H0, H1, H2, H3); p16_st(dst + pstride, A0, A1, A2, A3); p16_st(dst + 2 * pstride, B0, B1, B2, B3);
-            p16_st(dst + 3 * pstride, F10, F11, F12, F13); p16_st(dst + 4 * pstride, F20, F21, F22, F23);
-            // row maximum with first / last arg-max (abpoa_align_simd.c:1107-1119)
-            if (local || wb >= 0) {
+            const unsigned didx = roff + (unsigned)(c - cb), un = (unsigned)nch;
+            p16_st(slab_lane + (size_t)didx * P16_CPB, H0, H1, H2, H3);
+            p16_st(slab_lane + (size_t)(didx + un) * P16_CPB, A0, A1, A2, A3);
+            p16_st(slab_lane + (size_t)(didx + 2 * un) * P16_CPB, B0, B1, B2, B3);
+            p16_st(slab_lane + (size_t)(didx + 3 * un) * P16_CPB, F10, F11, F12, F13);
+            p16_st(slab_lane + (size_t)(didx + 4 * un) * P16_CPB, F20, F21, F22, F23);
+            // row maximum (abpoa_align_simd.c:1107-1119): remember the first and the last chunk attaining it
+            if (track) {
                 const unsigned cm = p_max(p_max3(H0, H1, H2), H3);
                 const int cmx = poa_redux_max(imax(p_lo(cm), p_hi(cm)));
                 if (cmx >= rmx) {  // uniform
-                    const unsigned pat = p_pack(cmx, cmx);
-                    const int jl = c0 + lane * 4, jh = jl + 128;
-                    const unsigned x0 = H0 ^ pat, x1 = H1 ^ pat, x2 = H2 ^ pat, x3 = H3 ^ pat;
-                    int first = INT_MAX, last = -1;
-                    // lowest column first: low halves 0..3, then high halves 0..3
-                    if ((x0 & 0xffffu) == 0) first = jl; else if ((x1 & 0xffffu) == 0) first = jl + 1;
-                    else if ((x2 & 0xffffu) == 0) first = jl + 2; else if ((x3 & 0xffffu) == 0) first = jl + 3;
-                    else if ((x0 >> 16) == 0) first = jh; else if ((x1 >> 16) == 0) first = jh + 1;
-                    else if ((x2 >> 16) == 0) first = jh + 2; else if ((x3 >> 16) == 0) first = jh + 3;
-                    // highest column first: high halves 3..0, then low halves 3..0
-                    if ((x3 >> 16) == 0) last = jh + 3; else if ((x2 >> 16) == 0) last = jh + 2;
-                    else if ((x1 >> 16) == 0) last = jh + 1; else if ((x0 >> 16) == 0) last = jh;
-                    else if ((x3 & 0xffffu) == 0) last = jl + 3; else if ((x2 & 0xffffu) == 0) last = jl + 2;
-                    else if ((x1 & 0xffffu) == 0) last = jl + 1; else if ((x0 & 0xffffu) == 0) last = jl;
-                    const int gl = poa_redux_min(first), gr = poa_redux_max(last);
-                    if (cmx > rmx) { rmx = cmx; left = gl; right = gr; } else right = gr;
+                    if (cmx > rmx) { rmx = cmx; fc = c; fh0 = H0; fh1 = H1; fh2 = H2; fh3 = H3; }
+                    lc = c; lh0 = H0; lh1 = H1; lh2 = H2; lh3 = H3;
                 }
             }
         }
-        if (lane == 0) rowmeta[i] = poa_make_int4((int)roff, beg, end, 0);
-        if (local || wb >= 0) {
+        prev_meta = poa_make_int4((int)roff, beg, end, 0);
+        if (lane == 0) rowmeta[i] = prev_meta;
+        if (track) {
+            // first / last column holding the row maximum: bit r of a lane's mask = low-half cell r equals it, bit 4+r = high half
+            const unsigned pat = p_pack(rmx, rmx);
+            const unsigned fz = p_minu(fh0 ^ pat, 0x00010001u) | (p_minu(fh1 ^ pat, 0x00010001u) << 1)
+                              | (p_minu(fh2 ^ pat, 0x00010001u) << 2) | (p_minu(fh3 ^ pat, 0x00010001u) << 3);
+            const unsigned lz = p_minu(lh0 ^ pat, 0x00010001u) | (p_minu(lh1 ^ pat, 0x00010001u) << 1)
+                              | (p_minu(lh2 ^ pat, 0x00010001u) << 2) | (p_minu(lh3 ^ pat, 0x00010001u) << 3);
+            const unsigned fm = (~fz & 0xfu) | ((~fz >> 12) & 0xf0u), lm = (~lz & 0xfu) | ((~lz >> 12) & 0xf0u);
+            int first = INT_MAX, last = -1;
+            if (fm) { const int b = p_ctz(fm); first = fc * P16_CW + lane * 4 + b + (b >= 4 ? 124 : 0); }
+            if (lm) { const int b = 31 - p_clz(lm); last = lc * P16_CW + lane * 4 + b + (b >= 4 ? 124 : 0); }
+            const int left = poa_redux_min(first), right = poa_redux_max(last);
             if (local && rmx > best_score) { best_score = rmx; best_i = i; best_j = left; }  // abpoa_align_simd.c:1208-1210
             if (wb >= 0) {  // abpoa_align_simd.c:1121-1130
                 for (int k = lane; k < ri.w; k += POA_WARP) {

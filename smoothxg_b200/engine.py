@@ -95,10 +95,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise FileNotFoundError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = os.environ.get("POA_B200_LIB", LIB_PATH)  # alternative builds of the same CUDA library (tuning experiments)
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                                 "(nvcc -gencode arch=compute_100a,code=sm_100a); there is no CPU fallback")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     lib.poa_b200_abi_version.restype = C.c_int
     lib.poa_b200_strerror.restype = C.c_char_p
