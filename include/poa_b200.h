@@ -68,7 +68,7 @@ typedef struct poa_b200_engine_opts {
     int32_t ctas_per_sm;       /* resident POA blocks per SM; 0 = occupancy-derived default */
     int32_t emit_cigar;        /* 1: also return per-sequence graph cigars (debug / parity instrumentation) */
     int32_t flags;             /* bit 0: disable the packed 16-bit fill (A/B testing; results are identical either way) */
-    double  slab_rows_factor;  /* DP workspace rows per query base before a retry is needed; 0 = default (2.0) */
+    double  slab_rows_factor;  /* DP workspace rows per query base before a retry is needed; 0 = default (1.7) */
     int64_t device_mem_budget; /* bytes of HBM the engine may use for workspaces; 0 = 70 % of free memory */
 } poa_b200_engine_opts_t;
 

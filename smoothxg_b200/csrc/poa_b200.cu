@@ -30,7 +30,8 @@ using namespace poa;
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, POA_MIN_BLOCKS / NW) poa_b200_block_kernel(DevParams P, DevBatch B, WsLayout L, char *ws_base, DevOut O) {
     __shared__ Shared sh;
-    if (threadIdx.x == 0) ws_bind(sh.ws, ws_base + (long long)blockIdx.x * L.stride, L);
+    extern __shared__ __align__(16) char dyn_smem[];  // NW == 1: P16_RING_BYTES
+    if (threadIdx.x == 0) { ws_bind(sh.ws, ws_base + (long long)blockIdx.x * L.stride, L); sh.ring = dyn_smem; }
     for (;;) {
         if (threadIdx.x == 0) sh.blk = atomicAdd(O.counter, 1);
         __syncthreads();
@@ -182,7 +183,7 @@ namespace {
 
 template <int NW>
 cudaError_t launch_nw(int n_ctas, cudaStream_t st, const DevParams &P, const DevBatch &B, const WsLayout &L, char *ws, const DevOut &O) {
-    poa_b200_block_kernel<NW><<<n_ctas, NW * 32, 0, st>>>(P, B, L, ws, O);
+    poa_b200_block_kernel<NW><<<n_ctas, NW * 32, NW == 1 ? P16_RING_BYTES : 0, st>>>(P, B, L, ws, O);
     return cudaGetLastError();
 }
 
@@ -243,8 +244,14 @@ Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int lev
     s.pool_growth = 8 * edges + 64;
     long long row_bytes = vecs_per_row * 5 * (may32 ? 32 : 16);
     if (b->dp.p16_ok) {  // chunked rows of the packed 16-bit fill: whole 256-column chunks, 5 planes x 512 B each
-        const long long chunks = level >= 2 ? width / 256 + 2 : (width * 10 + 2559) / 2560 + 1;  // typical: one partial chunk extra
-        row_bytes = std::max(row_bytes, (level >= 1 ? width / 256 + 2 : chunks) * 2560);
+        long long p16_bytes = (width / 256 + 2) * 2560;  // worst case: a partial chunk at either end
+        if (level == 0) {
+            // first guess: a band-wide row touches band/256 + 1 chunks on average (measured 3.46 for 743-column bands,
+            // whose rows are clipped at the matrix edges); 12 % headroom, overflow is retried at the next level
+            const long long band = wb >= 0 ? std::min<long long>(max_len + 1, 2 * (wb + (long long)(b->dp.wf * max_len)) + 1) : max_len + 1;
+            p16_bytes = (long long)((band / 256.0 + 1.0) * 1.12 * 2560.0);
+        }
+        row_bytes = std::max(row_bytes, p16_bytes);
     }
     s.slab_bytes = rows * row_bytes;
     return s;
@@ -252,7 +259,7 @@ Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int lev
 
 int run_launch(poa_b200_batch *b, const std::vector<int> &blocks, int level, cudaStream_t st, bool record_events) {
     poa_b200_engine *eng = b->eng;
-    const double rows_factor = eng->opts.slab_rows_factor > 0 ? eng->opts.slab_rows_factor : 2.0;
+    const double rows_factor = eng->opts.slab_rows_factor > 0 ? eng->opts.slab_rows_factor : 1.7;
     Sizing sz = size_for(b, blocks, level, rows_factor);
     WsLayout L;
     make_layout(L, sz.nmax, sz.max_bases, sz.max_len, sz.max_seq, sz.pool_growth, sz.slab_bytes, b->dp.emit_cigar);

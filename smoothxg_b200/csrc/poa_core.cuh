@@ -64,6 +64,8 @@ static inline long long poa_clock() { return 0; }
 static inline unsigned long long poa_atomic_add(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 static inline int poa_atomic_add(int *p, int v) { int o = *p; *p += v; return o; }
 static inline int4 poa_make_int4(int x, int y, int z, int w) { int4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+static inline void poa_red_max(int *p, int v) { if (v > *p) *p = v; }
+static inline void poa_red_min(int *p, int v) { if (v < *p) *p = v; }
 #else
 #define POA_D __device__ __forceinline__
 #define POA_DN __device__ __noinline__
@@ -81,6 +83,8 @@ POA_D long long poa_clock() { return clock64(); }
 POA_D unsigned long long poa_atomic_add(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
 POA_D int poa_atomic_add(int *p, int v) { return atomicAdd(p, v); }
 POA_D int4 poa_make_int4(int x, int y, int z, int w) { return make_int4(x, y, z, w); }
+POA_D void poa_red_max(int *p, int v) { atomicMax(p, v); }
+POA_D void poa_red_min(int *p, int v) { atomicMin(p, v); }
 #endif
 
 namespace poa {
@@ -174,6 +178,7 @@ struct Shared {
     int scan_x[2][2][MAX_WARPS];
     int red_x[2][3][MAX_WARPS];
     int bcast[4];
+    char *ring;  // previous-row cache of the packed 16-bit fill (dynamic shared memory, poa_fill16.cuh)
 };
 
 #ifdef POA_HOST_EMU
@@ -1025,7 +1030,6 @@ POA_DN int fuse_par(Shared &sh, const uint8_t *seq, int seq_l, int wt, int *path
     const int n_cigar = sh.n_cigar;
     if (n_cigar == 0) return 0;  // abpoa_graph.c:706-708: the read is silently not added
     const int n_old = sh.n_node;
-    if (n_old + seq_l > sh.nmax) { sync_block<NW>(); if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return 0; }
     int *flag = w.tmp0, *lastm = w.tmp1, *anc = w.tmp2, *cnode = w.tmp3, *scratch = w.rr;
     // cigar -> per query position: the graph node it is matched with, or -1 for an inserted base.  A MATCH op
     // carries its query index; an INS op carries the index of its last base and its length (abpoa_align.h:54-73).
@@ -1051,6 +1055,7 @@ POA_DN int fuse_par(Shared &sh, const uint8_t *seq, int seq_l, int wt, int *path
     }
     sync_block<NW>();
     const int n_new = block_excl_scan<NW>(sh, flag, flag, seq_l, scratch);  // flag[t] = rank among created nodes
+    if (n_old + n_new > sh.nmax) { sync_block<NW>(); if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return 0; }
     block_incl_maxscan<NW>(sh, lastm, seq_l, scratch);                      // last matched position <= t
     for (int t = tid; t < seq_l; t += NT) {
         if (path[t] >= 0) continue;
@@ -1260,7 +1265,7 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
             if (p16) {
                 t_ph[PH_SPARE] += 1;  // alignments that took the packed 16-bit fill
 #if POA_WARP == 32
-                fill_p16<NW>(sh, P, q, qlen, L.slab_bytes);
+                if (P.local) fill_p16<NW, true>(sh, P, q, qlen, L.slab_bytes); else fill_p16<NW, false>(sh, P, q, qlen, L.slab_bytes);
 #endif
             } else if (bits16) fill<NW, short>(sh, P, q, qlen, L.slab_bytes / 16);
             else fill<NW, int>(sh, P, q, qlen, L.slab_bytes / 32);

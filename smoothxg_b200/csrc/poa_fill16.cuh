@@ -53,6 +53,8 @@ POA_D unsigned p_lolo(unsigned a, unsigned b) { return __byte_perm(a, b, 0x5410u
 
 constexpr int P16_CW = 256;          // columns per chunk
 constexpr int P16_CPB = 512;         // bytes per chunk-plane
+constexpr int P16_SMCH = 6;          // chunks of the previous row kept in shared memory (H, E1, E2)
+constexpr int P16_RING_BYTES = P16_SMCH * 3 * P16_CPB;
 
 // address of cell (plane, j) of a row stored in the chunked layout; pm = {first chunk-plane of the row, beg, end, _}
 POA_D const short *cell_ptr16(const Ws &w, const int4 &pm, int plane, int j) {
@@ -61,7 +63,33 @@ POA_D const short *cell_ptr16(const Ws &w, const int4 &pm, int plane, int j) {
     return reinterpret_cast<const short *>(w.slab) + ((long long)pm.x + (long long)plane * nch + ((j >> 8) - cb)) * 256 + ((u & 127) << 1) + (u >> 7);
 }
 
+// the ring lives in shared memory: explicit ld/st.shared on the 32-bit shared-space address (a generic pointer
+// kept in the Shared struct would compile to slower generic LD/ST)
+#ifdef POA_HOST_EMU
+typedef char *ring_ptr_t;
+static inline ring_ptr_t ring_base(char *p, int lane) { return p + lane * 16; }
+static inline uint4 ring_ld(ring_ptr_t p, unsigned off) { return *reinterpret_cast<const uint4 *>(p + off); }
+static inline void ring_st(ring_ptr_t p, unsigned off, unsigned a, unsigned b, unsigned c, unsigned d) { uint4 u; u.x = a; u.y = b; u.z = c; u.w = d; *reinterpret_cast<uint4 *>(p + off) = u; }
+#else
+typedef unsigned ring_ptr_t;
+POA_D ring_ptr_t ring_base(char *p, int lane) { return (unsigned)__cvta_generic_to_shared(p) + lane * 16; }
+POA_D uint4 ring_ld(ring_ptr_t p, unsigned off) {
+    uint4 u;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(p + off));
+    return u;
+}
+POA_D void ring_st(ring_ptr_t p, unsigned off, unsigned a, unsigned b, unsigned c, unsigned d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(p + off), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+#endif
+
 POA_D uint4 p16_ld(const char *p) { return *reinterpret_cast<const uint4 *>(p); }
+// band inputs are updated with L2 reductions (poa_red_max/min), so they are read at L2, never from a stale L1 line
+#ifdef POA_HOST_EMU
+static inline int p16_ldcg(const int *p) { return *p; }
+#else
+POA_D int p16_ldcg(const int *p) { return __ldcg(p); }
+#endif
 POA_D void p16_st(char *p, unsigned a, unsigned b, unsigned c, unsigned d) {
     uint4 u; u.x = a; u.y = b; u.z = c; u.w = d;
     *reinterpret_cast<uint4 *>(p) = u;
@@ -74,7 +102,7 @@ POA_D bool p16_eligible(const DevParams &P, int qlen) {
     return P.p16_ok && (long long)qlen * P.match + (long long)emax * (P16_CW + 8) + 64 <= 32767;
 }
 
-template <int NW>
+template <int NW, bool LOCAL>
 POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, long long slab_bytes) {
     Ws &w = sh.ws;
     const int lane = poa_tid();
@@ -82,7 +110,7 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
     const int rows = n_node - 1;  // the sink row is never filled
     const int inf_min = inf_min_of<short>(P);
     const int pn = P.pn16;
-    const int local = P.local;
+    constexpr bool local = LOCAL;
     const int wb = local ? -1 : P.wb;  // abpoa_align.c:158
 #ifdef POA_HOST_EMU
     const int bw = wb < 0 ? qlen : wb + (int)(P.wf * qlen);  // abpoa_align_simd.c:474
@@ -111,8 +139,8 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
     const int negl = -32768 + 8 * emax + 8;  // below every value a band cell can take, never wraps when used
     const unsigned INFP = p_pack(inf_min, inf_min), NEGLP = p_pack(negl, negl), ZERO = 0u;
     const unsigned NOE1 = p_pack(-oe1, -oe1), NOE2 = p_pack(-oe2, -oe2), NE1 = p_pack(-e1, -e1), NE2 = p_pack(-e2, -e2);
-    const unsigned NE1_2 = p_pack(-2 * e1, -2 * e1), NE1_3 = p_pack(-3 * e1, -3 * e1);
-    const unsigned NE2_2 = p_pack(-2 * e2, -2 * e2), NE2_3 = p_pack(-3 * e2, -3 * e2);
+    const unsigned NE1_2 = p_add(NE1, NE1), NE1_3 = p_add(NE1_2, NE1);
+    const unsigned NE2_2 = p_add(NE2, NE2), NE2_3 = p_add(NE2_2, NE2);
     const unsigned OFF1 = p_pack(e1 * 4 * (lane + 1), e1 * 4 * (lane + 33)), NOFF1 = p_pack(-e1 * 4 * lane, -e1 * 4 * (lane + 32));
     const unsigned OFF2 = p_pack(e2 * 4 * (lane + 1), e2 * 4 * (lane + 33)), NOFF2 = p_pack(-e2 * 4 * lane, -e2 * 4 * (lane + 32));
     const unsigned NCW1 = p_pack(-e1 * P16_CW, -e1 * P16_CW), NCW2 = p_pack(-e2 * P16_CW, -e2 * P16_CW);
@@ -172,22 +200,51 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
     char *const slab_lane = slab + lane * 16;
     const bool track = local || wb >= 0;
     int4 prev_meta = rowmeta[0];  // {chunk-plane index, beg, end} of the row evaluated last
+    int prev_left = 0, prev_right = 0;  // its arg-max columns (band propagation, forwarded in registers)
+    // The previous row's H/E1/E2 chunks also stay in shared memory (each lane's own 16-byte slices; slot = chunk
+    // % P16_SMCH), so the common "predecessor = row just evaluated" read never leaves the SM.
+    const ring_ptr_t ring = ring_base(sh.ring, lane);
+    bool prev_res = false;  // is the previous row in the ring? (row 0 is not; rows wider than the ring are not)
+    const int *const fp = w.tmp0;  // build_rows(): row of the first predecessor
+#ifndef POA_HOST_EMU
+    __builtin_assume(__isGlobal(fp));
+#endif
+    // metadata of the row about to be evaluated is loaded one row ahead (its first predecessor's number two ahead,
+    // so that predecessor's row descriptor can be fetched one ahead as well)
+    int4 nri = rowinfo[rows > 1 ? 1 : 0];
+    int nrb = rbase[rows > 1 ? 1 : 0], np0 = fp[rows > 1 ? 1 : 0], nnp0 = fp[rows > 2 ? 2 : 0], nrr = 0, nml = 0, nmr = 0;
+    int4 npm = rowmeta[0];
+    if (wb >= 0 && rows > 1) { nrr = rr[1]; nml = p16_ldcg(&mplr[1]); nmr = p16_ldcg(&mprr[1]); }
 
     // ---- rows in index order (abpoa_align_simd.c:1205-1221)
     for (int i = 1; i < rows; ++i) {
-        const int4 ri = rowinfo[i];  // {in_off, in_n, out_off, out_n}
-        const int rb = rbase[i];
+        const int4 ri = nri;  // {in_off, in_n, out_off, out_n}
+        const int rb = nrb, p0 = np0;
+        const int r = nrr;
+        int ml = nml, mr = nmr;
         // first predecessor's row descriptor: from registers when it is the row just evaluated (the common case)
-        const int p0 = pool_row[ri.x];
-        const int4 pm0 = p0 == i - 1 ? prev_meta : rowmeta[p0];
+        const int4 pm0 = p0 == i - 1 ? prev_meta : npm;
+        if (i + 1 < rows) {  // next row's metadata; its band inputs miss only this row's contribution, forwarded below
+            nri = rowinfo[i + 1]; nrb = rbase[i + 1]; np0 = nnp0;
+            npm = rowmeta[np0 < i ? np0 : 0];  // np0 == i: this row, taken from registers next time round
+            if (i + 2 < rows) nnp0 = fp[i + 2];
+            if (wb >= 0) { nrr = rr[i + 1]; nml = p16_ldcg(&mplr[i + 1]); nmr = p16_ldcg(&mprr[i + 1]); }
+        }
+        // rows this row hands its arg-max columns to (one per lane; fetched now, used after the last chunk)
+        const int out_row = lane < ri.w ? pool_row[ri.z + lane] : -1;
         int beg, end;
         if (wb < 0) { beg = 0; end = qlen; }
         else {  // abpoa_align.h:34-35, abpoa_align_simd.c:946-960
-            const int r = rr[i];
-            beg = imax(0, imin(mplr[i], r) - bw);
-            end = imin(qlen, imax(mprr[i], r) + bw);
             int min_pre_beg = pm0.y;
-            for (int k = 1; k < ri.y; ++k) min_pre_beg = imin(min_pre_beg, rowmeta[pool_row[ri.x + k]].y);
+            bool from_prev = p0 == i - 1;
+            for (int k = 1; k < ri.y; ++k) {
+                const int pk = pool_row[ri.x + k];
+                from_prev |= pk == i - 1;
+                min_pre_beg = imin(min_pre_beg, rowmeta[pk].y);
+            }
+            if (from_prev) { ml = imin(ml, prev_left + 1); mr = imax(mr, prev_right + 1); }  // abpoa_align_simd.c:1121-1130
+            beg = imax(0, imin(ml, r) - bw);
+            end = imin(qlen, imax(mr, r) + bw);
             if ((beg >> pshift) < (min_pre_beg >> pshift)) beg = min_pre_beg;
         }
         if (end < beg) end = beg;
@@ -201,32 +258,47 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
         // F entering column cb*256 such that F[beg] comes out as f0 (cells left of beg are masked to inf_min)
         unsigned carry1 = p_pack(f0_1 + e1 * (beg - cb * P16_CW), f0_1 + e1 * (beg - cb * P16_CW));
         unsigned carry2 = p_pack(f0_2 + e2 * (beg - cb * P16_CW), f0_2 + e2 * (beg - cb * P16_CW));
-        int rmx = INT_MIN, fc = cb, lc = cb;  // row maximum, first / last chunk attaining it, and those chunks' H
-        unsigned fh0 = 0, fh1 = 0, fh2 = 0, fh3 = 0, lh0 = 0, lh1 = 0, lh2 = 0, lh3 = 0;
+        int rmx = INT_MIN, fc = cb, lc = cb;  // row maximum, first / last chunk attaining it
         const char *qrow = qp + (size_t)(unsigned)(rb * nchq) * P16_CPB + lane * 16;
+        int ring_last = inf_min;
+        const bool cur_res = nch <= P16_SMCH;
 
+        uint4 qnext = p16_ld(qrow + (size_t)(unsigned)cb * P16_CPB);  // profile chunk, fetched one chunk ahead
 #pragma unroll 1
         for (int c = cb; c <= ce; ++c) {
             const int c0 = c * P16_CW;
-            const uint4 qv = p16_ld(qrow + (size_t)(unsigned)c * P16_CPB);
+            const uint4 qv = qnext;
+            if (c < ce) qnext = p16_ld(qrow + (size_t)(unsigned)(c + 1) * P16_CPB);
             unsigned M0 = INFP, M1 = INFP, M2 = INFP, M3 = INFP;
             unsigned A0 = INFP, A1 = INFP, A2 = INFP, A3 = INFP;  // E1 in
             unsigned B0 = INFP, B1 = INFP, B2 = INFP, B3 = INFP;  // E2 in
 #pragma unroll 1
             for (int k = 0; k < ri.y; ++k) {  // predecessors in in_id order (abpoa_align_simd.c:966-1029)
                 int4 pm = pm0;
-                if (k > 0) pm = rowmeta[pool_row[ri.x + k]];
+                int pk = p0;
+                if (k > 0) { pk = pool_row[ri.x + k]; pm = rowmeta[pk]; }
                 const int pcb = pm.y >> 8, pce = pm.z >> 8;
                 if (c >= pcb && c <= pce + 1) {
                     const unsigned pn_ = (unsigned)(pce - pcb + 1), idx = (unsigned)pm.x + (unsigned)(c - pcb);
+                    const bool in_ring = prev_res && pk == i - 1;
                     int prevlast = inf_min;  // H_p[c0 - 1]: the last halfword of the previous chunk-plane
-                    if (c > pcb) prevlast = *reinterpret_cast<const short *>(slab + (size_t)idx * P16_CPB - 2);
+                    if (c > pcb) {
+                        if (in_ring && c > cb) prevlast = ring_last;  // that chunk was read one iteration ago
+                        else prevlast = *reinterpret_cast<const short *>(slab + (size_t)idx * P16_CPB - 2);
+                    }
                     if (c <= pce) {
-                        const uint4 h = p16_ld(slab_lane + (size_t)idx * P16_CPB);
-                        const uint4 a = p16_ld(slab_lane + (size_t)(idx + pn_) * P16_CPB);
-                        const uint4 b = p16_ld(slab_lane + (size_t)(idx + 2 * pn_) * P16_CPB);
+                        uint4 h, a, b;
+                        if (in_ring) {
+                            const unsigned ro = (unsigned)(c % P16_SMCH) * (3 * P16_CPB);
+                            h = ring_ld(ring, ro); a = ring_ld(ring, ro + P16_CPB); b = ring_ld(ring, ro + 2 * P16_CPB);
+                        } else {
+                            h = p16_ld(slab_lane + (size_t)idx * P16_CPB);
+                            a = p16_ld(slab_lane + (size_t)(idx + pn_) * P16_CPB);
+                            b = p16_ld(slab_lane + (size_t)(idx + 2 * pn_) * P16_CPB);
+                        }
                         const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
                         const unsigned s0 = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot;
+                        if (in_ring) ring_last = p_hi(rot);  // lane 0: last cell of this chunk of the previous row
                         M0 = p_max(M0, s0); M1 = p_max(M1, h.x); M2 = p_max(M2, h.y); M3 = p_max(M3, h.z);
                         A0 = p_max(A0, a.x); A1 = p_max(A1, a.y); A2 = p_max(A2, a.z); A3 = p_max(A3, a.w);
                         B0 = p_max(B0, b.x); B1 = p_max(B1, b.y); B2 = p_max(B2, b.z); B3 = p_max(B3, b.w);
@@ -298,21 +370,33 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
             p16_st(slab_lane + (size_t)(didx + 2 * un) * P16_CPB, B0, B1, B2, B3);
             p16_st(slab_lane + (size_t)(didx + 3 * un) * P16_CPB, F10, F11, F12, F13);
             p16_st(slab_lane + (size_t)(didx + 4 * un) * P16_CPB, F20, F21, F22, F23);
+            if (cur_res) {  // after every predecessor read of this chunk: a lane only ever touches its own slices
+                const unsigned ro = (unsigned)(c % P16_SMCH) * (3 * P16_CPB);
+                ring_st(ring, ro, H0, H1, H2, H3); ring_st(ring, ro + P16_CPB, A0, A1, A2, A3); ring_st(ring, ro + 2 * P16_CPB, B0, B1, B2, B3);
+            }
             // row maximum (abpoa_align_simd.c:1107-1119): remember the first and the last chunk attaining it
             if (track) {
                 const unsigned cm = p_max(p_max3(H0, H1, H2), H3);
                 const int cmx = poa_redux_max(imax(p_lo(cm), p_hi(cm)));
-                if (cmx >= rmx) {  // uniform
-                    if (cmx > rmx) { rmx = cmx; fc = c; fh0 = H0; fh1 = H1; fh2 = H2; fh3 = H3; }
-                    lc = c; lh0 = H0; lh1 = H1; lh2 = H2; lh3 = H3;
-                }
+                if (cmx > rmx) { rmx = cmx; fc = c; }
+                if (cmx >= rmx) lc = c;
             }
         }
         prev_meta = poa_make_int4((int)roff, beg, end, 0);
+        prev_res = cur_res;
         if (lane == 0) rowmeta[i] = prev_meta;
         if (track) {
             // first / last column holding the row maximum: bit r of a lane's mask = low-half cell r equals it, bit 4+r = high half
             const unsigned pat = p_pack(rmx, rmx);
+            uint4 fh, lh;  // H of the first / last chunk holding the maximum: from the ring, else from the slab
+            if (cur_res) {
+                fh = ring_ld(ring, (unsigned)(fc % P16_SMCH) * (3 * P16_CPB));
+                lh = ring_ld(ring, (unsigned)(lc % P16_SMCH) * (3 * P16_CPB));
+            } else {
+                fh = p16_ld(slab_lane + (size_t)(roff + (unsigned)(fc - cb)) * P16_CPB);
+                lh = p16_ld(slab_lane + (size_t)(roff + (unsigned)(lc - cb)) * P16_CPB);
+            }
+            const unsigned fh0 = fh.x, fh1 = fh.y, fh2 = fh.z, fh3 = fh.w, lh0 = lh.x, lh1 = lh.y, lh2 = lh.z, lh3 = lh.w;
             const unsigned fz = p_minu(fh0 ^ pat, 0x00010001u) | (p_minu(fh1 ^ pat, 0x00010001u) << 1)
                               | (p_minu(fh2 ^ pat, 0x00010001u) << 2) | (p_minu(fh3 ^ pat, 0x00010001u) << 3);
             const unsigned lz = p_minu(lh0 ^ pat, 0x00010001u) | (p_minu(lh1 ^ pat, 0x00010001u) << 1)
@@ -322,12 +406,13 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
             if (fm) { const int b = p_ctz(fm); first = fc * P16_CW + lane * 4 + b + (b >= 4 ? 124 : 0); }
             if (lm) { const int b = 31 - p_clz(lm); last = lc * P16_CW + lane * 4 + b + (b >= 4 ? 124 : 0); }
             const int left = poa_redux_min(first), right = poa_redux_max(last);
+            prev_left = left; prev_right = right;
             if (local && rmx > best_score) { best_score = rmx; best_i = i; best_j = left; }  // abpoa_align_simd.c:1208-1210
-            if (wb >= 0) {  // abpoa_align_simd.c:1121-1130
-                for (int k = lane; k < ri.w; k += POA_WARP) {
+            if (wb >= 0) {  // abpoa_align_simd.c:1121-1130; reductions without a return value: nothing to wait for
+                if (out_row >= 0) { poa_red_max(&mprr[out_row], right + 1); poa_red_min(&mplr[out_row], left + 1); }
+                for (int k = lane + POA_WARP; k < ri.w; k += POA_WARP) {
                     const int o = pool_row[ri.z + k];
-                    if (right + 1 > mprr[o]) mprr[o] = right + 1;
-                    if (left + 1 < mplr[o]) mplr[o] = left + 1;
+                    poa_red_max(&mprr[o], right + 1); poa_red_min(&mplr[o], left + 1);
                 }
             }
         }

@@ -116,6 +116,10 @@ extern "C" int32_t *emu_poa_block(const pd_params_t *pp, int n_seq, const int32_
     DevOut O; O.hdr = hdr.data(); O.arena = arena.data(); O.arena_used = &used; O.arena_cap = (unsigned long long)cap; O.phase = phase; O.counter = &counter;
     Shared sh; memset(&sh, 0, sizeof(sh));
     ws_bind(sh.ws, wsp, L);
+#if POA_EMU_LANES == 32
+    std::vector<char> ring((size_t)P16_RING_BYTES + 16);
+    sh.ring = ring.data();
+#endif
 #if POA_EMU_LANES > 1
     poa_emu::run_warp([&]() { poa_block<1>(sh, dp, B, L, O, 0); });
 #else

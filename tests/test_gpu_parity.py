@@ -40,6 +40,11 @@ def test_golden_vectors(warps):
     (dict(n_blocks=8, n_seqs=8, length=500, seed=204, divergence=0.12), dict(banded=False)),
     (dict(n_blocks=6, n_seqs=32, length=2000, seed=205), dict()),
     (dict(n_blocks=4, n_seqs=10, length=800, seed=206, divergence=0.001), dict(out_msa=True)),
+    # rows wider than the packed fill's shared-memory ring (6 x 256 columns): unbanded and local, int16
+    (dict(n_blocks=3, n_seqs=5, length=2100, seed=207), dict(banded=False)),
+    (dict(n_blocks=3, n_seqs=5, length=1800, seed=208, indel_prob=0.3, indel_len=(50, 300)), dict(local=True, out_msa=True)),
+    # long band with large indels: predecessor rows far back, bands that jump
+    (dict(n_blocks=3, n_seqs=6, length=3000, seed=209, indel_prob=0.5, indel_len=(100, 600)), dict()),
 ])
 def test_fresh_inputs_vs_oracle(engine, oracle, kw, pk):
     batch = synth.make_batch(**kw)
@@ -118,6 +123,16 @@ def _properties(batch, res, blocks):
             eset = set(zip(src.tolist(), v.out_id.tolist()))
             assert (0, int(c[0])) in eset and (int(c[-1]), 1) in eset
             assert all((int(a), int(b_)) in eset for a, b_ in zip(c[:-1], c[1:]))
+
+
+def test_packed_fill_equals_generic_fill(oracle):
+    """engine flag bit 0 turns the packed 16-bit fill off; both code paths must give the oracle's result."""
+    batch = synth.make_batch(n_blocks=12, n_seqs=10, length=900, seed=210, indel_prob=0.2)
+    want = oracle.poa_batch(oracle_params(out_msa=True), batch)
+    for flags in (0, 1):
+        eng = E.PoaEngine(device=0, emit_cigar=True, flags=flags, warps_per_block=1)
+        _check_batch(eng, batch, E.make_params(out_msa=True), want, f"flags={flags}")
+        eng.close()
 
 
 def test_full_size_config1_properties_and_determinism():
