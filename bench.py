@@ -107,14 +107,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_per_launch(workload: str):
-    """DRAM bytes per launch of the POA kernel from the committed ncu --set full capture, if one matches."""
+def traffic_per_launch(workload: str, cells_per_launch: float):
+    """DRAM bytes per launch of the POA kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    `ncu --set full` capture of this workload.  The capture holds one launch over fewer blocks of the same shape
+    (a full 10 000-block launch does not fit ncu's 40-pass replay in the GPU budget), so profiles/traffic.json
+    stores bytes per in-band cell and the figure is scaled to this launch's cells."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as f:
             t = json.load(f)
-        if t.get("workload") == workload:
-            return t.get("dram_bytes_per_launch")
+        if t.get("workload") == workload and t.get("dram_bytes_per_cell"):
+            return float(t["dram_bytes_per_cell"]) * cells_per_launch
     return None
 
 
@@ -295,7 +298,7 @@ def main():
                 "engine": {"n_ctas": st["n_ctas"], "warps_per_block": st["warps_per_block"], "workspace_gb": st["workspace_bytes"] / 1e9,
                            "retried_blocks": st["retried_blocks"], "phase_cycles": st["phase_cycles"]},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic_per_launch(args.workload), "peak_source": peak_src,
+                             "traffic": traffic_per_launch(args.workload, float(cells)), "peak_source": peak_src,
                              "kernel": "poa_b200_block_kernel", "algorithmic_bytes_per_cell": bytes_per_cell,
                              "kernel_ms_per_launch": per_launch_s * 1e3}}
         if e2e_ms is not None:

@@ -23,7 +23,7 @@
  *
  * Everything behind this ABI runs on the GPU (hand-written sm_100a kernels); there is no CPU
  * fallback.  Blocks the device could not finish (workspace exhausted even after the engine's
- * automatic retry with larger workspaces, unsupported gap mode) come back with a non-zero
+ * automatic retry with larger workspaces) come back with a non-zero
  * per-block status and the call returns POA_B200_EBLOCK.
  */
 #ifndef POA_B200_H
@@ -44,7 +44,7 @@ enum {
     POA_B200_ESLAB     = 1, /* per-block: DP workspace exhausted (retried automatically with a larger one) */
     POA_B200_EARENA    = 2, /* per-block: result arena exhausted (retried automatically with a larger one) */
     POA_B200_EINTERNAL = 3, /* per-block: traceback reached a dead end (the reference aborts here, abpoa_align_simd.c:448) */
-    POA_B200_EUNSUP    = 4, /* unsupported parameters (only the convex gap mode gap_open1>0 && gap_open2>0 is implemented) */
+    POA_B200_EUNSUP    = 4, /* unsupported parameters (gap_ext1 == gap_ext2 == 0, scores outside the 16-bit head room abPOA assumes) */
     POA_B200_EBLOCK    = 5, /* call-level: at least one block has a non-zero status */
     POA_B200_ECUDA     = 6, /* CUDA runtime error; see poa_b200_last_error() */
     POA_B200_EARG      = 7, /* bad argument */
@@ -52,7 +52,9 @@ enum {
 };
 
 /* Mirrors the abpoa_para_t fields smooth_abpoa sets (reference src/smooth.cpp:256-297).
- * Penalties are positive numbers, as smoothxg passes them (src/smooth.cpp:282-287). */
+ * Penalties are positive numbers, as smoothxg passes them (src/smooth.cpp:282-287).  The gap mode follows
+ * abpoa_set_gap_mode (deps/abPOA/src/abpoa_align.c:87-91): gap_open1 == 0 linear, gap_open2 == 0 affine (what a
+ * four-value -p gives, src/main.cpp:353-359), otherwise convex (smoothxg's default and all -a presets). */
 typedef struct poa_b200_params {
     int32_t match, mismatch, gap_open1, gap_ext1, gap_open2, gap_ext2;
     int32_t align_mode; /* 0 = global, 1 = local (src/smooth.cpp:259-263); local forces wb = -1 (abpoa_align.c:158) */
@@ -166,6 +168,32 @@ int  poa_b200_result_from_parts(int64_t n_blocks, const int32_t *hdr, const int3
                                 poa_b200_result_t **result);
 void poa_b200_batch_free(poa_b200_batch_t *batch);
 int  poa_b200_batch_stats(const poa_b200_batch_t *batch, poa_b200_stats_t *stats);
+
+/* ---- next stage: the per-block graph smoothxg builds from the POA result.
+ * build_odgi_abPOA (reference src/smooth.cpp:2442-2574) turns abpoa_t into an odgi graph of 1-bp nodes
+ * (odgi id = abPOA id - 1), embeds one path per read with `padding_len` steps trimmed at both ends, embeds the
+ * consensus path restricted to nodes some read still covers, and drops every edge and node no path uses
+ * (:2559-2573).  poa_b200_block_graph() produces exactly that graph as flat arrays (pure host code, no GPU):
+ * nodes in the order build_odgi_abPOA creates them (Kahn walk from the source over out_id order, :2463-2511),
+ * edges as (from, to) pairs of odgi ids in creation order, paths as step lists in the POA's forward
+ * orientation -- for a read whose dup_is_revs flag is set the caller walks its list backwards and flips the
+ * handles, as :2524-2529 does; duplicate names of a deduplicated read share its list. */
+typedef struct poa_b200_graph_view {
+    int32_t n_node;             /* nodes kept: covered by at least one trimmed read path */
+    const int32_t *node_id;     /* [n_node] odgi id (abPOA id - 1) */
+    const char    *node_base;   /* [n_node] 'A','C','G','T','N' (ab_nt256_table) */
+    int32_t n_edge;             /* edges kept: traversed by at least one path */
+    const int32_t *edge_from;   /* [n_edge] odgi ids, forward strand both ends */
+    const int32_t *edge_to;
+    int32_t n_path;             /* n_seq, plus one when the consensus path was requested */
+    const int64_t *path_off;    /* [n_path + 1] offsets into path_node; the consensus path is the last one */
+    const int32_t *path_node;   /* odgi ids */
+} poa_b200_graph_view_t;
+typedef struct poa_b200_graph poa_b200_graph_t;
+int  poa_b200_block_graph(const poa_b200_block_view_t *view, int32_t padding_len, int32_t include_consensus,
+                          poa_b200_graph_t **graph);
+int  poa_b200_graph_view(const poa_b200_graph_t *graph, poa_b200_graph_view_t *view);
+void poa_b200_graph_free(poa_b200_graph_t *graph);
 
 int64_t poa_b200_result_n_blocks(const poa_b200_result_t *res);
 int  poa_b200_result_block(const poa_b200_result_t *res, int64_t block, poa_b200_block_view_t *view);

@@ -1,0 +1,163 @@
+// poa_b200_smooth.hpp -- host-side mirror of smoothxg's per-block abPOA adapter above the C ABI (header only).
+//
+// Reference: smooth_abpoa (src/smooth.cpp:133-627) and build_odgi_abPOA (:2442-2574).  The reference function
+// (a) walks the block's path ranges in XG and produces one oriented, padded string per range (:177-214),
+// (b) de-duplicates identical strings, counting multiplicities (:217-241),
+// (c) runs abPOA (:256-351), (d) builds the odgi graph with one path per *name* (:2513-2532) and the consensus path.
+// Step (a) needs smoothxg's XG index and stays in smoothxg; this header mirrors (b), (c) and (d) with the same
+// names and argument meaning, on plain C++ containers, so that the patched smooth_abpoa is a handful of lines
+//  and the batched variant can be called once per chunk of blocks.  (c) is the GPU engine behind
+// include/poa_b200.h; there is no CPU path.  Errors: the reference exits the process (err_fatal, exit(1) :350,
+// :553); here they are thrown as std::runtime_error.
+#ifndef POA_B200_SMOOTH_HPP
+#define POA_B200_SMOOTH_HPP
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "poa_b200.h"
+
+namespace poa_b200 {
+
+// What smooth_abpoa holds after the de-duplication loop (src/smooth.cpp:217-241).
+struct block_sequences {
+    std::vector<std::string> seqs;                          // unique sequences, first-occurrence order
+    std::vector<int32_t> weights;                           // multiplicity of each (weights[rank]++, :236)
+    std::vector<std::vector<std::string>> dup_seq_names;    // names sharing each sequence
+    std::vector<std::vector<bool>> dup_is_revs;             // their orientation flags
+};
+
+// src/smooth.cpp:217-241.  The reference keys on XXH64(seq) only; identical strings always share a key, so keying
+// on the string itself gives the same grouping except on a 64-bit hash collision between different strings.
+inline block_sequences dedup_sequences(const std::vector<std::string> &seqs, const std::vector<std::string> &names,
+                                       const std::vector<bool> &is_revs) {
+    if (seqs.size() != names.size() || seqs.size() != is_revs.size()) throw std::runtime_error("poa_b200: ragged block input");
+    block_sequences b;
+    std::unordered_map<std::string, size_t> rank_of;
+    for (size_t i = 0; i < seqs.size(); ++i) {
+        auto it = rank_of.find(seqs[i]);
+        if (it == rank_of.end()) {
+            rank_of.emplace(seqs[i], b.seqs.size());
+            b.seqs.push_back(seqs[i]); b.weights.push_back(1);
+            b.dup_seq_names.push_back({names[i]}); b.dup_is_revs.push_back({is_revs[i]});
+        } else {
+            b.weights[it->second]++;
+            b.dup_seq_names[it->second].push_back(names[i]); b.dup_is_revs[it->second].push_back(is_revs[i]);
+        }
+    }
+    return b;
+}
+
+struct step_t { int32_t node_id; bool is_rev; };            // odgi handle: id + orientation
+struct path_t { std::string name; std::vector<step_t> steps; };
+
+// What build_odgi_abPOA leaves in `output` (src/smooth.cpp:2442-2574), before unchop/sort (:545-620).
+struct block_graph {
+    std::vector<int32_t> node_id;                           // creation order
+    std::string node_base;                                  // one base per node
+    std::vector<std::pair<int32_t, int32_t>> edges;         // forward-forward
+    std::vector<path_t> paths;                              // one per name, consensus last when requested
+    int32_t msa_len = -1, msa_rows = 0;
+    std::vector<uint8_t> msa;                               // abc->msa_base rows (gap = 5), when asked for
+};
+
+inline poa_b200_params_t make_params(int poa_m, int poa_n, int poa_g, int poa_e, int poa_q, int poa_c,
+                                     bool local_alignment, bool banded_alignment, bool want_msa, bool add_consensus) {
+    poa_b200_params_t p;                                    // src/smooth.cpp:256-297
+    p.match = poa_m; p.mismatch = poa_n; p.gap_open1 = poa_g; p.gap_ext1 = poa_e; p.gap_open2 = poa_q; p.gap_ext2 = poa_c;
+    p.align_mode = local_alignment ? 1 : 0;
+    p.wb = banded_alignment ? 311 : -1; p.wf = 0.03f;
+    p.out_cons = add_consensus ? 1 : 0; p.out_msa = want_msa ? 1 : 0;
+    return p;
+}
+
+namespace detail {
+inline void check(int rc, const char *what) {
+    if (rc != POA_B200_OK) throw std::runtime_error(std::string("poa_b200: ") + what + ": " + poa_b200_strerror(rc) + ": " + poa_b200_last_error());
+}
+
+inline block_graph graph_of(const poa_b200_result_t *res, int64_t blk, const block_sequences &b, int padding_len,
+                            const std::string &consensus_name) {
+    poa_b200_block_view_t v;
+    check(poa_b200_result_block(res, blk, &v), "result_block");
+    if (v.status != POA_B200_OK) throw std::runtime_error(std::string("poa_b200: block failed: ") + poa_b200_strerror(v.status));
+    const bool add_consensus = !consensus_name.empty();
+    if (add_consensus && v.cons_len < 0) throw std::runtime_error("poa_b200: no consensus sequence generated");  // :348-351
+    poa_b200_graph_t *g = nullptr;
+    check(poa_b200_block_graph(&v, padding_len, add_consensus ? 1 : 0, &g), "block_graph");
+    poa_b200_graph_view_t gv;
+    check(poa_b200_graph_view(g, &gv), "graph_view");
+    block_graph out;
+    out.node_id.assign(gv.node_id, gv.node_id + gv.n_node);
+    out.node_base.assign(gv.node_base, gv.node_base + gv.n_node);
+    for (int32_t i = 0; i < gv.n_edge; ++i) out.edges.emplace_back(gv.edge_from[i], gv.edge_to[i]);
+    for (size_t i = 0; i < b.seqs.size() && (int32_t)i < gv.n_path; ++i) {  // :2513-2532: one path per name
+        const int32_t *s0 = gv.path_node + gv.path_off[i], *s1 = gv.path_node + gv.path_off[i + 1];
+        for (size_t z = 0; z < b.dup_seq_names[i].size(); ++z) {
+            path_t p; p.name = b.dup_seq_names[i][z];
+            if (b.dup_is_revs[i][z]) for (const int32_t *s = s1; s != s0;) p.steps.push_back({*--s, true});
+            else for (const int32_t *s = s0; s != s1; ++s) p.steps.push_back({*s, false});
+            out.paths.push_back(std::move(p));
+        }
+    }
+    if (add_consensus) {                                     // :2534-2549
+        path_t p; p.name = consensus_name;
+        for (int64_t k = gv.path_off[gv.n_path - 1]; k < gv.path_off[gv.n_path]; ++k) p.steps.push_back({gv.path_node[k], false});
+        out.paths.push_back(std::move(p));
+    }
+    if (v.msa_len >= 0) { out.msa_len = v.msa_len; out.msa_rows = v.msa_rows; out.msa.assign(v.msa, v.msa + (size_t)v.msa_rows * v.msa_len); }
+    poa_b200_graph_free(g);
+    return out;
+}
+}  // namespace detail
+
+// Batched form of smooth_abpoa (src/smooth.cpp:133-627) from the de-duplicated sequences on: one GPU launch for all
+// blocks.  `padding_len[b]` is the block's poa_padding (:1946-1970), `consensus_name[b]` empty = no consensus path.
+inline std::vector<block_graph> smooth_abpoa_batch(poa_b200_engine_t *engine, const std::vector<block_sequences> &blocks,
+                                                   int poa_m, int poa_n, int poa_g, int poa_e, int poa_q, int poa_c,
+                                                   const std::vector<int> &padding_len, bool local_alignment, bool want_msa,
+                                                   const std::vector<std::string> &consensus_name, bool banded_alignment = true) {
+    const size_t nb = blocks.size();
+    if (padding_len.size() != nb || consensus_name.size() != nb) throw std::runtime_error("poa_b200: ragged batch input");
+    bool any_cons = false;
+    for (auto &c : consensus_name) any_cons |= !c.empty();
+    const poa_b200_params_t params = make_params(poa_m, poa_n, poa_g, poa_e, poa_q, poa_c, local_alignment, banded_alignment, want_msa, any_cons);
+    std::vector<int64_t> block_seq_off(1, 0), seq_off(1, 0);
+    std::vector<int32_t> seq_len, weight;
+    std::vector<uint8_t> bases;
+    for (auto &b : blocks) {
+        for (size_t i = 0; i < b.seqs.size(); ++i) {
+            const size_t at = bases.size();
+            bases.resize(at + b.seqs[i].size());
+            poa_b200_encode_bases(b.seqs[i].data(), (int64_t)b.seqs[i].size(), bases.data() + at);  // :304-313
+            seq_len.push_back((int32_t)b.seqs[i].size()); weight.push_back(b.weights[i]);
+            seq_off.push_back((int64_t)bases.size());
+        }
+        block_seq_off.push_back((int64_t)seq_len.size());
+    }
+    poa_b200_result_t *res = nullptr;
+    const int rc = poa_b200_run_batch(engine, &params, (int64_t)nb, block_seq_off.data(), seq_len.data(), seq_off.data(), bases.data(), weight.data(), &res);
+    if (rc != POA_B200_OK && rc != POA_B200_EBLOCK) detail::check(rc, "run_batch");
+    std::vector<block_graph> out;
+    try {
+        for (size_t b = 0; b < nb; ++b) out.push_back(detail::graph_of(res, (int64_t)b, blocks[b], padding_len[b], consensus_name[b]));
+    } catch (...) { poa_b200_result_free(res); throw; }
+    poa_b200_result_free(res);
+    return out;
+}
+
+// Per-block form with smooth_abpoa's parameter list (src/smooth.cpp:133-150) minus the XG arguments.
+inline block_graph smooth_abpoa(poa_b200_engine_t *engine, const block_sequences &block,
+                                int poa_m, int poa_n, int poa_g, int poa_e, int poa_q, int poa_c,
+                                int poa_padding, bool local_alignment, bool want_msa, bool banded_alignment,
+                                const std::string &consensus_name) {
+    return smooth_abpoa_batch(engine, {block}, poa_m, poa_n, poa_g, poa_e, poa_q, poa_c, {poa_padding}, local_alignment, want_msa,
+                              {consensus_name}, banded_alignment)[0];
+}
+
+}  // namespace poa_b200
+#endif  // POA_B200_SMOOTH_HPP

@@ -27,9 +27,9 @@
  * pinned by bit-comparing its canonical dump (poa_dump.h) with the unmodified vendored abPOA run
  * through oracle/ref_shim.c on every fixture (tests/test_oracle_vs_ref.py, tests/golden/).
  *
- * Scope: convex gap mode (gap_open1 > 0 && gap_open2 > 0 -- smoothxg's default 1,4,6,2,26,1 and all
- * five adaptive presets, src/smooth.cpp:2028-2062), global (banded or not) and local alignment.
- * Affine/linear modes return NULL.
+ * Scope: all three gap modes of abpoa_set_gap_mode (abpoa_align.c:87-91) -- convex (smoothxg's default
+ * 1,4,6,2,26,1 and all five adaptive presets, src/smooth.cpp:2028-2062), affine (four-value -p,
+ * src/main.cpp:353-359) and linear -- global (banded or not) and local alignment.
  */
 #include <stdio.h>
 #include <stdint.h>
@@ -457,6 +457,238 @@ static void align_sequence(graph_t *g, const pd_params_t *P, const int mat[25], 
 #undef PL
 }
 
+/* ---- affine (gap_open1 > 0, gap_open2 == 0) and linear (gap_open1 == 0) gap modes (abpoa_align.c:87-91).
+ * smoothxg reaches the affine kernel when -p has four values (src/main.cpp:353-359).
+ *   affine row  simd_abpoa_ag_dp  abpoa_align_simd.c:817-933, first row :645-658, backtrack :196-307
+ *   linear row  simd_abpoa_lg_dp  abpoa_align_simd.c:727-815, first row :631-643, backtrack :116-194
+ * Differences from the convex kernel that are restated here on purpose:
+ *   - affine: F1 is fed by M + profile alone, not by max(M + profile, E1) (:908); the stored E1 is reset to
+ *     inf_min (0 in local mode) where F1 strictly won the cell (:926,:930); local mode does not clamp E1;
+ *   - affine: the first cell of a row's first vector gets F1 = (M + profile) - oe1 of the SAME column (:898,:908);
+ *     it never wins a cell or feeds one, but it is stored, so it is restated (vector start = beg rounded down to pn);
+ *   - linear: one plane; a cell is max over predecessors of (H_p[j-1] + s, H_p[j] - e1), then the row-wise
+ *     running max with H[j-1] - e1; local mode clamps at 0 only after that pass (:813);
+ *   - traceback order: affine M, E1, F1; linear M, deletion, insertion (put_gap_on_right = put_gap_at_end = 0). */
+static void align_sequence_al(graph_t *g, const pd_params_t *P, const int mat[25], const uint8_t *query, int qlen,
+                              dpm_t *dp, aln_t *res, int linear) {
+    const int gn = g->n;
+    const int local = P->align_mode == 1;
+    const int wb = local ? -1 : P->wb;
+    const int32_t e1 = P->gap_ext1, e2 = P->gap_ext2, o1 = P->gap_open1, o2 = P->gap_open2;
+    const int32_t oe1 = o1 + e1, oe2 = o2 + e2;
+    const int32_t match = P->match < 0 ? -P->match : P->match;
+    const int32_t min_mis = P->mismatch < 0 ? -P->mismatch : P->mismatch;
+    int len = qlen > gn ? qlen : gn;
+    int64_t max_score = MAX2((int64_t)qlen * match, (int64_t)len * e1 + o1);
+    int bits16 = max_score <= INT16_MAX - min_mis - oe1 - oe2;
+    int64_t base_min = bits16 ? INT16_MIN : INT32_MIN;
+    int32_t inf_min = (int32_t)(MAX2(MAX2(base_min + min_mis, base_min + oe1), base_min + oe2) + 512 * MAX2(e1, e2));
+    int pn = bits16 ? g_pn16 : g_pn32;
+    int w = wb < 0 ? qlen : wb + (int)(P->wf * qlen);
+    int rows = gn - 1;
+    const int NPL = linear ? 1 : 3; /* H | H, E1, F1 */
+    int i, j, k;
+    if (rows > dp->rows_m) {
+        dp->rows_m = rows * 2;
+        dp->off = (int64_t*)realloc(dp->off, sizeof(int64_t) * dp->rows_m);
+        dp->beg = (int*)realloc(dp->beg, sizeof(int) * dp->rows_m);
+        dp->end = (int*)realloc(dp->end, sizeof(int) * dp->rows_m);
+        dp->beg_sn = (int*)realloc(dp->beg_sn, sizeof(int) * dp->rows_m);
+    }
+    size_t used = 0;
+#define ROW_ALLOC(r, b, e) do { \
+        size_t need = used + (size_t)NPL * ((e) - (b) + 1); \
+        if (need > dp->mem_m) { dp->mem_m = need * 2 + (1 << 20); dp->mem = (int32_t*)realloc(dp->mem, sizeof(int32_t) * dp->mem_m); } \
+        dp->off[r] = (int64_t)used; dp->beg[r] = (b); dp->end[r] = (e); dp->beg_sn[r] = (b) / pn; used = need; } while (0)
+#define PL(r, p) (dp->mem + dp->off[r] + (int64_t)(p) * (dp->end[r] - dp->beg[r] + 1) - dp->beg[r])
+    int64_t inband = 0, edge_rows = 0;
+    {   /* first row */
+        int end0;
+        if (wb >= 0) {
+            g->mpl[SRC_ID] = g->mpr[SRC_ID] = 0;
+            for (i = 0; i < g->node[SRC_ID].out.n; ++i) { int o = g->node[SRC_ID].out.id[i]; g->mpl[o] = g->mpr[o] = 1; }
+            int r = qlen - (g->remain[SRC_ID] - g->remain[SINK_ID] - 1);
+            end0 = MIN2(qlen, MAX2(g->mpr[SRC_ID], r) + w);
+        } else end0 = qlen;
+        ROW_ALLOC(0, 0, end0);
+        int32_t *H = PL(0, 0);
+        if (linear) {
+            for (j = 0; j <= end0; ++j) H[j] = local ? 0 : WRAP(-e1 * j);
+        } else {
+            int32_t *E1 = PL(0, 1), *F1 = PL(0, 2);
+            if (local) { for (j = 0; j <= end0; ++j) H[j] = E1[j] = F1[j] = 0; }
+            else {
+                H[0] = 0; E1[0] = WRAP(-oe1); F1[0] = inf_min;
+                for (j = 1; j <= end0; ++j) { E1[j] = inf_min; F1[j] = H[j] = WRAP(-o1 - e1 * j); }
+            }
+        }
+        inband += end0 + 1;
+    }
+    int32_t best_score = inf_min; int best_i = 0, best_j = 0;
+    for (i = 1; i < rows; ++i) {
+        int v = g->idx2id[i];
+        const elist_t *in = &g->node[v].in;
+        int beg, end;
+        if (wb < 0) { beg = 0; end = qlen; }
+        else {
+            int r = qlen - (g->remain[v] - g->remain[SINK_ID] - 1);
+            beg = MAX2(0, MIN2(g->mpl[v], r) - w);
+            end = MIN2(qlen, MAX2(g->mpr[v], r) + w);
+            int beg_sn = beg / pn, min_pre_beg = INT_MAX, min_pre_beg_sn = INT_MAX;
+            for (k = 0; k < in->n; ++k) {
+                int pi = g->id2idx[in->id[k]];
+                if (min_pre_beg > dp->beg[pi]) { min_pre_beg = dp->beg[pi]; min_pre_beg_sn = dp->beg_sn[pi]; }
+            }
+            if (beg_sn < min_pre_beg_sn) beg = min_pre_beg;
+        }
+        if (end < beg) end = beg;
+        ROW_ALLOC(i, beg, end);
+        int32_t *H = PL(i, 0);
+        const int *mrow = mat + 5 * g->node[v].base;
+        inband += end - beg + 1; edge_rows += (int64_t)in->n * (end - beg + 1);
+        if (linear) {
+            for (j = beg; j <= end; ++j) H[j] = inf_min;
+            for (k = 0; k < in->n; ++k) {
+                int pi = g->id2idx[in->id[k]];
+                const int32_t *pH = PL(pi, 0);
+                int pb = dp->beg[pi], pe = dp->end[pi];
+                for (j = beg; j <= end; ++j) {
+                    int32_t s = j == 0 ? 0 : mrow[query[j - 1]];
+                    int32_t m = (j - 1 >= pb && j - 1 <= pe) ? pH[j - 1] : inf_min;
+                    if (local && j == 0) m = 0;  /* :760 `first` = 0 */
+                    int32_t d = (j >= pb && j <= pe) ? pH[j] : inf_min;
+                    int32_t c = MAX2(WRAP(m + s), WRAP(d - e1));
+                    /* the reference only visits vectors that overlap the predecessor's (:764-771); cells it skips keep
+                     * inf_min, cells it visits with both operands out of range get inf_min + s or inf_min - e1: junk either way */
+                    if (j - 1 > pe + pn || j < pb - pn) continue;
+                    if (c > H[j]) H[j] = c;
+                }
+            }
+            for (j = beg + 1; j <= end; ++j) { int32_t f = WRAP(H[j - 1] - e1); if (f > H[j]) H[j] = f; }
+            if (local) for (j = beg; j <= end; ++j) if (H[j] < 0) H[j] = 0;
+        } else {
+            int32_t *E1 = PL(i, 1), *F1 = PL(i, 2);
+            for (j = beg; j <= end; ++j) { H[j] = inf_min; E1[j] = inf_min; }
+            for (k = 0; k < in->n; ++k) {
+                int pi = g->id2idx[in->id[k]];
+                const int32_t *pH = PL(pi, 0), *pE1 = PL(pi, 1);
+                int pb = dp->beg[pi], pe = dp->end[pi];
+                int lo = MAX2(beg, pb + 1), hi = MIN2(end, pe + 1);
+                for (j = lo; j <= hi; ++j) if (pH[j - 1] > H[j]) H[j] = pH[j - 1];
+                if (local && beg == 0 && 0 > H[0]) H[0] = 0;
+                lo = MAX2(beg, pb); hi = MIN2(end, pe);
+                for (j = lo; j <= hi; ++j) if (pE1[j] > E1[j]) E1[j] = pE1[j];
+            }
+            int32_t prevHm = inf_min, f1 = inf_min;
+            for (j = beg; j <= end; ++j) {
+                int32_t s = j == 0 ? 0 : mrow[query[j - 1]];
+                int32_t hm = WRAP(H[j] + s);
+                if (j == beg) f1 = (beg % pn == 0) ? WRAP(hm - oe1) : WRAP(inf_min - oe1);  /* :898,:908 */
+                else f1 = MAX2(WRAP(prevHm - oe1), WRAP(f1 - e1));
+                F1[j] = f1;
+                int32_t t = MAX2(hm, E1[j]);
+                int32_t h = MAX2(t, f1);
+                if (local) h = MAX2(h, 0);
+                H[j] = h;
+                E1[j] = (h == t) ? MAX2(WRAP(E1[j] - e1), WRAP(h - oe1)) : (local ? 0 : inf_min);  /* :926,:930 */
+                prevHm = hm;
+            }
+        }
+        if (local || wb >= 0) {
+            int32_t mx = inf_min; int left = -1, right = -1;
+            for (j = beg; j <= end; ++j) {
+                if (H[j] > mx) { mx = H[j]; left = right = j; }
+                else if (H[j] == mx) right = j;
+            }
+            if (local && mx > best_score) { best_score = mx; best_i = i; best_j = left; }
+            if (wb >= 0) {
+                const elist_t *out = &g->node[v].out;
+                for (k = 0; k < out->n; ++k) {
+                    int o = out->id[k];
+                    if (right + 1 > g->mpr[o]) g->mpr[o] = right + 1;
+                    if (left + 1 < g->mpl[o]) g->mpl[o] = left + 1;
+                }
+            }
+        }
+    }
+    if (!local) {
+        const elist_t *in = &g->node[SINK_ID].in;
+        for (k = 0; k < in->n; ++k) {
+            int pi = g->id2idx[in->id[k]];
+            int e = qlen > dp->end[pi] ? dp->end[pi] : qlen;
+            int32_t sc = PL(pi, 0)[e];
+            if (sc > best_score) { best_score = sc; best_i = pi; best_j = e; }
+        }
+    }
+    res->best_score = best_score;
+    res->inband = inband; res->edge_rows = edge_rows; res->full = (int64_t)rows * (qlen + 1);
+    {   /* traceback */
+        int cur_op = OP_ALL, hit, id, s;
+        i = best_i; j = best_j; id = g->idx2id[i];
+        if (best_j < qlen) push_cigar(res, CINS, qlen - best_j, -1, qlen - 1);
+        while (i > 0 && j > 0) {
+            const int32_t *H = PL(i, 0);
+            if (local && H[j] == 0) break;
+            const elist_t *in = &g->node[id].in;
+            s = mat[5 * g->node[id].base + query[j - 1]]; hit = 0;
+            if (linear || (cur_op & OP_M)) {
+                for (k = 0; k < in->n; ++k) {
+                    int pi = g->id2idx[in->id[k]];
+                    if (j - 1 < dp->beg[pi] || j - 1 > dp->end[pi]) continue;
+                    if (WRAP(PL(pi, 0)[j - 1] + s) == H[j]) {
+                        push_cigar(res, CMATCH, 1, id, j - 1);
+                        i = pi; --j; id = g->idx2id[i]; hit = 1; cur_op = OP_ALL;
+                        break;
+                    }
+                }
+            }
+            if (linear) {
+                if (hit == 0) for (k = 0; k < in->n; ++k) {
+                    int pi = g->id2idx[in->id[k]];
+                    if (j < dp->beg[pi] || j > dp->end[pi]) continue;
+                    if (WRAP(PL(pi, 0)[j] - e1) == H[j]) { push_cigar(res, CDEL, 1, id, j - 1); i = pi; id = g->idx2id[i]; hit = 1; break; }
+                }
+                if (hit == 0) {
+                    int32_t hl = (j - 1 >= dp->beg[i]) ? H[j - 1] : inf_min;
+                    if (WRAP(hl - e1) == H[j]) { push_cigar(res, CINS, 1, id, j - 1); --j; hit = 1; }
+                }
+            } else {
+                const int32_t *E1 = PL(i, 1), *F1 = PL(i, 2);
+                if (hit == 0 && (cur_op & OP_E1)) {
+                    for (k = 0; k < in->n; ++k) {
+                        int pi = g->id2idx[in->id[k]];
+                        if (j < dp->beg[pi] || j > dp->end[pi]) continue;
+                        const int32_t *pH = PL(pi, 0), *pE1 = PL(pi, 1);
+                        int cond = (cur_op & OP_M) ? (H[j] == pE1[j]) : (E1[j] == WRAP(pE1[j] - e1));
+                        if (cond) {
+                            if (WRAP(pH[j] - oe1) == pE1[j]) cur_op = OP_M | OP_F; else cur_op = OP_E1;
+                            hit = 1; push_cigar(res, CDEL, 1, id, j - 1);
+                            i = pi; id = g->idx2id[i];
+                            break;
+                        }
+                    }
+                }
+                if (hit == 0 && (cur_op & OP_F)) {
+                    int32_t hl = (j - 1 >= dp->beg[i]) ? H[j - 1] : inf_min;
+                    int32_t f1l = (j - 1 >= dp->beg[i]) ? F1[j - 1] : inf_min;
+                    if (!(cur_op & OP_M) || H[j] == F1[j]) {
+                        if (WRAP(hl - oe1) == F1[j]) { cur_op = OP_M | OP_E; hit = 1; }
+                        else if (WRAP(f1l - e1) == F1[j]) { cur_op = OP_F1; hit = 1; }
+                    }
+                    if (hit == 1) { push_cigar(res, CINS, 1, id, j - 1); --j; }
+                }
+            }
+            if (hit == 0) { fprintf(stderr, "[poa_oracle] %s backtrack dead end at (%d,%d) cur_op=%d\n", linear ? "lg" : "ag", i, j, cur_op); abort(); }
+        }
+        if (j > 0) push_cigar(res, CINS, j, -1, j - 1);
+        for (k = 0; k < res->n_cigar >> 1; ++k) {
+            uint64_t t = res->cigar[k]; res->cigar[k] = res->cigar[res->n_cigar - 1 - k]; res->cigar[res->n_cigar - 1 - k] = t;
+        }
+    }
+#undef ROW_ALLOC
+#undef PL
+}
+
 /* abpoa_graph.c:688-773 (+ :573-592 for the first sequence); records qpos -> node id in path[] */
 static void add_alignment(graph_t *g, int banded, const uint8_t *seq, int w, int seq_l, const aln_t *res, int have_aln, int *path, int *path_len) {
     int i, j;
@@ -592,7 +824,7 @@ int32_t *oracle_poa_block(const pd_params_t *P, int n_seq, const int32_t *seq_le
                           const int32_t *weight, int instrument, int64_t *n_out) {
     (void)instrument;
     *n_out = 0;
-    if (!(P->gap_open1 > 0 && P->gap_open2 > 0)) return NULL; /* convex only, abpoa_align.c:87-91 */
+    const int gap_mode = P->gap_open1 == 0 ? 2 : (P->gap_open2 == 0 ? 1 : 0); /* abpoa_align.c:87-91: 0 convex, 1 affine, 2 linear */
     int mat[25], i, j, k;
     { /* abpoa_align.c:12-25 */
         int match = P->match < 0 ? -P->match : P->match;
@@ -616,7 +848,8 @@ int32_t *oracle_poa_block(const pd_params_t *P, int n_seq, const int32_t *seq_le
         aln_t res; memset(&res, 0, sizeof(res));
         int have = 0;
         if (g.n > 2) { /* abpoa_align.c:193-198 */
-            align_sequence(&g, P, mat, bases + off, seq_len[i], &dp, &res);
+            if (gap_mode == 0) align_sequence(&g, P, mat, bases + off, seq_len[i], &dp, &res);
+            else align_sequence_al(&g, P, mat, bases + off, seq_len[i], &dp, &res, gap_mode == 2);
             have = 1;
             inband += res.inband; full += res.full; edge_rows += res.edge_rows;
             best[i] = res.best_score; ncig[i] = res.n_cigar;

@@ -149,6 +149,12 @@ struct poa_b200_result {
     std::vector<std::vector<uint64_t>> cigar_cache;  // lazily repacked cigars (lo/hi words -> uint64)
 };
 
+struct poa_b200_graph {
+    std::vector<int32_t> node_id, edge_from, edge_to, path_node;
+    std::vector<char> node_base;
+    std::vector<int64_t> path_off;
+};
+
 struct poa_b200_batch {
     poa_b200_engine *eng = nullptr;
     poa_b200_params_t params{};
@@ -677,6 +683,83 @@ int poa_b200_poa_block(poa_b200_engine_t *eng, const poa_b200_params_t *params, 
     for (int i = 0; i < n_seq; ++i) if (seq_lens[i]) memcpy(cat.data() + so[(size_t)i], seqs[i], (size_t)seq_lens[i]);
     return poa_b200_run_batch(eng, params, 1, bso.data(), seq_lens, so.data(), cat.data(), weights, result);
 }
+
+int poa_b200_block_graph(const poa_b200_block_view_t *v, int32_t padding_len, int32_t include_consensus, poa_b200_graph_t **out) {
+    if (!v || !out || padding_len < 0) return set_err(POA_B200_EARG, "bad argument");
+    *out = nullptr;
+    if (v->status != POA_B200_OK) return set_err(POA_B200_EBLOCK, "block has no result");
+    poa_b200_graph *g = new (std::nothrow) poa_b200_graph();
+    if (!g) return set_err(POA_B200_ENOMEM, "graph alloc");
+    const int n = v->n_node, ns = v->n_seq;
+    g->path_off.assign(1, 0);
+    if (n <= 2) {  // src/smooth.cpp:2451: nothing is built
+        for (int i = 0; i < ns + (include_consensus ? 1 : 0); ++i) g->path_off.push_back(0);
+        *out = g;
+        return POA_B200_OK;
+    }
+    std::vector<int64_t> in_off((size_t)n + 1, 0), out_off((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i) { in_off[(size_t)i + 1] = in_off[(size_t)i] + v->in_n[i]; out_off[(size_t)i + 1] = out_off[(size_t)i] + v->out_n[i]; }
+    // read paths with the padding trimmed (:2520-2531), node coverage
+    std::vector<char> covered((size_t)n, 0);
+    int64_t poff = 0;
+    for (int i = 0; i < ns; ++i) {
+        const int len = v->path_len[i];
+        for (int j = padding_len; j < len - padding_len; ++j) {
+            const int id = v->path_node[poff + j];
+            g->path_node.push_back(id - 1);
+            covered[(size_t)id] = 1;
+        }
+        g->path_off.push_back((int64_t)g->path_node.size());
+        poff += len;
+    }
+    if (include_consensus) {  // :2534-2549: only nodes some read still covers
+        for (int i = 0; i < v->cons_len; ++i) { const int id = v->cons_node[i]; if (covered[(size_t)id]) g->path_node.push_back(id - 1); }
+        g->path_off.push_back((int64_t)g->path_node.size());
+    }
+    // edges some path walks (either direction walks the same edge)
+    std::vector<std::pair<int, int>> used;
+    for (size_t p = 0; p + 1 < g->path_off.size(); ++p)
+        for (int64_t k = g->path_off[p]; k + 1 < g->path_off[p + 1]; ++k) used.emplace_back(g->path_node[(size_t)k], g->path_node[(size_t)k + 1]);
+    std::sort(used.begin(), used.end());
+    used.erase(std::unique(used.begin(), used.end()), used.end());
+    // Kahn walk from the source in out_id order = node / edge creation order of build_odgi_abPOA (:2463-2511)
+    static const char code2base[6] = {'A', 'C', 'G', 'T', 'N', '-'};
+    std::vector<int> indeg((size_t)n), queue; queue.reserve((size_t)n);
+    for (int i = 0; i < n; ++i) indeg[(size_t)i] = v->in_n[i];
+    queue.push_back(0);
+    for (size_t qh = 0; qh < queue.size(); ++qh) {
+        const int cur = queue[qh];
+        if (cur == 1) break;
+        if (cur != 0) {
+            if (covered[(size_t)cur]) {
+                g->node_id.push_back(cur - 1);
+                const int b = v->base[cur];
+                g->node_base.push_back(code2base[b >= 0 && b < 5 ? b : 4]);
+            }
+            for (int64_t k = in_off[(size_t)cur]; k < in_off[(size_t)cur + 1]; ++k) {
+                const int pre = v->in_id[k];
+                if (pre == 0) continue;
+                if (std::binary_search(used.begin(), used.end(), std::make_pair(pre - 1, cur - 1))) { g->edge_from.push_back(pre - 1); g->edge_to.push_back(cur - 1); }
+            }
+        }
+        for (int64_t k = out_off[(size_t)cur]; k < out_off[(size_t)cur + 1]; ++k) {
+            const int o = v->out_id[k];
+            if (--indeg[(size_t)o] == 0) queue.push_back(o);
+        }
+    }
+    *out = g;
+    return POA_B200_OK;
+}
+
+int poa_b200_graph_view(const poa_b200_graph_t *g, poa_b200_graph_view_t *v) {
+    if (!g || !v) return set_err(POA_B200_EARG, "NULL argument");
+    v->n_node = (int32_t)g->node_id.size(); v->node_id = g->node_id.data(); v->node_base = g->node_base.data();
+    v->n_edge = (int32_t)g->edge_from.size(); v->edge_from = g->edge_from.data(); v->edge_to = g->edge_to.data();
+    v->n_path = (int32_t)g->path_off.size() - 1; v->path_off = g->path_off.data(); v->path_node = g->path_node.data();
+    return POA_B200_OK;
+}
+
+void poa_b200_graph_free(poa_b200_graph_t *g) { delete g; }
 
 int64_t poa_b200_result_n_blocks(const poa_b200_result_t *res) { return res ? res->n_blocks : 0; }
 

@@ -117,6 +117,7 @@ struct DevParams {
     int pn16, pn32;  // lane counts of the reference build whose band-start rule we reproduce (AVX-512BW: 32/16)
     int emit_cigar;
     int p16_ok;  // scoring parameters allow the packed 16-bit fill (poa_fill16.cuh)
+    int gap_mode;  // 0 convex, 1 affine, 2 linear (abpoa_set_gap_mode, abpoa_align.c:87-91)
 };
 
 // Device-resident batch input (flat, same arrays as the C ABI takes).
@@ -369,17 +370,29 @@ POA_DN void toposort_incr(Shared &sh, int banded, int n_old) {
     Ws &w = sh.ws;
     const int tid = poa_tid();
     const int n = sh.n_node, n_new = n - n_old;
-    // abpoa_graph.c:192-219: exchange sort by weight, strict <, not stable; one node per thread
-    for (int v = tid; v < n; v += NT) {
-        for (int side = 0; side < 2; ++side) {
-            int cnt = side ? w.out_n[v] : w.in_n[v];
-            int off = side ? w.out_off[v] : w.in_off[v];
-            for (int j = 0; j < cnt - 1; ++j)
-                for (int k = j + 1; k < cnt; ++k)
-                    if (w.pool_w[off + j] < w.pool_w[off + k]) {
-                        int t = w.pool_id[off + j]; w.pool_id[off + j] = w.pool_id[off + k]; w.pool_id[off + k] = t;
-                        t = w.pool_w[off + j]; w.pool_w[off + j] = w.pool_w[off + k]; w.pool_w[off + k] = t;
-                    }
+    // abpoa_graph.c:192-219: exchange sort by weight, strict <, not stable; one node per thread, degrees of four
+    // nodes fetched together (most lists have one entry and need nothing)
+    for (int v0 = tid; v0 < n; v0 += 4 * NT) {
+        int cn[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int v = v0 + u * NT;
+            cn[u][0] = v < n ? w.in_n[v] : 0; cn[u][1] = v < n ? w.out_n[v] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int v = v0 + u * NT;
+            for (int side = 0; side < 2; ++side) {
+                const int cnt = cn[u][side];
+                if (cnt < 2) continue;
+                const int off = side ? w.out_off[v] : w.in_off[v];
+                for (int j = 0; j < cnt - 1; ++j)
+                    for (int k = j + 1; k < cnt; ++k)
+                        if (w.pool_w[off + j] < w.pool_w[off + k]) {
+                            int t = w.pool_id[off + j]; w.pool_id[off + j] = w.pool_id[off + k]; w.pool_id[off + k] = t;
+                            t = w.pool_w[off + j]; w.pool_w[off + j] = w.pool_w[off + k]; w.pool_w[off + k] = t;
+                        }
+            }
         }
     }
     if (n_new > 0) {
@@ -404,19 +417,32 @@ POA_DN void toposort_incr(Shared &sh, int banded, int n_old) {
     sync_block<NW>();
     if (banded) {
         int *d0 = w.tmp0, *d1 = w.tmp1, *t0 = w.tmp2, *t1 = w.tmp3;
-        for (int v = tid; v < n; v += NT) {
-            const bool sink = v == SINK_ID;
-            d0[v] = sink ? 0 : 1;
-            t0[v] = sink ? SINK_ID : w.pool_id[w.out_off[v]];  // heaviest out-edge: first after the weight sort
+        for (int v0 = tid; v0 < n; v0 += 4 * NT) {
+            int oo[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int v = v0 + u * NT; oo[u] = (v < n && v != SINK_ID) ? w.out_off[v] : -1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (oo[u] >= 0) oo[u] = w.pool_id[oo[u]];  // heaviest out-edge: first after the weight sort
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int v = v0 + u * NT;
+                if (v < n) { d0[v] = oo[u] >= 0 ? 1 : 0; t0[v] = oo[u] >= 0 ? oo[u] : SINK_ID; }
+            }
         }
         sync_block<NW>();
         for (;;) {
             int busy = 0;
-            for (int v = tid; v < n; v += NT) {
-                const int t = t0[v];
-                const int tt = t0[t];
-                d1[v] = d0[v] + d0[t]; t1[v] = tt;
-                busy |= tt != SINK_ID;
+            for (int v0 = tid; v0 < n; v0 += 4 * NT) {
+                int t[4], dd[4], tt[4], dt[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int v = v0 + u * NT; t[u] = v < n ? t0[v] : SINK_ID; dd[u] = v < n ? d0[v] : 0; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { tt[u] = t0[t[u]]; dt[u] = d0[t[u]]; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int v = v0 + u * NT;
+                    if (v < n) { d1[v] = dd[u] + dt[u]; t1[v] = tt[u]; busy |= tt[u] != SINK_ID; }
+                }
             }
             int *x = d0; d0 = d1; d1 = x; x = t0; t0 = t1; t1 = x;
             sync_block<NW>();
@@ -471,17 +497,37 @@ POA_DN void build_rows(Shared &sh, int qlen, int banded) {
     Ws &w = sh.ws;
     const int tid = poa_tid();
     const int n = sh.n_node;
-    for (int i = tid; i < n; i += NT) {
-        int v = w.idx2id[i];
-        int in = w.in_n[v], ioff = w.in_off[v], on = w.out_n[v], ooff = w.out_off[v];
-        w.rowinfo[i] = poa_make_int4(ioff, in, ooff, on);
-        w.rbase[i] = w.base[v];
-        w.tmp0[i] = in > 0 ? w.id2idx[w.pool_id[ioff]] : 0;  // backtrack(): row of the first predecessor
-        for (int k = 0; k < in; ++k) w.pool_row[ioff + k] = w.id2idx[w.pool_id[ioff + k]];
-        for (int k = 0; k < on; ++k) w.pool_row[ooff + k] = w.id2idx[w.pool_id[ooff + k]];
-        if (banded) {
-            w.rr[i] = qlen - w.remain[v];  // qlen - (remain[v] - remain[sink] - 1), remain[sink] = -1
-            w.mplr[i] = n; w.mprr[i] = 0;  // abpoa_graph.c:349-352
+    // four rows per thread in flight: every stage is a batch of independent loads (the walk is latency bound)
+    for (int i0 = tid; i0 < n; i0 += 4 * NT) {
+        int v[4], in[4], ioff[4], on[4], ooff[4], bs[4], rm[4], fpid[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int i = i0 + u * NT; v[u] = i < n ? w.idx2id[i] : -1; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            in[u] = on[u] = ioff[u] = ooff[u] = bs[u] = rm[u] = 0;
+            if (v[u] >= 0) {
+                in[u] = w.in_n[v[u]]; ioff[u] = w.in_off[v[u]]; on[u] = w.out_n[v[u]]; ooff[u] = w.out_off[v[u]];
+                bs[u] = w.base[v[u]]; if (banded) rm[u] = w.remain[v[u]];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) fpid[u] = (v[u] >= 0 && in[u] > 0) ? w.pool_id[ioff[u]] : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (fpid[u] >= 0) fpid[u] = w.id2idx[fpid[u]];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (v[u] < 0) continue;
+            const int i = i0 + u * NT;
+            w.rowinfo[i] = poa_make_int4(ioff[u], in[u], ooff[u], on[u]);
+            w.rbase[i] = (uint8_t)bs[u];
+            w.tmp0[i] = fpid[u] >= 0 ? fpid[u] : 0;  // backtrack(), fill_p16(): row of the first predecessor
+            if (in[u] > 0) w.pool_row[ioff[u]] = fpid[u];
+            for (int k = 1; k < in[u]; ++k) w.pool_row[ioff[u] + k] = w.id2idx[w.pool_id[ioff[u] + k]];
+            for (int k = 0; k < on[u]; ++k) w.pool_row[ooff[u] + k] = w.id2idx[w.pool_id[ooff[u] + k]];
+            if (banded) {
+                w.rr[i] = qlen - rm[u];       // qlen - (remain[v] - remain[sink] - 1), remain[sink] = -1
+                w.mplr[i] = n; w.mprr[i] = 0;  // abpoa_graph.c:349-352
+            }
         }
     }
     sync_block<NW>();
@@ -532,8 +578,16 @@ POA_D const S *cell_ptr(const Ws &w, const int4 &pm, int plane, int j) {
     return reinterpret_cast<const S *>(w.slab) + ((long long)pm.x + (long long)plane * nv) * 8 + (j - vb * 8);
 }
 
-template <int NW, typename S>
+// MODE: abpoa_set_gap_mode (abpoa_align.c:87-91) -- 0 convex (five planes H,E1,E2,F1,F2; simd_abpoa_cg_dp
+// abpoa_align_simd.c:935-1074), 1 affine (H,E1,F1; simd_abpoa_ag_dp :817-933), 2 linear (H; simd_abpoa_lg_dp :727-815).
+// What the affine kernel does differently from "convex with one piece" is restated on purpose: F1 is fed by
+// M + profile alone (:908), the stored E1 is reset where F1 strictly won the cell (:926,:930), local mode does
+// not clamp E1, and the first cell of a row's first vector stores F1 = (M + profile) - oe1 of its own column
+// (:898,:908).  The linear kernel folds the deletion into the predecessor pass and clamps local scores only
+// after the horizontal pass (:813).
+template <int NW, typename S, int MODE>
 POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, long long slab_vecs) {
+    constexpr int NPL = MODE == 0 ? 5 : (MODE == 1 ? 3 : 1);
     constexpr int NT = NW * POA_WARP;
     Ws &w = sh.ws;
     const int tid = poa_tid();
@@ -568,7 +622,7 @@ POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, lon
             end0 = imin(qlen, imax(0, w.rr[0]) + bw);
         } else end0 = qlen;
         int nv = (end0 >> 3) + 1;
-        if (5LL * nv > slab_vecs) { if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+        if ((long long)NPL * nv > slab_vecs) { if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
         if (tid == 0) w.rowmeta[0] = poa_make_int4(0, 0, end0, 0);
         for (int vc = tid; vc < nv; vc += NT) {
             int H[8], E1[8], E2[8], F1[8], F2[8];
@@ -577,16 +631,21 @@ POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, lon
                 if (j > end0) { H[c] = E1[c] = E2[c] = F1[c] = F2[c] = inf_min; }
                 else if (local) { H[c] = E1[c] = E2[c] = F1[c] = F2[c] = 0; }
                 else if (j == 0) { H[c] = 0; E1[c] = (S)(-oe1); E2[c] = (S)(-oe2); F1[c] = F2[c] = inf_min; }
-                else {
+                else if (MODE == 0) {
                     F1[c] = (S)(-P.o1 - e1 * j); F2[c] = (S)(-P.o2 - e2 * j);
                     H[c] = imax(F1[c], F2[c]); E1[c] = E2[c] = inf_min;
-                }
+                } else if (MODE == 1) { F1[c] = H[c] = (S)(-P.o1 - e1 * j); E1[c] = inf_min; E2[c] = F2[c] = inf_min; }
+                else { H[c] = (S)(-e1 * j); E1[c] = E2[c] = F1[c] = F2[c] = inf_min; }
+                if (MODE == 2 && j == 0 && !local) H[c] = 0;
             }
             S *p = slab + (long long)vc * 8;
-            VecIO<S>::store(p, H); VecIO<S>::store(p + (long long)nv * 8, E1); VecIO<S>::store(p + 2LL * nv * 8, E2);
-            VecIO<S>::store(p + 3LL * nv * 8, F1); VecIO<S>::store(p + 4LL * nv * 8, F2);
+            VecIO<S>::store(p, H);
+            if (MODE == 0) {
+                VecIO<S>::store(p + (long long)nv * 8, E1); VecIO<S>::store(p + 2LL * nv * 8, E2);
+                VecIO<S>::store(p + 3LL * nv * 8, F1); VecIO<S>::store(p + 4LL * nv * 8, F2);
+            } else if (MODE == 1) { VecIO<S>::store(p + (long long)nv * 8, E1); VecIO<S>::store(p + 2LL * nv * 8, F1); }
         }
-        used = 5LL * nv;
+        used = (long long)NPL * nv;
         inband += end0 + 1;
         sync_block<NW>();
     }
@@ -613,13 +672,16 @@ POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, lon
         }
         if (end < beg) end = beg;
         const int vb = beg >> 3, ve = end >> 3, nv = ve - vb + 1;
-        if (used + 5LL * nv > slab_vecs) { if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+        if (used + (long long)NPL * nv > slab_vecs) { if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
         const long long roff = used;
-        used += 5LL * nv;
+        used += (long long)NPL * nv;
         inband += end - beg + 1;
         edge_rows += (long long)ri.y * (end - beg + 1);
 
-        int carry1 = f0_1 + e1 * beg, carry2 = f0_2 + e2 * beg;  // G[beg] of the two gap pieces
+        // G[beg] of the gap pieces.  Affine: the scan starts from inf_min - oe1 (cell beg itself is patched below);
+        // linear: nothing enters from the left of the band.
+        int carry1 = MODE == 0 ? f0_1 + e1 * beg : (MODE == 1 ? (int)(S)(inf_min - oe1) + e1 * beg : NEG_INF32);
+        int carry2 = f0_2 + e2 * beg;
         int mx = inf_min, left = -1, right = -1;
         for (int vc0 = vb; vc0 <= ve; vc0 += NT) {
             const int vc = vc0 + tid;
@@ -637,10 +699,16 @@ POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, lon
                         const S *ph = pH + (long long)(vc - pvb) * 8;
                         VecIO<S>::load(ph, hv);
                         for (int c = 0; c < 7; ++c) M[c + 1] = imax(M[c + 1], hv[c]);
-                        VecIO<S>::load(ph + (long long)pnv * 8, ev);
-                        for (int c = 0; c < 8; ++c) E1[c] = imax(E1[c], ev[c]);
-                        VecIO<S>::load(ph + 2LL * pnv * 8, ev);
-                        for (int c = 0; c < 8; ++c) E2[c] = imax(E2[c], ev[c]);
+                        if (MODE == 2) {  // linear: the deletion operand is the predecessor's H of the same column
+                            for (int c = 0; c < 8; ++c) E1[c] = imax(E1[c], hv[c]);
+                        } else {
+                            VecIO<S>::load(ph + (long long)pnv * 8, ev);
+                            for (int c = 0; c < 8; ++c) E1[c] = imax(E1[c], ev[c]);
+                        }
+                        if (MODE == 0) {
+                            VecIO<S>::load(ph + 2LL * pnv * 8, ev);
+                            for (int c = 0; c < 8; ++c) E2[c] = imax(E2[c], ev[c]);
+                        }
                     }
                     if (vc - 1 >= pvb && vc - 1 <= pve) M[0] = imax(M[0], (int)pH[(long long)(vc - 1 - pvb) * 8 + 7]);
                 }
@@ -656,11 +724,19 @@ POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, lon
                 if (inb) {
                     int s = j == 0 ? 0 : mrow[q[j - 1]];
                     int hm = (S)(M[c] + s);
-                    hh = imax(imax(hm, E1[c]), E2[c]);
                     // exclusive prefixes: value seen by cell j is the max over cells < j
                     c1[c] = t1; c2[c] = t2;
-                    t1 = imax(t1, hh - oe1 + e1 * (j + 1));
-                    t2 = imax(t2, hh - oe2 + e2 * (j + 1));
+                    if (MODE == 0) {
+                        hh = imax(imax(hm, E1[c]), E2[c]);
+                        t1 = imax(t1, hh - oe1 + e1 * (j + 1));
+                        t2 = imax(t2, hh - oe2 + e2 * (j + 1));
+                    } else if (MODE == 1) {
+                        hh = hm;  // F1 is fed by M + profile alone; E1 joins after the scan
+                        t1 = imax(t1, hm - oe1 + e1 * (j + 1));
+                    } else {
+                        hh = imax(hm, (int)(S)(E1[c] - e1));  // match/mismatch or deletion
+                        t1 = imax(t1, hh - e1 + e1 * (j + 1));
+                    }
                 } else { c1[c] = t1; c2[c] = t2; }
                 Hh[c] = hh;
             }
@@ -692,20 +768,39 @@ POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, lon
                 for (int c = 0; c < 8; ++c) {
                     const int j = j0 + c;
                     if (j >= beg && j <= end) {
-                        int f1 = (S)(imax(x1, c1[c]) - e1 * j);
-                        int f2 = (S)(imax(x2, c2[c]) - e2 * j);
-                        int h = imax(Hh[c], imax(f1, f2));
-                        if (local) h = imax(h, 0);
-                        int ne1 = imax((int)(S)(E1[c] - e1), (int)(S)(h - oe1));
-                        int ne2 = imax((int)(S)(E2[c] - e2), (int)(S)(h - oe2));
-                        if (local) { ne1 = imax(ne1, 0); ne2 = imax(ne2, 0); }
+                        int f1, f2 = inf_min, h, ne1, ne2 = inf_min;
+                        if (MODE == 0) {
+                            f1 = (S)(imax(x1, c1[c]) - e1 * j);
+                            f2 = (S)(imax(x2, c2[c]) - e2 * j);
+                            h = imax(Hh[c], imax(f1, f2));
+                            if (local) h = imax(h, 0);
+                            ne1 = imax((int)(S)(E1[c] - e1), (int)(S)(h - oe1));
+                            ne2 = imax((int)(S)(E2[c] - e2), (int)(S)(h - oe2));
+                            if (local) { ne1 = imax(ne1, 0); ne2 = imax(ne2, 0); }
+                        } else if (MODE == 1) {
+                            f1 = (S)(imax(x1, c1[c]) - e1 * j);
+                            if (j == beg) f1 = (beg % pn == 0) ? (int)(S)(Hh[c] - oe1) : (int)(S)(inf_min - oe1);  // abpoa_align_simd.c:898,:908
+                            const int t = imax(Hh[c], E1[c]);
+                            h = imax(t, f1);
+                            if (local) h = imax(h, 0);
+                            ne1 = h == t ? imax((int)(S)(E1[c] - e1), (int)(S)(h - oe1)) : (local ? 0 : inf_min);  // :926,:930
+                        } else {
+                            const int fl = imax(x1, c1[c]);
+                            f1 = fl == NEG_INF32 ? inf_min : (int)(S)(fl - e1 * j);
+                            h = imax(Hh[c], f1);
+                            if (local) h = imax(h, 0);
+                            ne1 = inf_min;
+                        }
                         H[c] = h; F1[c] = f1; F2[c] = f2; E1[c] = ne1; E2[c] = ne2;
                         if (h > mx) { mx = h; left = right = j; } else if (h == mx) right = j;  // abpoa_align_simd.c:1107-1119
                     } else { H[c] = E1[c] = E2[c] = F1[c] = F2[c] = inf_min; }
                 }
                 S *p = slab + (roff + (vc - vb)) * 8;
-                VecIO<S>::store(p, H); VecIO<S>::store(p + (long long)nv * 8, E1); VecIO<S>::store(p + 2LL * nv * 8, E2);
-                VecIO<S>::store(p + 3LL * nv * 8, F1); VecIO<S>::store(p + 4LL * nv * 8, F2);
+                VecIO<S>::store(p, H);
+                if (MODE == 0) {
+                    VecIO<S>::store(p + (long long)nv * 8, E1); VecIO<S>::store(p + 2LL * nv * 8, E2);
+                    VecIO<S>::store(p + 3LL * nv * 8, F1); VecIO<S>::store(p + 4LL * nv * 8, F2);
+                } else if (MODE == 1) { VecIO<S>::store(p + (long long)nv * 8, E1); VecIO<S>::store(p + 2LL * nv * 8, F1); }
             }
         }
         if (tid == 0) w.rowmeta[i] = poa_make_int4((int)roff, beg, end, 0);
@@ -784,7 +879,9 @@ POA_D const S *bt_cell(const Ws &w, const int4 &pm, int plane, int j) {
 
 // one iteration of the reference's traceback loop at cell (i, j) in state cur_op; 0 = moved, 1 = local alignment
 // ends here (H == 0), 2 = dead end
-template <typename S, bool LAY16>
+// MODE 0 convex (abpoa_align_simd.c:309-458), 1 affine (:196-307: no second gap piece, F1 is plane 2), 2 linear (:116-194:
+// match, then deletion, then insertion, no state)
+template <typename S, bool LAY16, int MODE>
 POA_D int bt_step(Shared &sh, const DevParams &P, const uint8_t *q, int &i, int &j, int &id, int &cur_op) {
     Ws &w = sh.ws;
     const int inf_min = inf_min_of<S>(P);
@@ -796,7 +893,7 @@ POA_D int bt_step(Shared &sh, const DevParams &P, const uint8_t *q, int &i, int 
         const int4 ri = w.rowinfo[i];
         const int s = P.mat[5 * w.rbase[i] + q[j - 1]];
         int hit = 0;
-        if (cur_op & OP_M) {
+        if (MODE == 2 || (cur_op & OP_M)) {
             for (int k = 0; k < ri.y; ++k) {
                 int pi = w.pool_row[ri.x + k];
                 const int4 pm = w.rowmeta[pi];
@@ -808,8 +905,28 @@ POA_D int bt_step(Shared &sh, const DevParams &P, const uint8_t *q, int &i, int 
                 }
             }
         }
+        if (MODE == 2) {
+            if (hit == 0) {
+                for (int k = 0; k < ri.y; ++k) {
+                    int pi = w.pool_row[ri.x + k];
+                    const int4 pm = w.rowmeta[pi];
+                    if (j < pm.y || j > pm.z) continue;
+                    if ((int)(S)(*bt_cell<S, LAY16>(w, pm, 0, j) - e1) == Hj) {
+                        push_cigar(sh, CDEL, 1, id, j - 1);
+                        i = pi; id = w.idx2id[i]; hit = 1;
+                        break;
+                    }
+                }
+            }
+            if (hit == 0) {
+                const int hl = j - 1 >= rm.y ? (int)*bt_cell<S, LAY16>(w, rm, 0, j - 1) : inf_min;
+                if ((int)(S)(hl - e1) == Hj) { push_cigar(sh, CINS, 1, id, j - 1); --j; hit = 1; }
+            }
+            if (hit == 0) { sh.err = ST_EINTERNAL; return 2; }
+            return 0;
+        }
         if (hit == 0 && (cur_op & OP_E)) {
-            const int E1j = *bt_cell<S, LAY16>(w, rm, 1, j), E2j = *bt_cell<S, LAY16>(w, rm, 2, j);
+            const int E1j = *bt_cell<S, LAY16>(w, rm, 1, j), E2j = MODE == 0 ? (int)*bt_cell<S, LAY16>(w, rm, 2, j) : inf_min;
             for (int k = 0; k < ri.y; ++k) {
                 int pi = w.pool_row[ri.x + k];
                 const int4 pm = w.rowmeta[pi];
@@ -825,7 +942,7 @@ POA_D int bt_step(Shared &sh, const DevParams &P, const uint8_t *q, int &i, int 
                         break;
                     }
                 }
-                if (cur_op & OP_E2) {
+                if (MODE == 0 && (cur_op & OP_E2)) {
                     const int pE2 = *bt_cell<S, LAY16>(w, pm, 2, j);
                     bool cond = (cur_op & OP_M) ? (Hj == pE2) : (E2j == (int)(S)(pE2 - e2));
                     if (cond) {
@@ -840,15 +957,16 @@ POA_D int bt_step(Shared &sh, const DevParams &P, const uint8_t *q, int &i, int 
         if (hit == 0 && (cur_op & OP_F)) {
             const bool inl = j - 1 >= rm.y;  // left neighbour inside this row's band?
             const int hl = inl ? (int)*bt_cell<S, LAY16>(w, rm, 0, j - 1) : inf_min;
-            const int F1j = *bt_cell<S, LAY16>(w, rm, 3, j), F2j = *bt_cell<S, LAY16>(w, rm, 4, j);
+            constexpr int PF1 = MODE == 0 ? 3 : 2;
+            const int F1j = *bt_cell<S, LAY16>(w, rm, PF1, j), F2j = MODE == 0 ? (int)*bt_cell<S, LAY16>(w, rm, 4, j) : inf_min;
             if (cur_op & OP_F1) {
                 if (!(cur_op & OP_M) || Hj == F1j) {
-                    const int f1l = inl ? (int)*bt_cell<S, LAY16>(w, rm, 3, j - 1) : inf_min;
+                    const int f1l = inl ? (int)*bt_cell<S, LAY16>(w, rm, PF1, j - 1) : inf_min;
                     if ((int)(S)(hl - oe1) == F1j) { cur_op = OP_M | OP_E; hit = 1; }
                     else if ((int)(S)(f1l - e1) == F1j) { cur_op = OP_F1; hit = 1; }
                 }
             }
-            if (hit == 0 && (cur_op & OP_F2)) {
+            if (MODE == 0 && hit == 0 && (cur_op & OP_F2)) {
                 if (!(cur_op & OP_M) || Hj == F2j) {
                     const int f2l = inl ? (int)*bt_cell<S, LAY16>(w, rm, 4, j - 1) : inf_min;
                     if ((int)(S)(hl - oe2) == F2j) { cur_op = OP_M | OP_E; hit = 1; }
@@ -866,7 +984,7 @@ POA_D int bt_step(Shared &sh, const DevParams &P, const uint8_t *q, int &i, int 
 // tries exactly that predecessor first (abpoa_align_simd.c:321-337), so lane t speculatively checks step t of
 // such a run -- rows come from chasing the first-predecessor table fp[] -- and the leading run of successful
 // lanes is committed at once; the first failing step falls back to bt_step() on lane 0.
-template <typename S, bool LAY16>
+template <typename S, bool LAY16, int MODE>
 POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen) {
     Ws &w = sh.ws;
     const int lane = poa_tid() % POA_WARP;
@@ -880,6 +998,8 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
     int n = sh.n_cigar;
     while (i > 0 && j > 0) {
         if (POA_WARP > 1 && cur_op == OP_ALL) {
+            // rows of the run: chase the first-predecessor table (all lanes walk the same chain; 32 dependent but
+            // cached loads -- rows of a bubble-rich graph are not consecutive, so the chain cannot be guessed)
             int ia = 0, ib = 0, r = i;
             for (int s = 0; s < POA_WARP; ++s) {
                 const int nx = r > 0 ? fp[r] : 0;
@@ -888,8 +1008,7 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
             }
             const int jt = j - lane;
             int ok = 0;
-            if (ia > 0 && jt > 0) {
-                const int4 rm = w.rowmeta[ia], pm = w.rowmeta[ib];
+            if (ia > 0 && jt > 0) {                const int4 rm = w.rowmeta[ia], pm = w.rowmeta[ib];
                 const int Hj = *bt_cell<S, LAY16>(w, rm, 0, jt);
                 if (jt - 1 >= pm.y && jt - 1 <= pm.z && !(local && Hj == 0)) {
                     const int sc = P.mat[5 * w.rbase[ia] + q[jt - 1]];
@@ -902,8 +1021,7 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
                 if (lane < nok)  // abpoa_align.h:54-73: a MATCH always opens a new cigar word
                     (w.cig + sh.cig_base)[n + lane] = (unsigned long long)(long long)w.idx2id[ia] << 34 | (unsigned long long)(long long)(jt - 1) << 4 | (unsigned)CMATCH;
                 n += nok;
-                const int src = nok < POA_WARP ? nok : POA_WARP - 1;
-                const int ni = poa_shfl(nok < POA_WARP ? ia : ib, src);
+                const int ni = poa_shfl(ib, nok - 1);  // first predecessor of the last committed row
                 i = ni; j -= nok; id = w.idx2id[i]; cur_op = OP_ALL;
                 continue;
             }
@@ -911,7 +1029,7 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
         if (lane == 0) {
             sh.n_cigar = n;
             int ti = i, tj = j, tid_ = id, top = cur_op;
-            const int rc = bt_step<S, LAY16>(sh, P, q, ti, tj, tid_, top);
+            const int rc = bt_step<S, LAY16, MODE>(sh, P, q, ti, tj, tid_, top);
             sh.bcast[0] = ti; sh.bcast[1] = tj; sh.bcast[2] = top; sh.bcast[3] = rc;
         }
         poa_sync_warp();
@@ -1267,15 +1385,21 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
 #if POA_WARP == 32
                 if (P.local) fill_p16<NW, true>(sh, P, q, qlen, L.slab_bytes); else fill_p16<NW, false>(sh, P, q, qlen, L.slab_bytes);
 #endif
-            } else if (bits16) fill<NW, short>(sh, P, q, qlen, L.slab_bytes / 16);
-            else fill<NW, int>(sh, P, q, qlen, L.slab_bytes / 32);
+            } else if (P.gap_mode == 0) {
+                if (bits16) fill<NW, short, 0>(sh, P, q, qlen, L.slab_bytes / 16); else fill<NW, int, 0>(sh, P, q, qlen, L.slab_bytes / 32);
+            } else if (P.gap_mode == 1) {
+                if (bits16) fill<NW, short, 1>(sh, P, q, qlen, L.slab_bytes / 16); else fill<NW, int, 1>(sh, P, q, qlen, L.slab_bytes / 32);
+            } else {
+                if (bits16) fill<NW, short, 2>(sh, P, q, qlen, L.slab_bytes / 16); else fill<NW, int, 2>(sh, P, q, qlen, L.slab_bytes / 32);
+            }
             long long t2 = poa_clock();
             t_ph[PH_FILL] += t2 - t1;
             if (sh.err != ST_OK) break;
             if (tid < POA_WARP) {
-                if (p16) backtrack<short, true>(sh, P, q, qlen);
-                else if (bits16) backtrack<short, false>(sh, P, q, qlen);
-                else backtrack<int, false>(sh, P, q, qlen);
+                if (p16) backtrack<short, true, 0>(sh, P, q, qlen);
+                else if (P.gap_mode == 0) { if (bits16) backtrack<short, false, 0>(sh, P, q, qlen); else backtrack<int, false, 0>(sh, P, q, qlen); }
+                else if (P.gap_mode == 1) { if (bits16) backtrack<short, false, 1>(sh, P, q, qlen); else backtrack<int, false, 1>(sh, P, q, qlen); }
+                else { if (bits16) backtrack<short, false, 2>(sh, P, q, qlen); else backtrack<int, false, 2>(sh, P, q, qlen); }
             }
             sync_block<NW>();
             long long t3 = poa_clock();

@@ -263,27 +263,61 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
         int ring_last = inf_min;
         const bool cur_res = nch <= P16_SMCH;
 
-        uint4 qnext = p16_ld(qrow + (size_t)(unsigned)cb * P16_CPB);  // profile chunk, fetched one chunk ahead
+        // running pointers (one 64-bit add per chunk instead of one multiply per access)
+        const char *qptr = qrow + (size_t)(unsigned)cb * P16_CPB;
+        uint4 qnext = p16_ld(qptr);  // profile chunk, fetched one chunk ahead (the buffer has a spare chunk behind the end)
+        char *dst = slab_lane + (size_t)roff * P16_CPB;
+        const size_t pstride = (size_t)(unsigned)nch * P16_CPB;
+        // first predecessor (always present; for most rows the only one, and the row just evaluated)
+        const int pcb0 = pm0.y >> 8, pce0 = pm0.z >> 8;
+        const unsigned pn0 = (unsigned)(pce0 - pcb0 + 1);
+        const bool ring0 = prev_res && p0 == i - 1;
 #pragma unroll 1
         for (int c = cb; c <= ce; ++c) {
             const int c0 = c * P16_CW;
             const uint4 qv = qnext;
-            if (c < ce) qnext = p16_ld(qrow + (size_t)(unsigned)(c + 1) * P16_CPB);
+            qptr += P16_CPB;
+            qnext = p16_ld(qptr);
             unsigned M0 = INFP, M1 = INFP, M2 = INFP, M3 = INFP;
             unsigned A0 = INFP, A1 = INFP, A2 = INFP, A3 = INFP;  // E1 in
             unsigned B0 = INFP, B1 = INFP, B2 = INFP, B3 = INFP;  // E2 in
+            if (c >= pcb0 && c <= pce0 + 1) {
+                const unsigned idx = (unsigned)pm0.x + (unsigned)(c - pcb0);
+                int prevlast = inf_min;  // H_p[c0 - 1]: the last halfword of the previous chunk-plane
+                if (c > pcb0) {
+                    if (ring0 && c > cb) prevlast = ring_last;  // that chunk was read one iteration ago
+                    else prevlast = *reinterpret_cast<const short *>(slab + (size_t)idx * P16_CPB - 2);
+                }
+                if (c <= pce0) {
+                    uint4 h, a, b;
+                    if (ring0) {
+                        const unsigned ro = (unsigned)(c % P16_SMCH) * (3 * P16_CPB);
+                        h = ring_ld(ring, ro); a = ring_ld(ring, ro + P16_CPB); b = ring_ld(ring, ro + 2 * P16_CPB);
+                    } else {
+                        h = p16_ld(slab_lane + (size_t)idx * P16_CPB);
+                        a = p16_ld(slab_lane + (size_t)(idx + pn0) * P16_CPB);
+                        b = p16_ld(slab_lane + (size_t)(idx + 2 * pn0) * P16_CPB);
+                    }
+                    const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
+                    if (ring0) ring_last = p_hi(rot);  // lane 0: last cell of this chunk of the previous row
+                    M0 = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot; M1 = h.x; M2 = h.y; M3 = h.z;
+                    A0 = a.x; A1 = a.y; A2 = a.z; A3 = a.w;
+                    B0 = b.x; B1 = b.y; B2 = b.z; B3 = b.w;
+                } else if (lane == 0) {
+                    M0 = p_pack(prevlast, inf_min);
+                }
+            }
 #pragma unroll 1
-            for (int k = 0; k < ri.y; ++k) {  // predecessors in in_id order (abpoa_align_simd.c:966-1029)
-                int4 pm = pm0;
-                int pk = p0;
-                if (k > 0) { pk = pool_row[ri.x + k]; pm = rowmeta[pk]; }
+            for (int k = 1; k < ri.y; ++k) {  // further predecessors in in_id order (abpoa_align_simd.c:966-1029)
+                const int pk = pool_row[ri.x + k];
+                const int4 pm = rowmeta[pk];
                 const int pcb = pm.y >> 8, pce = pm.z >> 8;
                 if (c >= pcb && c <= pce + 1) {
                     const unsigned pn_ = (unsigned)(pce - pcb + 1), idx = (unsigned)pm.x + (unsigned)(c - pcb);
                     const bool in_ring = prev_res && pk == i - 1;
-                    int prevlast = inf_min;  // H_p[c0 - 1]: the last halfword of the previous chunk-plane
+                    int prevlast = inf_min;
                     if (c > pcb) {
-                        if (in_ring && c > cb) prevlast = ring_last;  // that chunk was read one iteration ago
+                        if (in_ring && c > cb) prevlast = ring_last;
                         else prevlast = *reinterpret_cast<const short *>(slab + (size_t)idx * P16_CPB - 2);
                     }
                     if (c <= pce) {
@@ -298,7 +332,7 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
                         }
                         const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
                         const unsigned s0 = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot;
-                        if (in_ring) ring_last = p_hi(rot);  // lane 0: last cell of this chunk of the previous row
+                        if (in_ring) ring_last = p_hi(rot);
                         M0 = p_max(M0, s0); M1 = p_max(M1, h.x); M2 = p_max(M2, h.y); M3 = p_max(M3, h.z);
                         A0 = p_max(A0, a.x); A1 = p_max(A1, a.y); A2 = p_max(A2, a.z); A3 = p_max(A3, a.w);
                         B0 = p_max(B0, b.x); B1 = p_max(B1, b.y); B2 = p_max(B2, b.z); B3 = p_max(B3, b.w);
@@ -364,12 +398,12 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
                 A0 = (A0 & ~m0) | (INFP & m0); A1 = (A1 & ~m1) | (INFP & m1); A2 = (A2 & ~m2) | (INFP & m2); A3 = (A3 & ~m3) | (INFP & m3);
                 B0 = (B0 & ~m0) | (INFP & m0); B1 = (B1 & ~m1) | (INFP & m1); B2 = (B2 & ~m2) | (INFP & m2); B3 = (B3 & ~m3) | (INFP & m3);
             }
-            const unsigned didx = roff + (unsigned)(c - cb), un = (unsigned)nch;
-            p16_st(slab_lane + (size_t)didx * P16_CPB, H0, H1, H2, H3);
-            p16_st(slab_lane + (size_t)(didx + un) * P16_CPB, A0, A1, A2, A3);
-            p16_st(slab_lane + (size_t)(didx + 2 * un) * P16_CPB, B0, B1, B2, B3);
-            p16_st(slab_lane + (size_t)(didx + 3 * un) * P16_CPB, F10, F11, F12, F13);
-            p16_st(slab_lane + (size_t)(didx + 4 * un) * P16_CPB, F20, F21, F22, F23);
+            p16_st(dst, H0, H1, H2, H3);
+            p16_st(dst + pstride, A0, A1, A2, A3);
+            p16_st(dst + 2 * pstride, B0, B1, B2, B3);
+            p16_st(dst + 3 * pstride, F10, F11, F12, F13);
+            p16_st(dst + 4 * pstride, F20, F21, F22, F23);
+            dst += P16_CPB;
             if (cur_res) {  // after every predecessor read of this chunk: a lane only ever touches its own slices
                 const unsigned ro = (unsigned)(c % P16_SMCH) * (3 * P16_CPB);
                 ring_st(ring, ro, H0, H1, H2, H3); ring_st(ring, ro + P16_CPB, A0, A1, A2, A3); ring_st(ring, ro + 2 * P16_CPB, B0, B1, B2, B3);

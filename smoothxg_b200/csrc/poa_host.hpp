@@ -34,15 +34,16 @@ inline void build_params(const poa_b200_params_t &p, const poa_b200_engine_opts_
     // builds into inf_min (512 * max(e1,e2), abpoa_align_simd.c:1295) must cover one mismatch, one gap open
     // and the scan's position offsets
     const long long emax = std::max(d.e1, d.e2);
-    d.p16_ok = (o.flags & 1) == 0 && emax >= 1 && emax <= 100 && 240 * emax >= (long long)d.min_mis + std::max(d.oe1, d.oe2) + 64
+    d.gap_mode = p.gap_open1 == 0 ? 2 : (p.gap_open2 == 0 ? 1 : 0);  // abpoa_align.c:87-91
+    d.p16_ok = d.gap_mode == 0 && (o.flags & 1) == 0 && emax >= 1 && emax <= 100 && 240 * emax >= (long long)d.min_mis + std::max(d.oe1, d.oe2) + 64
                && d.oe1 > d.e1 && d.oe2 > d.e2;
 }
 
 inline int check_params(const poa_b200_params_t &p) {
-    if (!(p.gap_open1 > 0 && p.gap_open2 > 0))
-        return set_err(POA_B200_EUNSUP, "only the convex gap mode (gap_open1 > 0 && gap_open2 > 0) is implemented");
-    if (p.gap_ext1 < 0 || p.gap_ext2 < 0 || p.align_mode < 0 || p.align_mode > 1)
-        return set_err(POA_B200_EARG, "bad gap extension or align_mode");
+    if (p.gap_open1 < 0 || p.gap_open2 < 0 || p.gap_ext1 < 0 || p.gap_ext2 < 0 || p.align_mode < 0 || p.align_mode > 1)
+        return set_err(POA_B200_EARG, "negative gap penalty or bad align_mode");
+    if (p.gap_ext1 == 0 && p.gap_ext2 == 0)
+        return set_err(POA_B200_EUNSUP, "gap extension 0: the reference's 16-bit scores have no head room (inf_min = INT16_MIN + ...); refused");
     // The kernel evaluates F as a max-plus prefix scan in 32-bit registers; that equals the reference's
     // wrapping 16-bit arithmetic as long as no junk cell can fall below INT16_MIN, which abPOA's own
     // inf_min margin guarantees for any sane scoring (abpoa_align_simd.c:1295).

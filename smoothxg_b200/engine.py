@@ -32,6 +32,7 @@ ABI_SYMBOLS = [
     "poa_b200_batch_upload", "poa_b200_batch_launch", "poa_b200_batch_download", "poa_b200_batch_finish",
     "poa_b200_batch_free", "poa_b200_batch_stats", "poa_b200_batch_device_result", "poa_b200_result_from_parts",
     "poa_b200_result_n_blocks", "poa_b200_result_block", "poa_b200_result_stats", "poa_b200_result_free",
+    "poa_b200_block_graph", "poa_b200_graph_view", "poa_b200_graph_free",
 ]
 
 
@@ -66,6 +67,26 @@ class _BlockView(C.Structure):
                 ("cigar", C.POINTER(C.c_uint64)),
                 ("in_total", C.c_int64), ("out_total", C.c_int64), ("aln_total", C.c_int64),
                 ("path_total", C.c_int64), ("cigar_total", C.c_int64), ("inband_cells", C.c_int64)]
+
+
+class _GraphView(C.Structure):
+    _fields_ = [("n_node", C.c_int32), ("node_id", C.POINTER(C.c_int32)), ("node_base", C.POINTER(C.c_char)),
+                ("n_edge", C.c_int32), ("edge_from", C.POINTER(C.c_int32)), ("edge_to", C.POINTER(C.c_int32)),
+                ("n_path", C.c_int32), ("path_off", C.POINTER(C.c_int64)), ("path_node", C.POINTER(C.c_int32))]
+
+
+@dataclass
+class BlockGraph:
+    """poa_b200_graph_view_t: what build_odgi_abPOA leaves in the odgi graph (reference src/smooth.cpp:2442-2574)."""
+    node_id: np.ndarray
+    node_base: bytes
+    edge_from: np.ndarray
+    edge_to: np.ndarray
+    path_off: np.ndarray
+    path_node: np.ndarray
+
+    def path(self, i: int) -> np.ndarray:
+        return self.path_node[self.path_off[i]:self.path_off[i + 1]]
 
 
 class Stats(C.Structure):
@@ -125,6 +146,10 @@ def load_library() -> C.CDLL:
     lib.poa_b200_result_n_blocks.argtypes = [vp]
     lib.poa_b200_result_n_blocks.restype = i64
     lib.poa_b200_result_block.argtypes = [vp, i64, C.POINTER(_BlockView)]
+    lib.poa_b200_block_graph.argtypes = [C.POINTER(_BlockView), i32, i32, C.POINTER(vp)]
+    lib.poa_b200_graph_view.argtypes = [vp, C.POINTER(_GraphView)]
+    lib.poa_b200_graph_free.argtypes = [vp]
+    lib.poa_b200_graph_free.restype = None
     lib.poa_b200_result_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.poa_b200_result_free.argtypes = [vp]
     lib.poa_b200_result_free.restype = None
@@ -210,6 +235,21 @@ class PoaResult:
                          _arr(v.aln_n, n), _arr(v.aln_id, v.aln_total),
                          _arr(v.path_len, s), _arr(v.path_node, v.path_total), _arr(v.cons_node, max(v.cons_len, 0)),
                          msa, _arr(v.best_score, s), _arr(v.n_cigar, s), cig, int(v.inband_cells))
+
+    def block_graph(self, i: int, padding_len: int = 0, include_consensus: bool = True) -> BlockGraph:
+        """The per-block graph smoothxg's build_odgi_abPOA would leave behind (poa_b200_block_graph)."""
+        v = _BlockView()
+        _check(self._lib, self._lib.poa_b200_result_block(self._h, i, C.byref(v)))
+        g = C.c_void_p()
+        _check(self._lib, self._lib.poa_b200_block_graph(C.byref(v), padding_len, int(include_consensus), C.byref(g)))
+        gv = _GraphView()
+        _check(self._lib, self._lib.poa_b200_graph_view(g, C.byref(gv)))
+        off = _arr(gv.path_off, gv.n_path + 1, np.int64)
+        out = BlockGraph(_arr(gv.node_id, gv.n_node), bytes(gv.node_base[:gv.n_node]) if gv.n_node else b"",
+                         _arr(gv.edge_from, gv.n_edge), _arr(gv.edge_to, gv.n_edge), off,
+                         _arr(gv.path_node, int(off[-1]) if off.size else 0))
+        self._lib.poa_b200_graph_free(g)
+        return out
 
     def stats(self) -> dict:
         s = Stats()

@@ -6,8 +6,8 @@ GPU box, which has no /root/reference, can still pin the oracle and the CUDA pat
 
 Upstream has no known-answer tests for abPOA, so these are our golden vectors:
   * abPOA's own test inputs: deps/abPOA/test_data/{seq,test,heter}.fa and example.c's second set
-  * seeded synthetic blocks in every mode the hot path supports (global banded / unbanded / local,
-    N bases, dedup weights, long indels, MSA on/off) and degenerate shapes (one sequence, empty block)
+  * seeded synthetic blocks in every mode the hot path supports (convex / affine / linear gaps; global banded /
+    unbanded / local, N bases, dedup weights, long indels, MSA on/off) and degenerate shapes (one sequence, empty block)
 Each case stores the flat inputs, the parameter tuple and the canonical dump (oracle/poa_dump.h)
 of an instrumented run: graph, read paths, consensus, MSA, per-sequence scores and cigars, band cells.
 """
@@ -70,6 +70,18 @@ def cases():
     out.append(("syn_divergent", make_batch(2, 6, 400, 0.25, seed=16), P(out_msa=True)))
     out.append(("syn_presets", make_batch(2, 6, 400, 0.02, seed=17), P(match=1, mismatch=19, gap_open1=39, gap_ext1=3, gap_open2=81, gap_ext2=1)))
     out.append(("syn_presets2", make_batch(2, 6, 400, 0.08, seed=18), P(match=1, mismatch=7, gap_open1=11, gap_ext1=2, gap_open2=33, gap_ext2=1)))
+    # affine gaps: what smoothxg passes when -p has four values (src/main.cpp:353-359); linear gaps: gap_open1 == 0
+    AFF, LIN = dict(gap_open2=0, gap_ext2=0), dict(gap_open1=0, gap_ext1=2, gap_open2=0, gap_ext2=0)
+    out.append(("affine_seq_fa", PoaBatch.from_strings([seq_fa]), P(out_msa=True, **AFF)))
+    out.append(("affine_global_band", make_batch(3, 8, 400, 0.03, seed=21, indel_prob=0.3, indel_len=(20, 120)), P(**AFF)))
+    out.append(("affine_local", make_batch(3, 6, 300, 0.04, seed=22, n_frac=0.01, dup_weights=True), P(local=True, out_msa=True, **AFF)))
+    out.append(("affine_unbanded", make_batch(2, 6, 300, 0.10, seed=23), P(banded=False, match=2, mismatch=5, gap_open1=8, gap_ext1=1, gap_open2=0, gap_ext2=0)))
+    out.append(("linear_seq_fa", PoaBatch.from_strings([seq_fa]), P(out_msa=True, **LIN)))
+    out.append(("linear_global_band", make_batch(3, 8, 400, 0.03, seed=24, indel_prob=0.3, indel_len=(20, 120)), P(**LIN)))
+    out.append(("linear_local", make_batch(3, 6, 300, 0.04, seed=25), P(local=True, out_msa=True, **LIN)))
+    out.append(("linear_unbanded", make_batch(2, 6, 300, 0.10, seed=26), P(banded=False, gap_open1=0, gap_ext1=3, gap_open2=0, gap_ext2=0)))
+    out.append(("affine_edge_shapes", PoaBatch.from_strings([["ACGTACGT", "ACGTTCGT", "ACGACGT"], ["A"], ["AC", "", "G"], [], ["NNNNACGTNN", "ACGT", "NNNN"]]), P(out_msa=True, **AFF)))
+    out.append(("linear_edge_shapes", PoaBatch.from_strings([["ACGTACGT", "ACGTTCGT", "ACGACGT"], ["A"], ["AC", "", "G"], [], ["NNNNACGTNN", "ACGT", "NNNN"]]), P(out_msa=True, **LIN)))
     return out
 
 

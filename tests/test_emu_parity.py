@@ -37,7 +37,8 @@ def emu():
 OUT32 = os.path.join(HERE, "emu", "_build", "libpoa_emu32.so")
 # cases the 32-lane emulation runs in the default CPU suite (the rest: POA_EMU32_ALL=1)
 FAST32 = {"abpoa_seq_fa_global", "abpoa_seq_fa_local", "abpoa_test_fa", "abpoa_example_c", "edge_shapes", "edge_shapes_local",
-          "syn_local", "syn_unbanded", "syn_presets", "syn_divergent"}
+          "syn_local", "syn_unbanded", "syn_presets", "syn_divergent", "affine_seq_fa", "linear_seq_fa", "affine_edge_shapes",
+          "linear_edge_shapes", "affine_local", "linear_local"}
 
 
 @pytest.fixture(scope="module")

@@ -82,11 +82,41 @@ def test_poa_block_call_shape(engine, oracle):
     assert np.array_equal(view_to_dump(res.block(0)).compare_part(), want.compare_part())
 
 
-def test_unsupported_gap_mode_is_refused(engine):
+@pytest.mark.parametrize("pk", [dict(gap_open2=0, gap_ext2=0), dict(gap_open1=0, gap_ext1=2, gap_open2=0, gap_ext2=0)], ids=["affine", "linear"])
+@pytest.mark.parametrize("mode", [dict(), dict(local=True, out_msa=True), dict(banded=False)], ids=["band", "local", "unbanded"])
+@pytest.mark.parametrize("warps", [1, 4])
+def test_affine_and_linear_gap_modes(oracle, pk, mode, warps):
+    """abpoa_set_gap_mode (abpoa_align.c:87-91): four-value -p in smoothxg gives the affine kernel; gap_open1 = 0 the linear one."""
+    batch = synth.make_batch(n_blocks=6, n_seqs=8, length=600, seed=220, indel_prob=0.3, indel_len=(20, 150), n_frac=0.01, dup_weights=True)
+    kw = dict(pk, **mode)
+    want = oracle.poa_batch(oracle_params(**kw), batch)
+    eng = E.PoaEngine(device=0, emit_cigar=True, warps_per_block=warps)
+    st = _check_batch(eng, batch, E.make_params(**kw), want, str(kw))
+    assert st["inband_cells"] == sum(d.inband_cells for d in want)
+    eng.close()
+
+
+def test_zero_gap_extension_is_refused(engine):
+    """e1 = e2 = 0 leaves the reference's 16-bit scores without head room (inf_min = INT16_MIN + ..., abpoa_align_simd.c:1295)."""
     batch = synth.make_batch(n_blocks=1, n_seqs=2, length=50, seed=1)
     with pytest.raises(E.PoaError) as e:
-        engine.run_batch(batch, E.make_params(gap_open2=0, gap_ext2=0))
+        engine.run_batch(batch, E.make_params(gap_ext1=0, gap_ext2=0))
     assert e.value.code == E.EUNSUP
+
+
+def test_block_graph_from_gpu_results(engine):
+    """poa_b200_block_graph (build_odgi_abPOA equivalent, src/smooth.cpp:2442-2574) on results of the CUDA path."""
+    from tests.test_block_graph import build_odgi_restated
+    batch = synth.make_batch(n_blocks=5, n_seqs=9, length=500, seed=230, indel_prob=0.3, dup_weights=True)
+    res = engine.run_batch(batch, E.make_params(out_msa=True))
+    for b in range(batch.n_blocks):
+        v = res.block(b)
+        for padding in (0, 31):
+            g = res.block_graph(b, padding, True)
+            nodes, edges, paths = build_odgi_restated(v, padding, True)
+            assert g.node_id.tolist() == nodes and list(zip(g.edge_from.tolist(), g.edge_to.tolist())) == edges
+            assert [g.path(i).tolist() for i in range(len(paths))] == paths
+    res.close()
 
 
 def test_empty_batch(engine):

@@ -29,8 +29,11 @@ def test_oracle_lane_count_only_moves_junk(oracle):
         oracle.set_lane_counts(32, 16)
 
 
-def test_affine_is_refused(oracle):
+def test_gap_mode_follows_abpoa_set_gap_mode(oracle):
+    """gap_open1 == 0 -> linear, gap_open2 == 0 -> affine, else convex (abpoa_align.c:87-91): the three kernels give
+    different graphs on an indel-rich block, and each is pinned by its own golden case above."""
     from oracle.oracle import make_params
-    p = make_params(gap_open2=0, gap_ext2=0)
-    name, batch, _, _ = CASES[0]
-    assert oracle.poa_block(p, *batch.block(0)) is None
+    name, batch, _, _ = next(c for c in CASES if c[0] == "syn_indel")
+    lens = [oracle.poa_block(make_params(**kw), *batch.block(0)).raw.tobytes()
+            for kw in (dict(), dict(gap_open2=0, gap_ext2=0), dict(gap_open1=0, gap_ext1=2, gap_open2=0, gap_ext2=0))]
+    assert len(set(lens)) == 3

@@ -14,6 +14,13 @@ pytestmark = pytest.mark.skipif(not ref_available(), reason="oracle/_ref not bui
     (dict(n_blocks=2, n_seqs=6, length=400, seed=102), dict(local=True, out_msa=True)),
     (dict(n_blocks=2, n_seqs=8, length=900, seed=103, indel_prob=0.7, dup_weights=True, n_frac=0.02), dict(out_msa=True)),
     (dict(n_blocks=2, n_seqs=6, length=300, seed=104, divergence=0.15), dict(banded=False)),
+    # affine (four-value -p in smoothxg) and linear gap kernels
+    (dict(n_blocks=2, n_seqs=10, length=700, seed=111, indel_prob=0.4, indel_len=(30, 200)), dict(gap_open2=0, gap_ext2=0)),
+    (dict(n_blocks=2, n_seqs=6, length=400, seed=112, n_frac=0.02, dup_weights=True), dict(gap_open2=0, gap_ext2=0, local=True, out_msa=True)),
+    (dict(n_blocks=2, n_seqs=6, length=300, seed=113, divergence=0.15), dict(gap_open1=9, gap_ext1=1, gap_open2=0, gap_ext2=0, mismatch=3, banded=False)),
+    (dict(n_blocks=2, n_seqs=10, length=700, seed=114, indel_prob=0.4, indel_len=(30, 200)), dict(gap_open1=0, gap_ext1=2, gap_open2=0, gap_ext2=0)),
+    (dict(n_blocks=2, n_seqs=6, length=400, seed=115), dict(gap_open1=0, gap_ext1=3, gap_open2=0, gap_ext2=0, local=True, out_msa=True)),
+    (dict(n_blocks=2, n_seqs=6, length=300, seed=116, divergence=0.15), dict(gap_open1=0, gap_ext1=2, gap_open2=0, gap_ext2=0, banded=False)),
 ])
 def test_restatement_equals_reference(oracle, kw, pk):
     ref = RefAbpoa()
