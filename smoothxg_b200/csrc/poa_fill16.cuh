@@ -55,6 +55,9 @@ constexpr int P16_CW = 256;          // columns per chunk
 constexpr int P16_CPB = 512;         // bytes per chunk-plane
 constexpr int P16_SMCH = 6;          // chunks of the previous row kept in shared memory (H, E1, E2)
 constexpr int P16_RING_BYTES = P16_SMCH * 3 * P16_CPB;
+constexpr int P16_QCH = 6;           // profile chunks of the row in flight staged in shared memory
+constexpr int P16_QBUF_OFF = P16_RING_BYTES, P16_META_OFF = P16_QBUF_OFF + P16_QCH * P16_CPB;  // meta: 2 x 128 B + 128 B
+constexpr int P16_SMEM_BYTES = P16_META_OFF + 3 * 128;
 
 // address of cell (plane, j) of a row stored in the chunked layout; pm = {first chunk-plane of the row, beg, end, _}
 POA_D const short *cell_ptr16(const Ws &w, const int4 &pm, int plane, int j) {
@@ -81,6 +84,36 @@ POA_D uint4 ring_ld(ring_ptr_t p, unsigned off) {
 POA_D void ring_st(ring_ptr_t p, unsigned off, unsigned a, unsigned b, unsigned c, unsigned d) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(p + off), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+#endif
+
+// Asynchronous global -> shared copies (cp.async / LDGSTS).  Everything the next row or the next chunk needs
+// from global memory is staged this way: completion is tracked by cp.async groups, not by the load scoreboards,
+// so an in-flight prefetch can never stall an unrelated instruction that happens to share a scoreboard slot.
+// `ring_ptr_t` arithmetic: shared-space byte address (device) / host pointer (emulation).
+#ifdef POA_HOST_EMU
+static inline void cpa16(ring_ptr_t s, unsigned off, const void *g, bool l2_only) { (void)l2_only; memcpy(s + off, g, 16); }
+static inline void cpa4(ring_ptr_t s, unsigned off, const void *g) { memcpy(s + off, g, 4); }
+static inline void cpa_commit() {}
+static inline void cpa_wait_pending(int n) { (void)n; }
+static inline int ring_ld32(ring_ptr_t p, unsigned off) { int v; memcpy(&v, p + off, 4); return v; }
+#else
+POA_D void cpa16(ring_ptr_t s, unsigned off, const void *g, bool l2_only) {
+    if (l2_only) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s + off), "l"(g) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(s + off), "l"(g) : "memory");
+}
+POA_D void cpa4(ring_ptr_t s, unsigned off, const void *g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(s + off), "l"(g) : "memory"); }
+POA_D void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+POA_D void cpa_wait_pending(int n) {  // wait until at most n of the most recent groups are still in flight (uniform n)
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    }
+}
+POA_D int ring_ld32(ring_ptr_t p, unsigned off) { int v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p + off)); return v; }
 #endif
 
 POA_D uint4 p16_ld(const char *p) { return *reinterpret_cast<const uint4 *>(p); }
@@ -209,29 +242,56 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
 #ifndef POA_HOST_EMU
     __builtin_assume(__isGlobal(fp));
 #endif
-    // metadata of the row about to be evaluated is loaded one row ahead (its first predecessor's number two ahead,
-    // so that predecessor's row descriptor can be fetched one ahead as well)
-    int4 nri = rowinfo[rows > 1 ? 1 : 0];
-    int nrb = rbase[rows > 1 ? 1 : 0], np0 = fp[rows > 1 ? 1 : 0], nnp0 = fp[rows > 2 ? 2 : 0], nrr = 0, nml = 0, nmr = 0;
-    int4 npm = rowmeta[0];
-    if (wb >= 0 && rows > 1) { nrr = rr[1]; nml = p16_ldcg(&mplr[1]); nmr = p16_ldcg(&mprr[1]); }
+    // Metadata of the next row is gathered into shared memory one row ahead by cp.async, one item per lane
+    // (its first predecessor's number two ahead, so that predecessor's row descriptor can be fetched one ahead too).
+    // Layout of a 128-byte slot: +0 rowinfo, +16 rowmeta[first pred], +32 base word, +36 fp two ahead, +40 rr,
+    // +48 mplr window, +64 mprr window (16-byte windows read at L2: they are updated by reductions).
+    const ring_ptr_t sm = ring_base(sh.ring, 0);
+    // each of lanes 0..6 owns one item: its array, element size and slot offset are fixed for the whole alignment
+    const char *gsrc = nullptr; unsigned gdst = 0; int gkind = 0;  // kind: 1 = 16 bytes, 2 = 16 bytes at L2, 3 = 4 bytes
+    if (lane == 0) { gsrc = (const char *)rowinfo; gdst = 0; gkind = 1; }
+    else if (lane == 1) { gsrc = (const char *)rowmeta; gdst = 16; gkind = 1; }
+    else if (lane == 2) { gsrc = (const char *)rbase; gdst = 32; gkind = 3; }
+    else if (lane == 3) { gsrc = (const char *)fp; gdst = 36; gkind = 3; }
+    else if (lane == 4 && wb >= 0) { gsrc = (const char *)rr; gdst = 40; gkind = 3; }
+    else if (lane == 5 && wb >= 0) { gsrc = (const char *)mplr; gdst = 48; gkind = 2; }
+    else if (lane == 6 && wb >= 0) { gsrc = (const char *)mprr; gdst = 64; gkind = 2; }
+    auto gather = [&](const int n1, const int np0_n1, const int cur) {  // row n1 into its slot; `cur`: row being evaluated
+        if (n1 >= rows) return;
+        const unsigned slot = P16_META_OFF + (unsigned)(n1 & 1) * 128 + gdst;
+        // element index of this lane's item: the row itself, its first predecessor (lane 1), the row after (lane 3),
+        // or the 4-element window holding it (byte / reduction-updated arrays)
+        int idx = n1;
+        if (lane == 1) idx = np0_n1; else if (lane == 3) idx = n1 + 1;
+        const bool live = lane == 1 ? np0_n1 < cur : (lane == 3 ? n1 + 1 < rows : true);
+        if (gkind == 1 && live) cpa16(sm, slot, gsrc + (size_t)(unsigned)idx * 16, false);
+        else if (gkind == 2) cpa16(sm, slot, gsrc + (size_t)(unsigned)(idx & ~3) * 4, true);
+        else if (gkind == 3 && live) cpa4(sm, slot, gsrc + (lane == 2 ? (size_t)(unsigned)(idx & ~3) : (size_t)(unsigned)idx * 4));
+    };
+    int np0 = fp[rows > 1 ? 1 : 0];  // first predecessor of the row about to be evaluated
+    gather(1, np0, 1);
+    cpa_commit();
 
     // ---- rows in index order (abpoa_align_simd.c:1205-1221)
     for (int i = 1; i < rows; ++i) {
-        const int4 ri = nri;  // {in_off, in_n, out_off, out_n}
-        const int rb = nrb, p0 = np0;
-        const int r = nrr;
-        int ml = nml, mr = nmr;
+        cpa_wait_pending(0);
+        sync_block<NW>();  // the slot was filled by other lanes' copies
+        const unsigned slot = P16_META_OFF + (unsigned)(i & 1) * 128;
+        const uint4 ri_u = ring_ld(sm, slot), npm_u = ring_ld(sm, slot + 16);
+        const int4 ri = poa_make_int4((int)ri_u.x, (int)ri_u.y, (int)ri_u.z, (int)ri_u.w);  // {in_off, in_n, out_off, out_n}
+        const int4 npm = poa_make_int4((int)npm_u.x, (int)npm_u.y, (int)npm_u.z, (int)npm_u.w);
+        const int rb = (ring_ld32(sm, slot + 32) >> (8 * (i & 3))) & 0xff, p0 = np0;
+        const int nnp0 = i + 1 < rows ? ring_ld32(sm, slot + 36) : 0;
+        const int r = ring_ld32(sm, slot + 40);
+        int ml = ring_ld32(sm, slot + 48 + 4 * (i & 3)), mr = ring_ld32(sm, slot + 64 + 4 * (i & 3));
         // first predecessor's row descriptor: from registers when it is the row just evaluated (the common case)
         const int4 pm0 = p0 == i - 1 ? prev_meta : npm;
-        if (i + 1 < rows) {  // next row's metadata; its band inputs miss only this row's contribution, forwarded below
-            nri = rowinfo[i + 1]; nrb = rbase[i + 1]; np0 = nnp0;
-            npm = rowmeta[np0 < i ? np0 : 0];  // np0 == i: this row, taken from registers next time round
-            if (i + 2 < rows) nnp0 = fp[i + 2];
-            if (wb >= 0) { nrr = rr[i + 1]; nml = p16_ldcg(&mplr[i + 1]); nmr = p16_ldcg(&mprr[i + 1]); }
-        }
-        // rows this row hands its arg-max columns to (one per lane; fetched now, used after the last chunk)
-        const int out_row = lane < ri.w ? pool_row[ri.z + lane] : -1;
+        // next row's metadata; its band inputs miss only this row's contribution, forwarded below
+        gather(i + 1, nnp0, i);
+        // rows this row hands its arg-max columns to (one per lane; staged now, used after the last chunk)
+        if (lane < ri.w) cpa4(sm, P16_META_OFF + 256 + lane * 4, &pool_row[ri.z + lane]);
+        cpa_commit();
+        np0 = nnp0;
         int beg, end;
         if (wb < 0) { beg = 0; end = qlen; }
         else {  // abpoa_align.h:34-35, abpoa_align_simd.c:946-960
@@ -264,8 +324,12 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
         const bool cur_res = nch <= P16_SMCH;
 
         // running pointers (one 64-bit add per chunk instead of one multiply per access)
-        const char *qptr = qrow + (size_t)(unsigned)cb * P16_CPB;
-        uint4 qnext = p16_ld(qptr);  // profile chunk, fetched one chunk ahead (the buffer has a spare chunk behind the end)
+        // the row's profile chunks are staged in shared memory, one cp.async group per chunk
+        const bool qst = nch <= P16_QCH;
+        if (qst) {
+            for (int k = 0; k < nch; ++k) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qrow + (size_t)(unsigned)(cb + k) * P16_CPB, false);
+            cpa_commit();
+        }
         char *dst = slab_lane + (size_t)roff * P16_CPB;
         const size_t pstride = (size_t)(unsigned)nch * P16_CPB;
         // first predecessor (always present; for most rows the only one, and the row just evaluated)
@@ -275,9 +339,9 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
 #pragma unroll 1
         for (int c = cb; c <= ce; ++c) {
             const int c0 = c * P16_CW;
-            const uint4 qv = qnext;
-            qptr += P16_CPB;
-            qnext = p16_ld(qptr);
+            uint4 qv;
+            if (qst) { if (c == cb) cpa_wait_pending(0); qv = ring_ld(sm, P16_QBUF_OFF + (unsigned)(c - cb) * P16_CPB + lane * 16); }
+            else qv = p16_ld(qrow + (size_t)(unsigned)c * P16_CPB);
             unsigned M0 = INFP, M1 = INFP, M2 = INFP, M3 = INFP;
             unsigned A0 = INFP, A1 = INFP, A2 = INFP, A3 = INFP;  // E1 in
             unsigned B0 = INFP, B1 = INFP, B2 = INFP, B3 = INFP;  // E2 in
@@ -443,7 +507,8 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
             prev_left = left; prev_right = right;
             if (local && rmx > best_score) { best_score = rmx; best_i = i; best_j = left; }  // abpoa_align_simd.c:1208-1210
             if (wb >= 0) {  // abpoa_align_simd.c:1121-1130; reductions without a return value: nothing to wait for
-                if (out_row >= 0) { poa_red_max(&mprr[out_row], right + 1); poa_red_min(&mplr[out_row], left + 1); }
+                cpa_wait_pending(0);
+                if (lane < ri.w) { const int out_row = ring_ld32(sm, P16_META_OFF + 256 + lane * 4); poa_red_max(&mprr[out_row], right + 1); poa_red_min(&mplr[out_row], left + 1); }
                 for (int k = lane + POA_WARP; k < ri.w; k += POA_WARP) {
                     const int o = pool_row[ri.z + k];
                     poa_red_max(&mprr[o], right + 1); poa_red_min(&mplr[o], left + 1);

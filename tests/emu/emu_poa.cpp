@@ -117,7 +117,7 @@ extern "C" int32_t *emu_poa_block(const pd_params_t *pp, int n_seq, const int32_
     Shared sh; memset(&sh, 0, sizeof(sh));
     ws_bind(sh.ws, wsp, L);
 #if POA_EMU_LANES == 32
-    std::vector<char> ring((size_t)P16_RING_BYTES + 16);
+    std::vector<char> ring((size_t)P16_SMEM_BYTES + 16);
     sh.ring = ring.data();
 #endif
 #if POA_EMU_LANES > 1
