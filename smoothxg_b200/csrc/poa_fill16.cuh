@@ -292,12 +292,17 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
         if (lane < ri.w) cpa4(sm, P16_META_OFF + 256 + lane * 4, &pool_row[ri.z + lane]);
         cpa_commit();
         np0 = nnp0;
+        // second predecessor's row descriptor, once per row (every chunk needs it; a third one is rare)
+        int pk1 = -1;
+        int4 pm1 = pm0;
+        if (ri.y > 1) { pk1 = pool_row[ri.x + 1]; pm1 = rowmeta[pk1]; }
         int beg, end;
         if (wb < 0) { beg = 0; end = qlen; }
         else {  // abpoa_align.h:34-35, abpoa_align_simd.c:946-960
             int min_pre_beg = pm0.y;
             bool from_prev = p0 == i - 1;
-            for (int k = 1; k < ri.y; ++k) {
+            if (ri.y > 1) { from_prev |= pk1 == i - 1; min_pre_beg = imin(min_pre_beg, pm1.y); }
+            for (int k = 2; k < ri.y; ++k) {
                 const int pk = pool_row[ri.x + k];
                 from_prev |= pk == i - 1;
                 min_pre_beg = imin(min_pre_beg, rowmeta[pk].y);
@@ -373,8 +378,9 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
             }
 #pragma unroll 1
             for (int k = 1; k < ri.y; ++k) {  // further predecessors in in_id order (abpoa_align_simd.c:966-1029)
-                const int pk = pool_row[ri.x + k];
-                const int4 pm = rowmeta[pk];
+                int pk = pk1;
+                int4 pm = pm1;
+                if (k > 1) { pk = pool_row[ri.x + k]; pm = rowmeta[pk]; }
                 const int pcb = pm.y >> 8, pce = pm.z >> 8;
                 if (c >= pcb && c <= pce + 1) {
                     const unsigned pn_ = (unsigned)(pce - pcb + 1), idx = (unsigned)pm.x + (unsigned)(c - pcb);
