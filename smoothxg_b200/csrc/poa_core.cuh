@@ -1161,15 +1161,22 @@ POA_DN int fuse_par(Shared &sh, const uint8_t *seq, int seq_l, int wt, int *path
         }
     }
     sync_block<NW>();
-    for (int t = tid; t < seq_l; t += NT) {
-        const int x = cnode[t], b = seq[t];
-        int node = -1;
-        if (x >= 0) {
-            if (w.base[x] == b) node = x; else node = get_aligned_id(w, x, b);
+    for (int t0 = tid; t0 < seq_l; t0 += 4 * NT) {  // four positions per thread in flight (latency-bound gathers)
+        int x[4], b[4], xb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int t = t0 + u * NT; x[u] = t < seq_l ? cnode[t] : -2; b[u] = t < seq_l ? seq[t] : 0; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xb[u] = x[u] >= 0 ? w.base[x[u]] : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * NT;
+            if (x[u] == -2) continue;
+            int node = -1;
+            if (x[u] >= 0) node = xb[u] == b[u] ? x[u] : get_aligned_id(w, x[u], b[u]);
+            path[t] = node;              // existing node the base lands on, or -1: a node must be created
+            flag[t] = node < 0;
+            lastm[t] = x[u] >= 0 ? t : -1;
         }
-        path[t] = node;              // existing node the base lands on, or -1: a node must be created
-        flag[t] = node < 0;
-        lastm[t] = x >= 0 ? t : -1;
     }
     sync_block<NW>();
     const int n_new = block_excl_scan<NW>(sh, flag, flag, seq_l, scratch);  // flag[t] = rank among created nodes
@@ -1186,18 +1193,33 @@ POA_DN int fuse_par(Shared &sh, const uint8_t *seq, int seq_l, int wt, int *path
     }
     sync_block<NW>();
     if (tid == 0) sh.n_node = n_old + n_new;
-    for (int t = tid; t <= seq_l; t += NT) {  // abpoa_graph.c:480-556
-        const int from = t == 0 ? SRC_ID : path[t - 1], to = t == seq_l ? SINK_ID : path[t];
-        int exist = 0;
-        if (from < n_old && to < n_old) {
-            int n = w.in_n[to], off = w.in_off[to];
-            for (int i = 0; i < n; ++i) if (w.pool_id[off + i] == from) { w.pool_w[off + i] += wt; break; }
-            n = w.out_n[from]; off = w.out_off[from];
-            for (int i = 0; i < n; ++i) if (w.pool_id[off + i] == to) { w.pool_w[off + i] += wt; exist = 1; break; }
+    for (int t0 = tid; t0 <= seq_l; t0 += 4 * NT) {  // abpoa_graph.c:480-556; every (node, list) pair belongs to one position
+        int from[4], to[4], inn[4], ino[4], outn[4], outo[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * NT;
+            from[u] = t > seq_l ? -1 : (t == 0 ? SRC_ID : path[t - 1]);
+            to[u] = t > seq_l ? -1 : (t == seq_l ? SINK_ID : path[t]);
         }
-        if (!exist) {
-            edge_push_par(sh, w.in_off, w.in_n, to, from, wt);
-            edge_push_par(sh, w.out_off, w.out_n, from, to, wt);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            inn[u] = ino[u] = outn[u] = outo[u] = 0;
+            if (from[u] >= 0 && from[u] < n_old && to[u] < n_old) {
+                inn[u] = w.in_n[to[u]]; ino[u] = w.in_off[to[u]]; outn[u] = w.out_n[from[u]]; outo[u] = w.out_off[from[u]];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (from[u] < 0) continue;
+            int exist = 0;
+            if (from[u] < n_old && to[u] < n_old) {
+                for (int i = 0; i < inn[u]; ++i) if (w.pool_id[ino[u] + i] == from[u]) { w.pool_w[ino[u] + i] += wt; break; }
+                for (int i = 0; i < outn[u]; ++i) if (w.pool_id[outo[u] + i] == to[u]) { w.pool_w[outo[u] + i] += wt; exist = 1; break; }
+            }
+            if (!exist) {
+                edge_push_par(sh, w.in_off, w.in_n, to[u], from[u], wt);
+                edge_push_par(sh, w.out_off, w.out_n, from[u], to[u], wt);
+            }
         }
     }
     sync_block<NW>();

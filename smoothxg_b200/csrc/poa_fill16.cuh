@@ -521,8 +521,9 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
                 }
             }
         }
-        sync_block<NW>();
+        // no barrier here: the next row starts with one (after its cp.async wait)
     }
+    sync_block<NW>();
     // ---- global best (abpoa_align_simd.c:1092-1105)
     if (lane == 0) {
         if (!local) {
