@@ -253,17 +253,22 @@ def main():
             t = torch.from_numpy(a).pin_memory()
             keep.append(t)
             setattr(pinned, name, t.numpy())
-        r = eng.run_batch(pinned, params); r.close()  # warm the pinned/device pools
+        for _ in range(2):  # warm the pinned/device pools (the first call page-locks ~4 GB for the result)
+            r = eng.run_batch(pinned, params); r.close()
         barrier()
         t0 = time.perf_counter()
         last = None
+        e2e_each, e2e_parts = [], {}
         for _ in range(args.steps):
+            ts = time.perf_counter()
             if last is not None:
                 last.close()
             r = eng.run_batch(pinned, params)
             s2 = r.stats(); h2d, d2h = s2["h2d_bytes"], s2["d2h_bytes"]
             chk = r.block(0).n_node  # the step's result is read on the host
             last = r
+            e2e_each.append((time.perf_counter() - ts) * 1e3)
+            e2e_parts = {"h2d_ms": s2["h2d_ms"], "kernel_ms": s2["kernel_ms"], "d2h_ms": s2["d2h_ms"]}
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
         assert chk > 2
@@ -303,7 +308,8 @@ def main():
                              "kernel_ms_per_launch": per_launch_s * 1e3}}
         if e2e_ms is not None:
             line["e2e"] = {"value": tot_cells * K / (e2e_ms / 1e3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                           "blocks_per_s": tot_blocks * K / (e2e_ms / 1e3), "ms_per_step": e2e_ms / K}
+                           "blocks_per_s": tot_blocks * K / (e2e_ms / 1e3), "ms_per_step": e2e_ms / K,
+                           "ms_each_step_rank0": [round(x, 1) for x in e2e_each], "last_step_parts_rank0": e2e_parts}
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             n_sample = args.cpu_sample or max(threads, min(batch.n_blocks, 64 * threads))

@@ -292,6 +292,14 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
         if (lane < ri.w) cpa4(sm, P16_META_OFF + 256 + lane * 4, &pool_row[ri.z + lane]);
         cpa_commit();
         np0 = nnp0;
+        // profile chunks of this row: staged now for the chunk range the previous row covered plus one (bands move
+        // slowly), so the copies overlap the band computation below; corrected after it if the guess was wrong
+        int scb = prev_meta.y >> 8, sce = imin(imin((prev_meta.z >> 8) + 1, scb + P16_QCH - 1), nchq - 1);
+        {
+            const char *qg = qp + (size_t)(unsigned)(rb * nchq + scb) * P16_CPB + lane * 16;
+            for (int k = 0; k <= sce - scb; ++k) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qg + (size_t)k * P16_CPB, false);
+            cpa_commit();
+        }
         // second predecessor's row descriptor, once per row (every chunk needs it; a third one is rare)
         int pk1 = -1;
         int4 pm1 = pm0;
@@ -330,10 +338,12 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
 
         // running pointers (one 64-bit add per chunk instead of one multiply per access)
         // the row's profile chunks are staged in shared memory, one cp.async group per chunk
-        const bool qst = nch <= P16_QCH;
-        if (qst) {
+        bool qst = cb >= scb && ce <= sce;
+        if (!qst && nch <= P16_QCH) {  // wrong guess (rare): let the speculative copies land, then stage the exact range over them
+            cpa_wait_pending(0);
             for (int k = 0; k < nch; ++k) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qrow + (size_t)(unsigned)(cb + k) * P16_CPB, false);
             cpa_commit();
+            scb = cb; qst = true;
         }
         char *dst = slab_lane + (size_t)roff * P16_CPB;
         const size_t pstride = (size_t)(unsigned)nch * P16_CPB;
@@ -344,9 +354,6 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
 #pragma unroll 1
         for (int c = cb; c <= ce; ++c) {
             const int c0 = c * P16_CW;
-            uint4 qv;
-            if (qst) { if (c == cb) cpa_wait_pending(0); qv = ring_ld(sm, P16_QBUF_OFF + (unsigned)(c - cb) * P16_CPB + lane * 16); }
-            else qv = p16_ld(qrow + (size_t)(unsigned)c * P16_CPB);
             unsigned M0 = INFP, M1 = INFP, M2 = INFP, M3 = INFP;
             unsigned A0 = INFP, A1 = INFP, A2 = INFP, A3 = INFP;  // E1 in
             unsigned B0 = INFP, B1 = INFP, B2 = INFP, B3 = INFP;  // E2 in
@@ -412,7 +419,10 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
                 }
             }
             if (local && c == 0 && lane == 0) M0 = p_max(M0, p_pack(0, inf_min));  // abpoa_align_simd.c:974 (`first` = 0)
-            // H~ = max(M + profile, E1, E2) (abpoa_align_simd.c:1032-1050)
+            // H~ = max(M + profile, E1, E2) (abpoa_align_simd.c:1032-1050); the profile chunk is read as late as possible
+            uint4 qv;
+            if (qst) { if (c == cb) cpa_wait_pending(0); qv = ring_ld(sm, P16_QBUF_OFF + (unsigned)(c - scb) * P16_CPB + lane * 16); }
+            else qv = p16_ld(qrow + (size_t)(unsigned)c * P16_CPB);
             unsigned H0 = p_max3(p_add(M0, qv.x), A0, B0), H1 = p_max3(p_add(M1, qv.y), A1, B1);
             unsigned H2 = p_max3(p_add(M2, qv.z), A2, B2), H3 = p_max3(p_add(M3, qv.w), A3, B3);
             // cells of this chunk outside [beg,end]
