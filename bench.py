@@ -268,7 +268,8 @@ def main():
             chk = r.block(0).n_node  # the step's result is read on the host
             last = r
             e2e_each.append((time.perf_counter() - ts) * 1e3)
-            e2e_parts = {"h2d_ms": s2["h2d_ms"], "kernel_ms": s2["kernel_ms"], "d2h_ms": s2["d2h_ms"]}
+            e2e_parts.setdefault("h2d_ms", []).append(round(s2["h2d_ms"], 1)); e2e_parts.setdefault("kernel_ms", []).append(round(s2["kernel_ms"], 1))
+            e2e_parts.setdefault("d2h_ms", []).append(round(s2["d2h_ms"], 1))
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
         assert chk > 2
@@ -309,7 +310,7 @@ def main():
         if e2e_ms is not None:
             line["e2e"] = {"value": tot_cells * K / (e2e_ms / 1e3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                            "blocks_per_s": tot_blocks * K / (e2e_ms / 1e3), "ms_per_step": e2e_ms / K,
-                           "ms_each_step_rank0": [round(x, 1) for x in e2e_each], "last_step_parts_rank0": e2e_parts}
+                           "ms_each_step_rank0": [round(x, 1) for x in e2e_each], "parts_each_step_rank0": e2e_parts}
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             n_sample = args.cpu_sample or max(threads, min(batch.n_blocks, 64 * threads))

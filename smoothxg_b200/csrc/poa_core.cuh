@@ -1,28 +1,31 @@
 // poa_core.cuh -- device code of the B200-native POA engine (one CUDA block per POA block).
 //
-// What it computes is abPOA v1.5.4's convex-gap partial order alignment exactly as smoothxg drives
-// it (reference citations relative to /root/reference):
+// What it computes is abPOA v1.5.4's partial order alignment (convex, affine or linear gaps) exactly as
+// smoothxg drives it (reference citations relative to /root/reference):
 //   per-block driver loop          deps/abPOA/src/abpoa_align.c:304-344        -> poa_block()
 //   int16/int32 choice, inf_min    deps/abPOA/src/abpoa_align_simd.c:1286-1302 -> poa_block()
-//   first row / row recurrence     deps/abPOA/src/abpoa_align_simd.c:617-688, :935-1074 -> fill<>()
+//   first row / row recurrence     deps/abPOA/src/abpoa_align_simd.c:617-688, :935-1074 (cg), :817-933 (ag), :727-815 (lg)
+//                                  -> fill<NW,S,MODE>() here, fill_p16<>() in poa_fill16.cuh (packed 16-bit, convex)
 //   adaptive band                  deps/abPOA/src/abpoa_align.h:34-35, abpoa_align_simd.c:1107-1130
 //   best cell                      deps/abPOA/src/abpoa_align_simd.c:1092-1105, :1208-1210
-//   backtrack                      deps/abPOA/src/abpoa_align_simd.c:309-458    -> backtrack<>()
-//   graph fusion                   deps/abPOA/src/abpoa_graph.c:688-773, :480-556, :573-592 -> fuse()
-//   topological sort               deps/abPOA/src/abpoa_graph.c:322-357 (:221-266, :192-219, :268-309)
+//   backtrack                      deps/abPOA/src/abpoa_align_simd.c:309-458 (cg), :196-307 (ag), :116-194 (lg) -> backtrack<>(), bt_step<>()
+//   graph fusion                   deps/abPOA/src/abpoa_graph.c:688-773, :480-556, :573-592 -> fuse_par()
+//   topological sort               deps/abPOA/src/abpoa_graph.c:322-357 (:221-266, :192-219, :268-309) -> toposort() (local mode),
+//                                  toposort_incr() (global mode: incremental order, pointer-jumping `remain`)
 //   heaviest-bundle consensus      deps/abPOA/src/abpoa_output.c:468-536, :375-391
 //   MSA rank                       deps/abPOA/src/abpoa_graph.c:359-419
 //
-// How it computes it is not the reference's: the DP row is evaluated by all threads of the CUDA
-// block at once on 8-cell vectors in absolute column coordinates (so predecessor rows line up without
-// shifts), the horizontal gap recurrences F1/F2 are max-plus prefix scans (G[j] = F[j] + e*j turns
-// F[j] = max(F[j-1]-e, H[j-1]-oe) into a running maximum) done with warp shuffles, the row maximum /
-// arg-max for the adaptive band is a redux.sync reduction, rows are stored band-only, and the whole
-// per-block loop (align, traceback, fusion, topological sort, consensus, MSA) stays on the device.
+// How it computes it is not the reference's: a DP row is evaluated by all lanes at once in absolute column
+// coordinates (so predecessor rows line up without shifts), the horizontal gap recurrences F1/F2 are max-plus
+// prefix scans (G[j] = F[j] + e*j turns F[j] = max(F[j-1]-e, H[j-1]-oe) into a running maximum) done with warp
+// shuffles, the row maximum / arg-max for the adaptive band is a redux.sync reduction, rows are stored band-only,
+// traceback commits diagonal runs 32 steps at a time, fusion and the order update are data-parallel, and the
+// whole per-block loop (align, traceback, fusion, order, consensus, MSA) stays on the device.
 //
-// The file also compiles as plain C++ with -DPOA_HOST_EMU (one emulated thread, warp size 1).  That
-// build exists only so the serial logic can be unit-debugged on a machine without a GPU; it is never
-// built by __graft_entry__.build(), never shipped and never reachable from the C ABI.
+// The file also compiles as plain C++ with -DPOA_HOST_EMU: one emulated thread (warp size 1), or with
+// -DPOA_EMU_LANES=32 thirty-two lock-step lanes run as fibers by the test harness (tests/emu/emu_poa.cpp), so
+// the warp-level logic is checked against the golden vectors on a machine without a GPU.  Those builds are test
+// infrastructure: never built by __graft_entry__.build(), never shipped, never reachable from the C ABI.
 #pragma once
 #include <stdint.h>
 #include <limits.h>
@@ -343,7 +346,7 @@ POA_DN void toposort(Shared &sh, int banded) {
 // score ties by BFS index, abpoa_align_simd.c:1208-1210, so it keeps the exact BFS.)  So the order is kept
 // as an invariant: topological, aligned groups contiguous.  A fused read visits old nodes in increasing
 // order; a node it creates is placed right behind the aligned group of the old node it follows (insertion)
-// or is aligned with (mismatch) -- fuse() records that old node in anc[].  New positions are old position +
+// or is aligned with (mismatch) -- fuse_par() records that old node in anc[].  New positions are old position +
 // number of insertions in front: one histogram, one block-wide prefix sum, no serial walk.
 // `remain` (abpoa_graph.c:268-309: edges to the sink along heaviest out-edges) is pointer jumping.
 // ------------------------------------------------------------------------------------------------
@@ -996,6 +999,7 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
     if (lane == 0) { sh.n_cigar = 0; if (j < qlen) push_cigar(sh, CINS, qlen - j, -1, qlen - 1); }
     poa_sync_warp();
     int n = sh.n_cigar;
+    poa_sync_warp();  // every lane has read it before lane 0 may write it again below
     while (i > 0 && j > 0) {
         if (POA_WARP > 1 && cur_op == OP_ALL) {
             // rows of the run: chase the first-predecessor table (all lanes walk the same chain; 32 dependent but
@@ -1052,63 +1056,14 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
 }
 
 // ------------------------------------------------------------------------------------------------
-// graph fusion (abpoa_graph.c:688-773), one thread.  path[qpos] = node id the base was placed on.
-// ------------------------------------------------------------------------------------------------
-POA_DN int fuse(Shared &sh, const uint8_t *seq, int seq_l, int wt, int *path) {
-    Ws &w = sh.ws;
-    const unsigned long long *cig = w.cig + sh.cig_base;
-    const int n_cigar = sh.n_cigar;
-    if (n_cigar == 0) return 0;  // abpoa_graph.c:706-708: the read is silently not added
-    if (sh.n_node + seq_l > sh.nmax) { sh.err = ST_ESLAB; return 0; }  // a read adds at most seq_l nodes
-    int query_id = -1, last_new = 0, last_id = SRC_ID;
-    const int n_old = sh.n_node;
-    int *anc = w.tmp2;       // anc[new_id - n_old]: see toposort_incr()
-    int anc_ref = SRC_ID;    // last pre-existing node on (or aligned with) the path so far
-    for (int i = 0; i < n_cigar; ++i) {
-        int op = (int)(cig[i] & 0xf);
-        if (op == CMATCH) {
-            int node_id = (int)((cig[i] >> 34) & 0x3fffffff);
-            query_id++;
-            int b = seq[query_id];
-            if (w.base[node_id] != b) {
-                int aligned_id = get_aligned_id(w, node_id, b);
-                if (aligned_id != -1) {
-                    add_edge(sh, last_id, aligned_id, 1 - last_new, wt);
-                    last_id = aligned_id; last_new = 0;
-                } else {
-                    int new_id = add_node(sh, b);
-                    add_edge(sh, last_id, new_id, 0, wt);
-                    last_id = new_id; last_new = 1;
-                    add_aligned(w, node_id, new_id);
-                    anc[new_id - n_old] = node_id;
-                }
-            } else {
-                add_edge(sh, last_id, node_id, 1 - last_new, wt);
-                last_id = node_id; last_new = 0;
-            }
-            anc_ref = node_id;
-            path[query_id] = last_id;
-        } else if (op == CINS) {
-            int len = (int)((cig[i] >> 4) & 0x3fffffff);
-            query_id += len;
-            for (int j = len - 1; j >= 0; --j) {
-                int new_id = add_node(sh, seq[query_id - j]);
-                add_edge(sh, last_id, new_id, 0, wt);
-                last_id = new_id; last_new = 1;
-                path[query_id - j] = last_id;
-                anc[new_id - n_old] = anc_ref;
-            }
-        }
-    }
-    add_edge(sh, last_id, SINK_ID, 1 - last_new, wt);
-    return seq_l;
-}
-
-// ------------------------------------------------------------------------------------------------
-// graph fusion, all threads.  Same result as fuse(): the read's path visits every graph node at most once,
+// graph fusion (abpoa_graph.c:688-773), all threads.  path[qpos] = node id the base was placed on.  The reference
+// walks the cigar once, serially: MATCH on the same base reuses the node, MATCH on another base takes the aligned
+// node holding that base or creates one and links it into the aligned group, INS creates nodes, DEL adds nothing;
+// every step adds `weight` to the edge from the previous path node (abpoa_add_graph_edge, :480-556), the last one
+// to the sink.  Same result here without the serial walk: the read's path visits every graph node at most once,
 // so each (node, edge list) pair is touched by exactly one query position and the positions can be
 // processed independently once node ids are known; ids of created nodes are handed out in query order by
-// a prefix sum, which is the order fuse() creates them in.
+// a prefix sum, which is the order the reference creates them in.
 // ------------------------------------------------------------------------------------------------
 POA_D void edge_push_par(Shared &sh, int *off_arr, int *n_arr, int v, int id, int wt) {
     Ws &w = sh.ws;

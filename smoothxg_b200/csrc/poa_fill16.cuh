@@ -351,7 +351,11 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
         const int pcb0 = pm0.y >> 8, pce0 = pm0.z >> 8;
         const unsigned pn0 = (unsigned)(pce0 - pcb0 + 1);
         const bool ring0 = prev_res && p0 == i - 1;
+#ifdef P16_UNROLL2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
         for (int c = cb; c <= ce; ++c) {
             const int c0 = c * P16_CW;
             unsigned M0 = INFP, M1 = INFP, M2 = INFP, M3 = INFP;

@@ -1,0 +1,26 @@
+// CPU-only check of poa_b200::dedup_sequences (reference src/smooth.cpp:217-241) and poa_b200_encode_bases
+// (reference src/smooth.cpp:304-313): reads "name strand seq" lines, prints the groups.
+#include <cstdio>
+#include <iostream>
+#include <sstream>
+#include "poa_b200_smooth.hpp"
+int main() {
+    std::vector<std::string> seqs, names; std::vector<bool> revs;
+    std::string line;
+    while (std::getline(std::cin, line)) {
+        std::istringstream is(line); std::string n, s, q;
+        if (!(is >> n >> s)) continue;
+        is >> q; names.push_back(n); revs.push_back(s == "-"); seqs.push_back(q);
+    }
+    const poa_b200::block_sequences b = poa_b200::dedup_sequences(seqs, names, revs);
+    for (size_t i = 0; i < b.seqs.size(); ++i) {
+        std::vector<uint8_t> codes(b.seqs[i].size());
+        poa_b200_encode_bases(b.seqs[i].data(), (int64_t)codes.size(), codes.data());
+        printf("%d", b.weights[i]);
+        for (size_t z = 0; z < b.dup_seq_names[i].size(); ++z) printf(" %s%c", b.dup_seq_names[i][z].c_str(), b.dup_is_revs[i][z] ? '-' : '+');
+        printf(" ");
+        for (uint8_t c : codes) printf("%d", (int)c);
+        printf("\n");
+    }
+    return 0;
+}

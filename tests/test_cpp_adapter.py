@@ -28,6 +28,18 @@ def test_adapter_header_compiles_and_links():
     assert os.path.exists(build_exe())
 
 
+def test_dedup_and_encoding_on_cpu():
+    """dedup_sequences = the XXH64 loop of src/smooth.cpp:217-241 (first-occurrence order, multiplicities, names and
+    strands per group); encode_bases = ab_nt4_table."""
+    exe = os.path.join(os.path.dirname(EXE), "dedup_test")
+    src = os.path.join(ROOT, "tests", "cpp", "dedup_test.cpp")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L", LIBDIR, "-lpoa_b200", f"-Wl,-rpath,{LIBDIR}"])
+    inp = "a\t+\tACGT\nb\t-\tACGTN\nc\t+\tACGT\nd\t-\tACGT\ne\t+\tacgu\nf\t+\tACGTN\n"
+    out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    assert out == ["3 a+ c+ d- 0123", "2 b- f+ 01234", "1 e+ 0123"]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("padding,local,cons", [(0, 0, "Consensus_0"), (5, 0, "-"), (3, 1, "cons")])
 def test_adapter_matches_ctypes_path(padding, local, cons):
