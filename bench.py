@@ -40,6 +40,7 @@ WORKLOADS = {
     # name: (n_blocks, n_seqs, length, divergence)
     "10000x32x2kb": (10000, 32, 2000, 0.02),
     "1000x16x1kb": (1000, 16, 1000, 0.02),
+    "100x256x8kb": (100, 256, 8000, 0.02),   # BASELINE.json configs[3], deep-block stress (int32 scores once rows > 16 361)
 }
 METRIC = "poa_dp_inband_gcells_per_s"
 UNIT = "Gcells/s"
@@ -162,7 +163,7 @@ def main():
     params_kw = dict(local=False, banded=True, out_cons=True, out_msa=False)
     config = {"workload": f"synthetic {nb} blocks x {ns} seqs x {L} bp per GPU, {div:.0%} divergence, global, adaptive band wb=311 wf=0.03, "
                           f"convex gaps 1,4,6,2,26,1 (BASELINE.json configs[2])" if args.workload == "10000x32x2kb" else
-                          f"synthetic {nb} blocks x {ns} seqs x {L} bp per GPU (BASELINE.json configs[1])",
+                          f"synthetic {nb} blocks x {ns} seqs x {L} bp per GPU (BASELINE.json configs[{1 if args.workload == '1000x16x1kb' else 3}])",
               "blocks_per_gpu": nb, "seqs_per_block": ns, "seq_len": L, "divergence": div,
               "l2": "inputs + per-block workspaces are tens of GB per step, far larger than the 126 MB L2 (no flush needed)",
               "sharding": "static, one 10k-block shard per rank, no data-path collective"}
@@ -298,7 +299,7 @@ def main():
         achieved = (float(cells) * bytes_per_cell) / per_launch_s / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int16", "data": "synthetic", "config": config,
+                "dtype": "int16" if args.workload != "100x256x8kb" else "int16/int32", "data": "synthetic", "config": config,
                 "blocks_per_s": tot_blocks * K / sec, "inband_cells_per_step": tot_cells, "p_bar": pbar,
                 "clocks": clocks, "gpu_launches": int(launches_all),
                 "engine": {"n_ctas": st["n_ctas"], "warps_per_block": st["warps_per_block"], "workspace_gb": st["workspace_bytes"] / 1e9,

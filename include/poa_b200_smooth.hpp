@@ -52,6 +52,18 @@ inline block_sequences dedup_sequences(const std::vector<std::string> &seqs, con
     return b;
 }
 
+// Score preset smooth_and_lace picks from the block's estimated identity when -a is given (src/smooth.cpp:2028-2062;
+// the MinHash estimate itself, rkmh::hash_sequences / rkmh::compare :2005-2023, stays in smoothxg).  Returns false and
+// leaves the scores alone below 0.90 ("use the set/default penalties").  Blocks with different presets go into one
+// batch per preset (the engine's parameters are per batch).
+inline bool adaptive_poa_preset(float est_identity_threshold, int &poa_m, int &poa_n, int &poa_g, int &poa_e, int &poa_q, int &poa_c) {
+    static const int presets[5][7] = {{99, 1, 19, 39, 3, 81, 1}, {98, 1, 13, 31, 3, 51, 1}, {97, 1, 9, 16, 2, 41, 1},
+                                      {95, 1, 7, 11, 2, 33, 1}, {90, 1, 4, 6, 2, 26, 1}};
+    for (const auto &p : presets)
+        if (est_identity_threshold >= (float)p[0] / 100.0f) { poa_m = p[1]; poa_n = p[2]; poa_g = p[3]; poa_e = p[4]; poa_q = p[5]; poa_c = p[6]; return true; }
+    return false;
+}
+
 struct step_t { int32_t node_id; bool is_rev; };            // odgi handle: id + orientation
 struct path_t { std::string name; std::vector<step_t> steps; };
 

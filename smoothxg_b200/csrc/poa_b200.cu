@@ -231,7 +231,9 @@ Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int lev
     long long width = max_len + 1;
     if (level >= 2) { nmax = worst_nodes; rows = worst_nodes; }
     else {
-        double f = rows_factor * (level == 1 ? 4.0 : 1.0);
+        // graph rows per query base: ~1.5 for 32 sequences at 2 % divergence, ~3.6 for 256: deep blocks get a
+        // proportionally larger first guess so that they are not all re-run
+        double f = rows_factor * (level == 1 ? 4.0 : 1.0) * (1.0 + (double)std::max<long long>(0, max_seq - 32) / 128.0);
         rows = std::min<long long>(worst_nodes, (long long)(f * max_len) + 64);
         nmax = std::min<long long>(worst_nodes, rows + max_len / 2 + 64);
         if (wb >= 0) {

@@ -63,6 +63,20 @@ def test_int32_scores_and_mid_block_switch(engine, oracle):
         _check_batch(engine, batch, E.make_params(), want, str(kw))
 
 
+@pytest.mark.parametrize("warps", [0, 1])
+def test_deep_block(oracle, warps):
+    """BASELINE.json configs[3] in miniature (deep-block stress): 96 sequences per block, the graph grows to ~3x the
+    sequence length, the first-guess workspace overflows and the block is re-run with a larger one.  warps=0 lets the
+    engine choose (several warps per block for a two-block batch: generic fill), warps=1 forces the packed fill."""
+    batch = synth.make_batch(n_blocks=2, n_seqs=96, length=2500, seed=240, divergence=0.03)
+    want = oracle.poa_batch(oracle_params(), batch)
+    assert want[0].n_node > 2 * 2500
+    eng = E.PoaEngine(device=0, emit_cigar=True, warps_per_block=warps)
+    st = _check_batch(eng, batch, E.make_params(), want, f"deep/w{warps}")
+    assert st["inband_cells"] == sum(d.inband_cells for d in want)
+    eng.close()
+
+
 def test_workspace_retry_gives_identical_results(oracle):
     """Blocks that exhaust the first-guess workspace are re-run with larger ones; results must not change."""
     batch = synth.make_batch(n_blocks=6, n_seqs=8, length=600, seed=9, divergence=0.25)
