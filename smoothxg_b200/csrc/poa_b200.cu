@@ -30,7 +30,7 @@ using namespace poa;
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, POA_MIN_BLOCKS / NW) poa_b200_block_kernel(DevParams P, DevBatch B, WsLayout L, char *ws_base, DevOut O) {
     __shared__ Shared sh;
-    extern __shared__ __align__(16) char dyn_smem[];  // NW == 1: P16_SMEM_BYTES
+    extern __shared__ __align__(16) char dyn_smem[];  // NW == 1: P16_SMEM_BYTES, else p16_mw_smem_bytes<NW>()
     if (threadIdx.x == 0) { ws_bind(sh.ws, ws_base + (long long)blockIdx.x * L.stride, L); sh.ring = dyn_smem; }
     for (;;) {
         if (threadIdx.x == 0) sh.blk = atomicAdd(O.counter, 1);
@@ -189,7 +189,7 @@ namespace {
 
 template <int NW>
 cudaError_t launch_nw(int n_ctas, cudaStream_t st, const DevParams &P, const DevBatch &B, const WsLayout &L, char *ws, const DevOut &O) {
-    poa_b200_block_kernel<NW><<<n_ctas, NW * 32, NW == 1 ? P16_SMEM_BYTES : 0, st>>>(P, B, L, ws, O);
+    poa_b200_block_kernel<NW><<<n_ctas, NW * 32, NW == 1 ? P16_SMEM_BYTES : p16_mw_smem_bytes<NW>(), st>>>(P, B, L, ws, O);
     return cudaGetLastError();
 }
 

@@ -50,18 +50,19 @@ static inline int poa_redux_max(int v) { return v; }
 static inline int poa_redux_min(int v) { return v; }
 static inline unsigned poa_ballot(int p) { return p ? 1u : 0u; }
 #else
-// 32 lock-step lanes emulated as fibers by the test harness (tests/emu/emu_simt.cpp): every collective is
-// an all-lanes exchange, so the warp-level logic (shuffle scans, reductions, lane-striped layouts) runs
-// on a machine without a GPU.  One warp per block only.
-namespace poa_emu { int lane(); void xchg(int v, int *all); }
+// Lock-step lanes emulated as fibers by the test harness (tests/emu/emu_poa.cpp): POA_EMU_NW warps of 32 lanes.
+// Every warp collective is an exchange among the 32 fibers of one warp, a block barrier a rendezvous of all of
+// them, so the warp- and block-level logic (shuffle scans, reductions, lane-striped layouts, cross-warp
+// exchanges through shared memory) runs on a machine without a GPU.
+namespace poa_emu { int lane(); void xchg(int v, int *all); void sync_all(); }
 static inline int poa_tid() { return poa_emu::lane(); }
-static inline void poa_sync_warp() { int a[POA_EMU_LANES]; poa_emu::xchg(0, a); }
-static inline void poa_sync_block() { poa_sync_warp(); }
-static inline int poa_shfl_up(int v, int d) { int a[POA_EMU_LANES]; poa_emu::xchg(v, a); int l = poa_emu::lane(); return l >= d ? a[l - d] : v; }
-static inline int poa_shfl(int v, int l) { int a[POA_EMU_LANES]; poa_emu::xchg(v, a); return a[l & (POA_EMU_LANES - 1)]; }
-static inline int poa_redux_max(int v) { int a[POA_EMU_LANES]; poa_emu::xchg(v, a); int m = a[0]; for (int i = 1; i < POA_EMU_LANES; ++i) m = a[i] > m ? a[i] : m; return m; }
-static inline int poa_redux_min(int v) { int a[POA_EMU_LANES]; poa_emu::xchg(v, a); int m = a[0]; for (int i = 1; i < POA_EMU_LANES; ++i) m = a[i] < m ? a[i] : m; return m; }
-static inline unsigned poa_ballot(int p) { int a[POA_EMU_LANES]; poa_emu::xchg(p ? 1 : 0, a); unsigned m = 0; for (int i = 0; i < POA_EMU_LANES; ++i) if (a[i]) m |= 1u << i; return m; }
+static inline void poa_sync_warp() { int a[32]; poa_emu::xchg(0, a); }
+static inline void poa_sync_block() { poa_emu::sync_all(); }
+static inline int poa_shfl_up(int v, int d) { int a[32]; poa_emu::xchg(v, a); int l = poa_emu::lane() & 31; return l >= d ? a[l - d] : v; }
+static inline int poa_shfl(int v, int l) { int a[32]; poa_emu::xchg(v, a); return a[l & 31]; }
+static inline int poa_redux_max(int v) { int a[32]; poa_emu::xchg(v, a); int m = a[0]; for (int i = 1; i < 32; ++i) m = a[i] > m ? a[i] : m; return m; }
+static inline int poa_redux_min(int v) { int a[32]; poa_emu::xchg(v, a); int m = a[0]; for (int i = 1; i < 32; ++i) m = a[i] < m ? a[i] : m; return m; }
+static inline unsigned poa_ballot(int p) { int a[32]; poa_emu::xchg(p ? 1 : 0, a); unsigned m = 0; for (int i = 0; i < 32; ++i) if (a[i]) m |= 1u << i; return m; }
 #endif
 static inline long long poa_clock() { return 0; }
 static inline unsigned long long poa_atomic_add(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
@@ -1353,14 +1354,15 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
             long long max_score = ms1 > ms2 ? ms1 : ms2;
             const bool bits16 = max_score <= (long long)INT16_MAX - P.min_mis - P.oe1 - P.oe2;
 #if POA_WARP == 32
-            const bool p16 = NW == 1 && bits16 && p16_eligible(P, qlen);
+            const bool p16 = bits16 && p16_eligible(P, qlen);
 #else
             const bool p16 = false;
 #endif
             if (p16) {
                 t_ph[PH_SPARE] += 1;  // alignments that took the packed 16-bit fill
 #if POA_WARP == 32
-                if (P.local) fill_p16<NW, true>(sh, P, q, qlen, L.slab_bytes); else fill_p16<NW, false>(sh, P, q, qlen, L.slab_bytes);
+                if (NW == 1) { if (P.local) fill_p16<NW, true>(sh, P, q, qlen, L.slab_bytes); else fill_p16<NW, false>(sh, P, q, qlen, L.slab_bytes); }
+                else { if (P.local) fill_p16_mw<NW, true>(sh, P, q, qlen, L.slab_bytes); else fill_p16_mw<NW, false>(sh, P, q, qlen, L.slab_bytes); }
 #endif
             } else if (P.gap_mode == 0) {
                 if (bits16) fill<NW, short, 0>(sh, P, q, qlen, L.slab_bytes / 16); else fill<NW, int, 0>(sh, P, q, qlen, L.slab_bytes / 32);

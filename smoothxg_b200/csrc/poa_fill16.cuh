@@ -556,4 +556,321 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
     sync_block<NW>();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Packed 16-bit fill for NW > 1 warps per POA block (small or deep batches: few blocks, long rows).
+// Same arithmetic and row layout as fill_p16(); the 256-column chunks of a row are dealt to the warps
+// (chunk c belongs to warp c % NW), NW chunks per round:
+//   phase A  each warp gathers its chunk's predecessors, runs the per-lane chains and the lane-half scan;
+//            lane 0 publishes the chunk's scan total (per gap piece) in shared memory        -- barrier --
+//   phase B  every warp replays the cheap scalar carry chain over the round's totals up to its own chunk,
+//            fixes up F, finishes H / E, stores.
+// A warp only ever reads ring slots it wrote itself (chunk ownership is by absolute chunk number); the one
+// cross-warp operand, the predecessor's last cell of the previous chunk, goes through a small shared array.
+// ------------------------------------------------------------------------------------------------
+constexpr int P16_MW_SMCH = 3;  // ring chunks per warp (rows up to 3 * NW chunks stay resident)
+template <int NW> constexpr int p16_mw_smem_bytes() { return NW * P16_MW_SMCH * 3 * P16_CPB + 2 * NW * 8 + NW * 16 + 2 * 64 * 4 + 64; }
+
+template <int NW, bool LOCAL>
+POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, long long slab_bytes) {
+    Ws &w = sh.ws;
+    const int tid = poa_tid(), lane = tid & 31, wid = tid >> 5;
+    const int n_node = sh.n_node;
+    const int rows = n_node - 1;
+    const int inf_min = inf_min_of<short>(P);
+    const int pn = P.pn16;
+    constexpr bool local = LOCAL;
+    const int wb = local ? -1 : P.wb;
+#ifdef POA_HOST_EMU
+    const int bw = wb < 0 ? qlen : wb + (int)(P.wf * qlen);
+#else
+    const int bw = wb < 0 ? qlen : wb + (int)__fmul_rn(P.wf, (float)qlen);
+#endif
+    const int e1 = P.e1, e2 = P.e2, oe1 = P.oe1, oe2 = P.oe2;
+    char *const slab = w.slab, *const qp = w.qp;
+    const int4 *const rowinfo = w.rowinfo;
+    int4 *const rowmeta = w.rowmeta;
+    const int *const pool_row = w.pool_row, *const rr = w.rr, *const fp = w.tmp0;
+    int *const mplr = w.mplr, *const mprr = w.mprr;
+    const uint8_t *const rbase = w.rbase;
+#ifndef POA_HOST_EMU
+    __builtin_assume(__isGlobal(slab)); __builtin_assume(__isGlobal(qp)); __builtin_assume(__isGlobal(rowinfo));
+    __builtin_assume(__isGlobal(rowmeta)); __builtin_assume(__isGlobal(pool_row)); __builtin_assume(__isGlobal(rr));
+    __builtin_assume(__isGlobal(mplr)); __builtin_assume(__isGlobal(mprr)); __builtin_assume(__isGlobal(rbase));
+    __builtin_assume(__isGlobal(q)); __builtin_assume(__isGlobal(fp));
+#endif
+    const long long slab_units = slab_bytes / P16_CPB;
+    long long used = 0, inband = 0, edge_rows = 0;
+    const int emax = imax(e1, e2);
+    const int negl = -32768 + 8 * emax + 8;
+    const unsigned INFP = p_pack(inf_min, inf_min), NEGLP = p_pack(negl, negl), ZERO = 0u;
+    const unsigned NOE1 = p_pack(-oe1, -oe1), NOE2 = p_pack(-oe2, -oe2), NE1 = p_pack(-e1, -e1), NE2 = p_pack(-e2, -e2);
+    const unsigned NE1_2 = p_add(NE1, NE1), NE1_3 = p_add(NE1_2, NE1), NE2_2 = p_add(NE2, NE2), NE2_3 = p_add(NE2_2, NE2);
+    const unsigned OFF1 = p_pack(e1 * 4 * (lane + 1), e1 * 4 * (lane + 33)), NOFF1 = p_pack(-e1 * 4 * lane, -e1 * 4 * (lane + 32));
+    const unsigned OFF2 = p_pack(e2 * 4 * (lane + 1), e2 * 4 * (lane + 33)), NOFF2 = p_pack(-e2 * 4 * lane, -e2 * 4 * (lane + 32));
+    const int f0_1 = imax(inf_min - oe1, inf_min - e1), f0_2 = imax(inf_min - oe2, inf_min - e2);
+    // shared memory: per-warp rings, round totals (two parities), per-warp row maxima, last H cell per chunk (two row parities)
+    const ring_ptr_t ring = ring_base(sh.ring + wid * (P16_MW_SMCH * 3 * P16_CPB), lane);
+    int *const xch = reinterpret_cast<int *>(sh.ring + NW * P16_MW_SMCH * 3 * P16_CPB);  // [2][NW][2]
+    int *const rowx = xch + 2 * NW * 2;                                                   // [NW][4]
+    int *const lastH = rowx + NW * 4;                                                     // [2][64]
+
+    const int nchq = (qlen >> 8) + 1;
+    for (int bc = wid; bc < 5 * nchq; bc += NW) {  // query profile, chunked layout
+        const int b = bc / nchq, c = bc % nchq;
+        unsigned v[4];
+        for (int r = 0; r < 4; ++r) {
+            const int jl = c * P16_CW + lane * 4 + r, jh = jl + 128;
+            const int sl = (jl == 0 || jl > qlen) ? 0 : P.mat[b * 5 + q[jl - 1]];
+            const int s2 = jh > qlen ? 0 : P.mat[b * 5 + q[jh - 1]];
+            v[r] = p_pack(sl, s2);
+        }
+        p16_st(qp + (size_t)(unsigned)bc * P16_CPB + lane * 16, v[0], v[1], v[2], v[3]);
+    }
+    {   // row 0
+        int end0;
+        if (wb >= 0) {
+            if (tid == 0) {
+                mplr[0] = 0; mprr[0] = 0;
+                const int4 ri = rowinfo[0];
+                for (int k = 0; k < ri.w; ++k) { int o = pool_row[ri.z + k]; mplr[o] = 1; mprr[o] = 1; }
+            }
+            end0 = imin(qlen, imax(0, rr[0]) + bw);
+        } else end0 = qlen;
+        const int nch = (end0 >> 8) + 1;
+        if (5LL * nch > slab_units) { if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+        if (tid == 0) rowmeta[0] = poa_make_int4(0, 0, end0, 0);
+        for (int c = wid; c < nch; c += NW) {
+            unsigned v[5][4];
+            for (int r = 0; r < 4; ++r) {
+                int x[2][5];
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int j = c * P16_CW + hf * 128 + lane * 4 + r;
+                    int *y = x[hf];
+                    if (j > end0) { y[0] = y[1] = y[2] = y[3] = y[4] = inf_min; }
+                    else if (local) { y[0] = y[1] = y[2] = y[3] = y[4] = 0; }
+                    else if (j == 0) { y[0] = 0; y[1] = -oe1; y[2] = -oe2; y[3] = y[4] = inf_min; }
+                    else { y[3] = -P.o1 - e1 * j; y[4] = -P.o2 - e2 * j; y[0] = imax((int)(short)y[3], (int)(short)y[4]); y[1] = y[2] = inf_min; }
+                }
+                for (int p = 0; p < 5; ++p) v[p][r] = p_pack(x[0][p], x[1][p]);
+            }
+            for (int p = 0; p < 5; ++p)
+                p16_st(slab + ((long long)p * nch + c) * P16_CPB + lane * 16, v[p][0], v[p][1], v[p][2], v[p][3]);
+        }
+        used = 5LL * nch;
+        inband += end0 + 1;
+        sync_block<NW>();
+    }
+    int best_score = inf_min, best_i = 0, best_j = 0;
+    const int pshift = 31 - p_clz((unsigned)pn);
+    char *const slab_lane = slab + lane * 16;
+    const bool track = local || wb >= 0;
+    int4 prev_meta = rowmeta[0];
+    int prev_left = 0, prev_right = 0;
+    bool prev_res = false;
+
+    for (int i = 1; i < rows; ++i) {
+        const int4 ri = rowinfo[i];
+        const int rb = rbase[i], p0 = fp[i];
+        const int4 pm0 = p0 == i - 1 ? prev_meta : rowmeta[p0];
+        int pk1 = -1;
+        int4 pm1 = pm0;
+        if (ri.y > 1) { pk1 = pool_row[ri.x + 1]; pm1 = rowmeta[pk1]; }
+        int beg, end;
+        if (wb < 0) { beg = 0; end = qlen; }
+        else {
+            const int r = rr[i];
+            int ml = p16_ldcg(&mplr[i]), mr = p16_ldcg(&mprr[i]);
+            int min_pre_beg = pm0.y;
+            bool from_prev = p0 == i - 1;
+            if (ri.y > 1) { from_prev |= pk1 == i - 1; min_pre_beg = imin(min_pre_beg, pm1.y); }
+            for (int k = 2; k < ri.y; ++k) {
+                const int pk = pool_row[ri.x + k];
+                from_prev |= pk == i - 1;
+                min_pre_beg = imin(min_pre_beg, rowmeta[pk].y);
+            }
+            if (from_prev) { ml = imin(ml, prev_left + 1); mr = imax(mr, prev_right + 1); }
+            beg = imax(0, imin(ml, r) - bw);
+            end = imin(qlen, imax(mr, r) + bw);
+            if ((beg >> pshift) < (min_pre_beg >> pshift)) beg = min_pre_beg;
+        }
+        if (end < beg) end = beg;
+        const int cb = beg >> 8, ce = end >> 8, nch = ce - cb + 1;
+        if (used + 5LL * nch > slab_units) { if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+        const unsigned roff = (unsigned)used;
+        used += 5LL * nch;
+        inband += end - beg + 1;
+        edge_rows += (long long)ri.y * (end - beg + 1);
+        int cf1 = f0_1 + e1 * (beg - cb * P16_CW), cf2 = f0_2 + e2 * (beg - cb * P16_CW);  // F entering column cb*256
+        int rmx = INT_MIN, fc = cb, lc = cb;  // this warp's chunks only
+        const char *qrow = qp + (size_t)(unsigned)(rb * nchq) * P16_CPB + lane * 16;
+        const size_t pstride = (size_t)(unsigned)nch * P16_CPB;
+        const bool cur_res = nch <= P16_MW_SMCH * NW;
+        int par = 0;
+
+#pragma unroll 1
+        for (int cbase = cb; cbase <= ce; cbase += NW) {
+            const int c = cbase + ((wid - (cbase % NW) + NW) % NW);  // the chunk of this round with c % NW == wid
+            const bool act = c <= ce;
+            const int c0 = c * P16_CW;
+            const unsigned cslot = (unsigned)((c / NW) % P16_MW_SMCH) * (3 * P16_CPB);
+            unsigned H0 = INFP, H1 = INFP, H2 = INFP, H3 = INFP, A0 = INFP, A1 = INFP, A2 = INFP, A3 = INFP, B0 = INFP, B1 = INFP, B2 = INFP, B3 = INFP;
+            unsigned l1 = 0, l2 = 0, l3 = 0, k1 = 0, k2 = 0, k3 = 0, x1 = 0, x2 = 0, t1 = NEGLP, t2 = NEGLP, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+            bool bnd = false;
+            if (act) {
+                unsigned M0 = INFP, M1 = INFP, M2 = INFP, M3 = INFP;
+#pragma unroll 1
+                for (int k = 0; k < ri.y; ++k) {  // predecessors in in_id order (abpoa_align_simd.c:966-1029)
+                    int pk = p0;
+                    int4 pm = pm0;
+                    if (k == 1) { pk = pk1; pm = pm1; } else if (k > 1) { pk = pool_row[ri.x + k]; pm = rowmeta[pk]; }
+                    const int pcb = pm.y >> 8, pce = pm.z >> 8;
+                    if (c < pcb || c > pce + 1) continue;
+                    const unsigned pn_ = (unsigned)(pce - pcb + 1), idx = (unsigned)pm.x + (unsigned)(c - pcb);
+                    const bool in_ring = prev_res && pk == i - 1;
+                    int prevlast = inf_min;  // H_p[c0 - 1]
+                    if (c > pcb) prevlast = in_ring ? lastH[((i - 1) & 1) * 64 + ((c - 1) & 63)] : (int)*reinterpret_cast<const short *>(slab + (size_t)idx * P16_CPB - 2);
+                    if (c <= pce) {
+                        uint4 h, a, b;
+                        if (in_ring) { h = ring_ld(ring, cslot); a = ring_ld(ring, cslot + P16_CPB); b = ring_ld(ring, cslot + 2 * P16_CPB); }
+                        else {
+                            h = p16_ld(slab_lane + (size_t)idx * P16_CPB);
+                            a = p16_ld(slab_lane + (size_t)(idx + pn_) * P16_CPB);
+                            b = p16_ld(slab_lane + (size_t)(idx + 2 * pn_) * P16_CPB);
+                        }
+                        const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
+                        const unsigned s0 = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot;
+                        M0 = p_max(M0, s0); M1 = p_max(M1, h.x); M2 = p_max(M2, h.y); M3 = p_max(M3, h.z);
+                        A0 = p_max(A0, a.x); A1 = p_max(A1, a.y); A2 = p_max(A2, a.z); A3 = p_max(A3, a.w);
+                        B0 = p_max(B0, b.x); B1 = p_max(B1, b.y); B2 = p_max(B2, b.z); B3 = p_max(B3, b.w);
+                    } else if (lane == 0) {
+                        M0 = p_max(M0, p_pack(prevlast, inf_min));
+                    }
+                }
+                if (local && c == 0 && lane == 0) M0 = p_max(M0, p_pack(0, inf_min));
+                const uint4 qv = p16_ld(qrow + (size_t)(unsigned)c * P16_CPB);
+                H0 = p_max3(p_add(M0, qv.x), A0, B0); H1 = p_max3(p_add(M1, qv.y), A1, B1);
+                H2 = p_max3(p_add(M2, qv.z), A2, B2); H3 = p_max3(p_add(M3, qv.w), A3, B3);
+                bnd = (c == cb && beg > c0) || (c == ce && end < c0 + P16_CW - 1);
+                if (bnd) {
+                    const int brel = imax(beg - c0, 0), erel = imin(end - c0, P16_CW - 1);
+                    const unsigned da = p_pack(lane * 4 - brel, 128 + lane * 4 - brel), db = p_pack(erel - lane * 4, erel - 128 - lane * 4);
+                    m0 = p_signmask(p_min(da, db));
+                    m1 = p_signmask(p_min(p_add(da, 0x00010001u), p_add(db, 0xffffffffu)));
+                    m2 = p_signmask(p_min(p_add(da, 0x00020002u), p_add(db, 0xfffefffeu)));
+                    m3 = p_signmask(p_min(p_add(da, 0x00030003u), p_add(db, 0xfffdfffdu)));
+                    H0 = (H0 & ~m0) | (INFP & m0); H1 = (H1 & ~m1) | (INFP & m1);
+                    H2 = (H2 & ~m2) | (INFP & m2); H3 = (H3 & ~m3) | (INFP & m3);
+                }
+                l1 = p_add(H0, NOE1); l2 = p_addmax(l1, NE1, p_add(H1, NOE1)); l3 = p_addmax(l2, NE1, p_add(H2, NOE1));
+                const unsigned lout = p_addmax(l3, NE1, p_add(H3, NOE1));
+                k1 = p_add(H0, NOE2); k2 = p_addmax(k1, NE2, p_add(H1, NOE2)); k3 = p_addmax(k2, NE2, p_add(H2, NOE2));
+                const unsigned kout = p_addmax(k3, NE2, p_add(H3, NOE2));
+                unsigned g1 = p_add(lout, OFF1), g2 = p_add(kout, OFF2);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned u1 = (unsigned)poa_shfl_up((int)g1, d), u2 = (unsigned)poa_shfl_up((int)g2, d);
+                    g1 = p_max(g1, u1); g2 = p_max(g2, u2);
+                }
+                x1 = (unsigned)poa_shfl_up((int)g1, 1); x2 = (unsigned)poa_shfl_up((int)g2, 1);
+                t1 = (unsigned)poa_shfl((int)g1, 31); t2 = (unsigned)poa_shfl((int)g2, 31);
+                if (lane == 0) { x1 = NEGLP; x2 = NEGLP; }
+                x1 = p_max(x1, p_lolo(NEGLP, t1)); x2 = p_max(x2, p_lolo(NEGLP, t2));
+            }
+            if (lane == 0) {
+                int *slot = xch + (par * NW + (c - cbase)) * 2;
+                slot[0] = imax(p_lo(t1), p_hi(t1)); slot[1] = imax(p_lo(t2), p_hi(t2));
+            }
+            sync_block<NW>();
+            // carry chain over the round's chunks: F entering each chunk's first column (scalar, F domain)
+            int mine1 = cf1, mine2 = cf2;
+            for (int k = 0; k < NW && cbase + k <= ce; ++k) {
+                if (cbase + k == c) { mine1 = cf1; mine2 = cf2; }
+                const int *slot = xch + (par * NW + k) * 2;
+                cf1 = imax(slot[0], cf1) - e1 * P16_CW; cf2 = imax(slot[1], cf2) - e2 * P16_CW;
+            }
+            par ^= 1;
+            if (act) {
+                x1 = p_max(x1, p_pack(mine1, mine1)); x2 = p_max(x2, p_pack(mine2, mine2));
+                const unsigned fin1 = p_add(x1, NOFF1), fin2 = p_add(x2, NOFF2);
+                const unsigned F10 = fin1, F11 = p_addmax(fin1, NE1, l1), F12 = p_addmax(fin1, NE1_2, l2), F13 = p_addmax(fin1, NE1_3, l3);
+                const unsigned F20 = fin2, F21 = p_addmax(fin2, NE2, k1), F22 = p_addmax(fin2, NE2_2, k2), F23 = p_addmax(fin2, NE2_3, k3);
+                H0 = p_max3(H0, F10, F20); H1 = p_max3(H1, F11, F21); H2 = p_max3(H2, F12, F22); H3 = p_max3(H3, F13, F23);
+                if (local) { H0 = p_max(H0, ZERO); H1 = p_max(H1, ZERO); H2 = p_max(H2, ZERO); H3 = p_max(H3, ZERO); }
+                A0 = p_addmax(A0, NE1, p_add(H0, NOE1)); A1 = p_addmax(A1, NE1, p_add(H1, NOE1));
+                A2 = p_addmax(A2, NE1, p_add(H2, NOE1)); A3 = p_addmax(A3, NE1, p_add(H3, NOE1));
+                B0 = p_addmax(B0, NE2, p_add(H0, NOE2)); B1 = p_addmax(B1, NE2, p_add(H1, NOE2));
+                B2 = p_addmax(B2, NE2, p_add(H2, NOE2)); B3 = p_addmax(B3, NE2, p_add(H3, NOE2));
+                if (local) {
+                    A0 = p_max(A0, ZERO); A1 = p_max(A1, ZERO); A2 = p_max(A2, ZERO); A3 = p_max(A3, ZERO);
+                    B0 = p_max(B0, ZERO); B1 = p_max(B1, ZERO); B2 = p_max(B2, ZERO); B3 = p_max(B3, ZERO);
+                }
+                if (bnd) {
+                    H0 = (H0 & ~m0) | (INFP & m0); H1 = (H1 & ~m1) | (INFP & m1); H2 = (H2 & ~m2) | (INFP & m2); H3 = (H3 & ~m3) | (INFP & m3);
+                    A0 = (A0 & ~m0) | (INFP & m0); A1 = (A1 & ~m1) | (INFP & m1); A2 = (A2 & ~m2) | (INFP & m2); A3 = (A3 & ~m3) | (INFP & m3);
+                    B0 = (B0 & ~m0) | (INFP & m0); B1 = (B1 & ~m1) | (INFP & m1); B2 = (B2 & ~m2) | (INFP & m2); B3 = (B3 & ~m3) | (INFP & m3);
+                }
+                char *dst = slab_lane + (size_t)(roff + (unsigned)(c - cb)) * P16_CPB;
+                p16_st(dst, H0, H1, H2, H3); p16_st(dst + pstride, A0, A1, A2, A3); p16_st(dst + 2 * pstride, B0, B1, B2, B3);
+                p16_st(dst + 3 * pstride, F10, F11, F12, F13); p16_st(dst + 4 * pstride, F20, F21, F22, F23);
+                if (cur_res) {
+                    ring_st(ring, cslot, H0, H1, H2, H3); ring_st(ring, cslot + P16_CPB, A0, A1, A2, A3); ring_st(ring, cslot + 2 * P16_CPB, B0, B1, B2, B3);
+                    if (lane == 31) lastH[(i & 1) * 64 + (c & 63)] = p_hi(H3);
+                }
+                if (track) {
+                    const unsigned cm = p_max(p_max3(H0, H1, H2), H3);
+                    const int cmx = poa_redux_max(imax(p_lo(cm), p_hi(cm)));
+                    if (cmx > rmx) { rmx = cmx; fc = c; }
+                    if (cmx >= rmx) lc = c;
+                }
+            }
+        }
+        prev_meta = poa_make_int4((int)roff, beg, end, 0);
+        prev_res = cur_res && nch <= 64;
+        if (tid == 0) rowmeta[i] = prev_meta;
+        if (track) {
+            if (lane == 0) { rowx[wid * 4] = rmx; rowx[wid * 4 + 1] = fc; rowx[wid * 4 + 2] = lc; }
+            sync_block<NW>();  // also: every warp's plane stores of this row are visible below
+            int gmx = INT_MIN, gfc = INT_MAX, glc = -1;
+            for (int k = 0; k < NW; ++k) gmx = imax(gmx, rowx[k * 4]);
+            for (int k = 0; k < NW; ++k) if (rowx[k * 4] == gmx) { gfc = imin(gfc, rowx[k * 4 + 1]); glc = imax(glc, rowx[k * 4 + 2]); }
+            const unsigned pat = p_pack(gmx, gmx);
+            const uint4 fh = p16_ld(slab_lane + (size_t)(roff + (unsigned)(gfc - cb)) * P16_CPB);
+            const uint4 lh = p16_ld(slab_lane + (size_t)(roff + (unsigned)(glc - cb)) * P16_CPB);
+            const unsigned fz = p_minu(fh.x ^ pat, 0x00010001u) | (p_minu(fh.y ^ pat, 0x00010001u) << 1)
+                              | (p_minu(fh.z ^ pat, 0x00010001u) << 2) | (p_minu(fh.w ^ pat, 0x00010001u) << 3);
+            const unsigned lz = p_minu(lh.x ^ pat, 0x00010001u) | (p_minu(lh.y ^ pat, 0x00010001u) << 1)
+                              | (p_minu(lh.z ^ pat, 0x00010001u) << 2) | (p_minu(lh.w ^ pat, 0x00010001u) << 3);
+            const unsigned fm = (~fz & 0xfu) | ((~fz >> 12) & 0xf0u), lm = (~lz & 0xfu) | ((~lz >> 12) & 0xf0u);
+            int first = INT_MAX, last = -1;
+            if (fm) { const int b = p_ctz(fm); first = gfc * P16_CW + lane * 4 + b + (b >= 4 ? 124 : 0); }
+            if (lm) { const int b = 31 - p_clz(lm); last = glc * P16_CW + lane * 4 + b + (b >= 4 ? 124 : 0); }
+            const int left = poa_redux_min(first), right = poa_redux_max(last);
+            prev_left = left; prev_right = right;
+            if (local && gmx > best_score) { best_score = gmx; best_i = i; best_j = left; }
+            if (wb >= 0 && wid == 0) {
+                for (int k = lane; k < ri.w; k += POA_WARP) {
+                    const int o = pool_row[ri.z + k];
+                    poa_red_max(&mprr[o], right + 1); poa_red_min(&mplr[o], left + 1);
+                }
+            }
+        }
+        sync_block<NW>();
+    }
+    if (tid == 0) {  // global best (abpoa_align_simd.c:1092-1105)
+        if (!local) {
+            const int4 ri = rowinfo[rows];
+            for (int k = 0; k < ri.y; ++k) {
+                const int pi = pool_row[ri.x + k];
+                const int4 pm = rowmeta[pi];
+                const int e = qlen > pm.z ? pm.z : qlen;
+                const int sc = *cell_ptr16(w, pm, 0, e);
+                if (sc > best_score) { best_score = sc; best_i = pi; best_j = e; }
+            }
+        }
+        sh.best_score = best_score; sh.best_i = best_i; sh.best_j = best_j;
+        sh.inband += inband; sh.edge_rows += edge_rows;
+    }
+    sync_block<NW>();
+}
+
 #endif  // POA_WARP == 32

@@ -22,46 +22,55 @@ int set_err(int code, const std::string &msg) { fprintf(stderr, "[emu] %s\n", ms
 using namespace poa;
 
 #if POA_EMU_LANES > 1
-// ---- 32 lock-step lanes as fibers: a collective publishes the lane's value and yields until all lanes arrived.
+// ---- POA_EMU_NW warps of 32 lock-step lanes as fibers: a warp collective publishes the lane's value and yields
+// until the other 31 lanes of its warp arrived; a block barrier waits for every fiber.
+#ifndef POA_EMU_NW
+#define POA_EMU_NW 1
+#endif
 #include <ucontext.h>
 #include <functional>
 namespace poa_emu {
-static const int NL = POA_EMU_LANES;
+static const int NL = 32 * POA_EMU_NW;
 static ucontext_t g_main, g_ctx[NL];
 static int g_cur = 0, g_done[NL];
-static long long g_gen[NL], g_arrivals = 0;
-static int g_buf[2][NL];
+static long long g_gen[NL], g_arrivals[POA_EMU_NW], g_bgen[NL], g_barrivals = 0, g_progress = 0;
+static int g_buf[POA_EMU_NW][2][32];
 static std::function<void()> g_body;
 int lane() { return g_cur; }
 static void yield_to_main() { swapcontext(&g_ctx[g_cur], &g_main); }
 void xchg(int v, int *all) {
-    const int me = g_cur;
+    const int me = g_cur, w = me >> 5, l = me & 31;
     const long long gen = g_gen[me]++;
-    g_buf[gen & 1][me] = v;
-    ++g_arrivals;
-    while (g_arrivals < (long long)NL * (gen + 1)) yield_to_main();
-    for (int i = 0; i < NL; ++i) all[i] = g_buf[gen & 1][i];
+    g_buf[w][gen & 1][l] = v;
+    ++g_arrivals[w]; ++g_progress;
+    while (g_arrivals[w] < 32LL * (gen + 1)) yield_to_main();
+    for (int i = 0; i < 32; ++i) all[i] = g_buf[w][gen & 1][i];
 }
-static void trampoline() { g_body(); g_done[g_cur] = 1; yield_to_main(); }
+void sync_all() {
+    const int me = g_cur;
+    const long long gen = g_bgen[me]++;
+    ++g_barrivals; ++g_progress;
+    while (g_barrivals < (long long)NL * (gen + 1)) yield_to_main();
+}
+static void trampoline() { g_body(); g_done[g_cur] = 1; ++g_progress; yield_to_main(); }
 static void run_warp(std::function<void()> body) {
     static std::vector<char> stacks;
     const size_t SS = 1 << 20;
     stacks.assign(SS * NL, 0);
-    g_body = body; g_arrivals = 0;
+    g_body = body; g_barrivals = 0; g_progress = 0;
+    for (int w = 0; w < POA_EMU_NW; ++w) g_arrivals[w] = 0;
     for (int i = 0; i < NL; ++i) {
-        g_done[i] = 0; g_gen[i] = 0;
+        g_done[i] = 0; g_gen[i] = 0; g_bgen[i] = 0;
         getcontext(&g_ctx[i]);
         g_ctx[i].uc_stack.ss_sp = stacks.data() + SS * i; g_ctx[i].uc_stack.ss_size = SS; g_ctx[i].uc_link = &g_main;
         makecontext(&g_ctx[i], trampoline, 0);
     }
     for (;;) {
         int alive = 0;
-        long long before = g_arrivals;
-        int finished_before = 0; for (int i = 0; i < NL; ++i) finished_before += g_done[i];
+        const long long before = g_progress;
         for (int i = 0; i < NL; ++i) if (!g_done[i]) { ++alive; g_cur = i; swapcontext(&g_main, &g_ctx[i]); }
         if (!alive) break;
-        int finished_after = 0; for (int i = 0; i < NL; ++i) finished_after += g_done[i];
-        if (g_arrivals == before && finished_after == finished_before) { fprintf(stderr, "[emu] divergent collective: lanes deadlocked\n"); abort(); }
+        if (g_progress == before) { fprintf(stderr, "[emu] divergent collective: lanes deadlocked\n"); abort(); }
     }
 }
 }  // namespace poa_emu
@@ -117,11 +126,11 @@ extern "C" int32_t *emu_poa_block(const pd_params_t *pp, int n_seq, const int32_
     Shared sh; memset(&sh, 0, sizeof(sh));
     ws_bind(sh.ws, wsp, L);
 #if POA_EMU_LANES == 32
-    std::vector<char> ring((size_t)P16_SMEM_BYTES + 16);
+    std::vector<char> ring((size_t)std::max<int>(P16_SMEM_BYTES, p16_mw_smem_bytes<8>()) + 16);
     sh.ring = ring.data();
 #endif
 #if POA_EMU_LANES > 1
-    poa_emu::run_warp([&]() { poa_block<1>(sh, dp, B, L, O, 0); });
+    poa_emu::run_warp([&]() { poa_block<POA_EMU_NW>(sh, dp, B, L, O, 0); });
 #else
     poa_block<1>(sh, dp, B, L, O, 0);
 #endif

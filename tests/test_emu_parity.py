@@ -54,6 +54,34 @@ def emu32():
     return _Checker(C.CDLL(OUT32), "emu_poa_block", "emu_free")
 
 
+OUT32X4 = os.path.join(HERE, "emu", "_build", "libpoa_emu32x4.so")
+FAST32X4 = {"abpoa_seq_fa_global", "abpoa_seq_fa_local", "abpoa_example_c", "edge_shapes", "edge_shapes_local", "syn_presets", "affine_seq_fa"}
+
+
+@pytest.fixture(scope="module")
+def emu32x4():
+    """Four warps of 32 emulated lanes per POA block (-DPOA_EMU_NW=4): the multi-warp packed fill (chunks dealt to
+    warps, carry chain through shared memory) and the generic multi-warp fill, cross-warp barriers included."""
+    os.makedirs(os.path.dirname(OUT32X4), exist_ok=True)
+    csrc = os.path.join(HERE, "..", "smoothxg_b200", "csrc")
+    deps = [SRC] + [os.path.join(csrc, f) for f in ("poa_core.cuh", "poa_fill16.cuh", "poa_host.hpp")]
+    if not os.path.exists(OUT32X4) or any(os.path.getmtime(d) > os.path.getmtime(OUT32X4) for d in deps):
+        subprocess.check_call(["/usr/bin/g++", "-O1", "-fPIC", "-shared", "-std=c++17", "-DPOA_EMU_LANES=32", "-DPOA_EMU_NW=4",
+                               "-I/usr/local/cuda/include", "-o", OUT32X4, SRC])
+    return _Checker(C.CDLL(OUT32X4), "emu_poa_block", "emu_free")
+
+
+@pytest.mark.parametrize("name,batch,p,dumps", CASES, ids=[c[0] for c in CASES])
+def test_emulated_multi_warp_logic_matches_golden(emu32x4, name, batch, p, dumps):
+    if name not in FAST32X4 and not os.environ.get("POA_EMU32_ALL"):
+        pytest.skip("slow under the fiber emulation; set POA_EMU32_ALL=1")
+    for b in range(batch.n_blocks):
+        got = emu32x4.poa_block(pd_params(p), *batch.block(b))
+        assert got is not None
+        assert np.array_equal(got.compare_part(), dumps[b].compare_part()), f"{name} block {b}"
+        assert got.edge_rows == dumps[b].edge_rows
+
+
 @pytest.mark.parametrize("name,batch,p,dumps", CASES, ids=[c[0] for c in CASES])
 def test_emulated_warp_logic_matches_golden(emu32, name, batch, p, dumps):
     if name not in FAST32 and not os.environ.get("POA_EMU32_ALL"):
