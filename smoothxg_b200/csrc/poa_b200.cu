@@ -31,7 +31,8 @@ template <int NW>
 __global__ void __launch_bounds__(NW * 32, POA_MIN_BLOCKS / NW) poa_b200_block_kernel(DevParams P, DevBatch B, WsLayout L, char *ws_base, DevOut O) {
     __shared__ Shared sh;
     extern __shared__ __align__(16) char dyn_smem[];  // NW == 1: P16_SMEM_BYTES, else p16_mw_smem_bytes<NW>()
-    if (threadIdx.x == 0) { ws_bind(sh.ws, ws_base + (long long)blockIdx.x * L.stride, L); sh.ring = dyn_smem; }
+    constexpr int dyn_bytes = NW == 1 ? P16_SMEM_BYTES : p16_mw_smem<NW>::bytes;
+    if (threadIdx.x == 0) { ws_bind(sh.ws, ws_base + (long long)blockIdx.x * L.stride, L); sh.ring = dyn_smem; sh.ring_bytes = dyn_bytes; }
     for (;;) {
         if (threadIdx.x == 0) sh.blk = atomicAdd(O.counter, 1);
         __syncthreads();

@@ -184,6 +184,7 @@ struct Shared {
     int red_x[2][3][MAX_WARPS];
     int bcast[4];
     char *ring;  // previous-row cache of the packed 16-bit fill (dynamic shared memory, poa_fill16.cuh)
+    int ring_bytes;
 };
 
 #ifdef POA_HOST_EMU
@@ -420,7 +421,11 @@ POA_DN void toposort_incr(Shared &sh, int banded, int n_old) {
     }
     sync_block<NW>();
     if (banded) {
-        int *d0 = w.tmp0, *d1 = w.tmp1, *t0 = w.tmp2, *t1 = w.tmp3;
+        // remain[v] = remain[heaviest out-neighbour] + 1, remain[sink] = -1 (abpoa_graph.c:263-283).  Targets first, by
+        // all threads; then warp 0 sweeps the order from the sink down, one warp-wide group of positions at a time:
+        // links inside a group are resolved by pointer jumping over shuffles, links to earlier groups read the
+        // finished values, kept by position in shared memory while the graph fits (the fill's ring is idle here).
+        int *tgt = w.tmp0;
         for (int v0 = tid; v0 < n; v0 += 4 * NT) {
             int oo[4];
 #pragma unroll
@@ -428,31 +433,38 @@ POA_DN void toposort_incr(Shared &sh, int banded, int n_old) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) if (oo[u] >= 0) oo[u] = w.pool_id[oo[u]];  // heaviest out-edge: first after the weight sort
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int v = v0 + u * NT;
-                if (v < n) { d0[v] = oo[u] >= 0 ? 1 : 0; t0[v] = oo[u] >= 0 ? oo[u] : SINK_ID; }
-            }
+            for (int u = 0; u < 4; ++u) { const int v = v0 + u * NT; if (v < n) tgt[v] = oo[u]; }
         }
         sync_block<NW>();
-        for (;;) {
-            int busy = 0;
-            for (int v0 = tid; v0 < n; v0 += 4 * NT) {
-                int t[4], dd[4], tt[4], dt[4];
+        if (tid < POA_WARP) {
+            const int lane = tid;
+            int *rem = (sh.ring != nullptr && (long long)n * 4 <= sh.ring_bytes) ? (int *)sh.ring : w.tmp1;
+            for (int hi = n - 1; hi >= 0; hi -= 4 * POA_WARP) {
+                int vv[4], ti[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int v = v0 + u * NT; t[u] = v < n ? t0[v] : SINK_ID; dd[u] = v < n ? d0[v] : 0; }
+                for (int u = 0; u < 4; ++u) { const int x = hi - u * POA_WARP - lane; vv[u] = x >= 0 ? w.idx2id[x] : -1; }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { tt[u] = t0[t[u]]; dt[u] = d0[t[u]]; }
+                for (int u = 0; u < 4; ++u) ti[u] = vv[u] >= 0 ? tgt[vv[u]] : -1;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ti[u] = ti[u] >= 0 ? w.id2idx[ti[u]] : -1;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int v = v0 + u * NT;
-                    if (v < n) { d1[v] = dd[u] + dt[u]; t1[v] = tt[u]; busy |= tt[u] != SINK_ID; }
+                    const int top = hi - u * POA_WARP, x = top - lane;
+                    if (top < 0) break;
+                    int acc, ptr = -1;
+                    if (ti[u] < 0) acc = -1;                                   // the sink (or a lane past the source end)
+                    else if (ti[u] <= top) { acc = 1; ptr = top - ti[u]; }     // inside this group: a lower lane
+                    else acc = rem[ti[u]] + 1;
+                    for (int r = 1; r < POA_WARP; r <<= 1) {
+                        const int src = ptr >= 0 ? ptr : lane;
+                        const int a = poa_shfl(acc, src), pp = poa_shfl(ptr, src);
+                        if (ptr >= 0) { acc += a; ptr = pp; }
+                    }
+                    if (x >= 0) { rem[x] = acc; w.remain[vv[u]] = acc; }
+                    poa_sync_warp();
                 }
             }
-            int *x = d0; d0 = d1; d1 = x; x = t0; t0 = t1; t1 = x;
-            sync_block<NW>();
-            if (!block_any<NW>(sh, busy)) break;
         }
-        for (int v = tid; v < n; v += NT) w.remain[v] = d0[v] - 1;  // remain[sink] = -1 (abpoa_graph.c:281)
     }
     sync_block<NW>();
 }
@@ -1001,8 +1013,9 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
     poa_sync_warp();
     int n = sh.n_cigar;
     poa_sync_warp();  // every lane has read it before lane 0 may write it again below
+    bool skip_fast = false;
     while (i > 0 && j > 0) {
-        if (POA_WARP > 1 && cur_op == OP_ALL) {
+        if (POA_WARP > 1 && cur_op == OP_ALL && !skip_fast) {
             // rows of the run: chase the first-predecessor table (all lanes walk the same chain; 32 dependent but
             // cached loads -- rows of a bubble-rich graph are not consecutive, so the chain cannot be guessed)
             int ia = 0, ib = 0, r = i;
@@ -1028,6 +1041,7 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
                 n += nok;
                 const int ni = poa_shfl(ib, nok - 1);  // first predecessor of the last committed row
                 i = ni; j -= nok; id = w.idx2id[i]; cur_op = OP_ALL;
+                skip_fast = nok < POA_WARP;  // the run ended on a cell that is not a first-predecessor match: the next attempt would commit nothing
                 continue;
             }
         }
@@ -1044,6 +1058,7 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
         if (rc == 2) return;
         if (rc == 1) break;
         id = w.idx2id[i];
+        skip_fast = false;
     }
     if (lane == 0) {
         sh.n_cigar = n;

@@ -568,7 +568,8 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
 // cross-warp operand, the predecessor's last cell of the previous chunk, goes through a small shared array.
 // ------------------------------------------------------------------------------------------------
 constexpr int P16_MW_SMCH = 3;  // ring chunks per warp (rows up to 3 * NW chunks stay resident)
-template <int NW> constexpr int p16_mw_smem_bytes() { return NW * P16_MW_SMCH * 3 * P16_CPB + 2 * NW * 8 + NW * 16 + 2 * 64 * 4 + 64; }
+template <int NW> struct p16_mw_smem { static constexpr int bytes = NW * P16_MW_SMCH * 3 * P16_CPB + 2 * NW * 8 + NW * 16 + 2 * 64 * 4 + 64; };
+template <int NW> constexpr int p16_mw_smem_bytes() { return p16_mw_smem<NW>::bytes; }
 
 template <int NW, bool LOCAL>
 POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, long long slab_bytes) {

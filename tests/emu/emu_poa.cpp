@@ -128,6 +128,7 @@ extern "C" int32_t *emu_poa_block(const pd_params_t *pp, int n_seq, const int32_
 #if POA_EMU_LANES == 32
     std::vector<char> ring((size_t)std::max<int>(P16_SMEM_BYTES, p16_mw_smem_bytes<8>()) + 16);
     sh.ring = ring.data();
+    sh.ring_bytes = POA_EMU_NW == 1 ? P16_SMEM_BYTES : p16_mw_smem_bytes<POA_EMU_NW>();
 #endif
 #if POA_EMU_LANES > 1
     poa_emu::run_warp([&]() { poa_block<POA_EMU_NW>(sh, dp, B, L, O, 0); });
