@@ -28,7 +28,7 @@ using namespace poa;
 #define POA_MIN_BLOCKS 12  // resident single-warp POA blocks per SM the register budget is sized for
 #endif
 template <int NW>
-__global__ void __launch_bounds__(NW * 32, POA_MIN_BLOCKS / NW) poa_b200_block_kernel(DevParams P, DevBatch B, WsLayout L, char *ws_base, DevOut O) {
+__global__ void __launch_bounds__(NW * 32, POA_MIN_BLOCKS / NW) poa_b200_block_kernel(const __grid_constant__ DevParams P, const __grid_constant__ DevBatch B, const __grid_constant__ WsLayout L, char *ws_base, const __grid_constant__ DevOut O) {
     __shared__ Shared sh;
     extern __shared__ __align__(16) char dyn_smem[];  // NW == 1: P16_SMEM_BYTES, else p16_mw_smem_bytes<NW>()
     constexpr int dyn_bytes = NW == 1 ? P16_SMEM_BYTES : p16_mw_smem<NW>::bytes;

@@ -136,7 +136,7 @@ POA_D bool p16_eligible(const DevParams &P, int qlen) {
 }
 
 template <int NW, bool LOCAL>
-POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, long long slab_bytes) {
+POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, long long slab_bytes) {
     Ws &w = sh.ws;
     const int lane = poa_tid();
     const int n_node = sh.n_node;
@@ -351,41 +351,36 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
         const int pcb0 = pm0.y >> 8, pce0 = pm0.z >> 8;
         const unsigned pn0 = (unsigned)(pce0 - pcb0 + 1);
         const bool ring0 = prev_res && p0 == i - 1;
-#ifdef P16_UNROLL2
-#pragma unroll 2
-#else
+        unsigned rslot = (unsigned)(cb % P16_SMCH) * (3 * P16_CPB);  // ring slot of chunk c: (c % P16_SMCH) chunk-plane triples in
 #pragma unroll 1
-#endif
         for (int c = cb; c <= ce; ++c) {
             const int c0 = c * P16_CW;
-            unsigned M0 = INFP, M1 = INFP, M2 = INFP, M3 = INFP;
-            unsigned A0 = INFP, A1 = INFP, A2 = INFP, A3 = INFP;  // E1 in
-            unsigned B0 = INFP, B1 = INFP, B2 = INFP, B3 = INFP;  // E2 in
-            if (c >= pcb0 && c <= pce0 + 1) {
-                const unsigned idx = (unsigned)pm0.x + (unsigned)(c - pcb0);
-                int prevlast = inf_min;  // H_p[c0 - 1]: the last halfword of the previous chunk-plane
-                if (c > pcb0) {
-                    if (ring0 && c > cb) prevlast = ring_last;  // that chunk was read one iteration ago
-                    else prevlast = *reinterpret_cast<const short *>(slab + (size_t)idx * P16_CPB - 2);
-                }
-                if (c <= pce0) {
-                    uint4 h, a, b;
+            // first predecessor: its chunk c (H shifted one column right for M, E1, E2 as they are), or nothing
+            unsigned M0, M1, M2, M3, A0, A1, A2, A3, B0, B1, B2, B3;
+            {
+                uint4 h, a, b;
+                if (c >= pcb0 && c <= pce0) {
                     if (ring0) {
-                        const unsigned ro = (unsigned)(c % P16_SMCH) * (3 * P16_CPB);
-                        h = ring_ld(ring, ro); a = ring_ld(ring, ro + P16_CPB); b = ring_ld(ring, ro + 2 * P16_CPB);
+                        h = ring_ld(ring, rslot); a = ring_ld(ring, rslot + P16_CPB); b = ring_ld(ring, rslot + 2 * P16_CPB);
                     } else {
+                        const unsigned idx = (unsigned)pm0.x + (unsigned)(c - pcb0);
                         h = p16_ld(slab_lane + (size_t)idx * P16_CPB);
                         a = p16_ld(slab_lane + (size_t)(idx + pn0) * P16_CPB);
                         b = p16_ld(slab_lane + (size_t)(idx + 2 * pn0) * P16_CPB);
                     }
-                    const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
-                    if (ring0) ring_last = p_hi(rot);  // lane 0: last cell of this chunk of the previous row
-                    M0 = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot; M1 = h.x; M2 = h.y; M3 = h.z;
-                    A0 = a.x; A1 = a.y; A2 = a.z; A3 = a.w;
-                    B0 = b.x; B1 = b.y; B2 = b.z; B3 = b.w;
-                } else if (lane == 0) {
-                    M0 = p_pack(prevlast, inf_min);
+                } else {
+                    h.x = h.y = h.z = h.w = INFP; a = h; b = h;
                 }
+                int prevlast = inf_min;  // H_p[c0 - 1]: the last halfword of the previous chunk-plane
+                if (c > pcb0 && c <= pce0 + 1) {
+                    if (ring0 && c > cb) prevlast = ring_last;  // that chunk was read one iteration ago
+                    else prevlast = *reinterpret_cast<const short *>(slab + (size_t)((unsigned)pm0.x + (unsigned)(c - pcb0)) * P16_CPB - 2);
+                }
+                const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
+                if (ring0) ring_last = p_hi(rot);  // lane 0: last cell of this chunk of the previous row (only read back if it was one)
+                M0 = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot; M1 = h.x; M2 = h.y; M3 = h.z;
+                A0 = a.x; A1 = a.y; A2 = a.z; A3 = a.w;
+                B0 = b.x; B1 = b.y; B2 = b.z; B3 = b.w;
             }
 #pragma unroll 1
             for (int k = 1; k < ri.y; ++k) {  // further predecessors in in_id order (abpoa_align_simd.c:966-1029)
@@ -404,8 +399,7 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
                     if (c <= pce) {
                         uint4 h, a, b;
                         if (in_ring) {
-                            const unsigned ro = (unsigned)(c % P16_SMCH) * (3 * P16_CPB);
-                            h = ring_ld(ring, ro); a = ring_ld(ring, ro + P16_CPB); b = ring_ld(ring, ro + 2 * P16_CPB);
+                            h = ring_ld(ring, rslot); a = ring_ld(ring, rslot + P16_CPB); b = ring_ld(ring, rslot + 2 * P16_CPB);
                         } else {
                             h = p16_ld(slab_lane + (size_t)idx * P16_CPB);
                             a = p16_ld(slab_lane + (size_t)(idx + pn_) * P16_CPB);
@@ -489,9 +483,9 @@ POA_DN void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen,
             p16_st(dst + 4 * pstride, F20, F21, F22, F23);
             dst += P16_CPB;
             if (cur_res) {  // after every predecessor read of this chunk: a lane only ever touches its own slices
-                const unsigned ro = (unsigned)(c % P16_SMCH) * (3 * P16_CPB);
-                ring_st(ring, ro, H0, H1, H2, H3); ring_st(ring, ro + P16_CPB, A0, A1, A2, A3); ring_st(ring, ro + 2 * P16_CPB, B0, B1, B2, B3);
+                ring_st(ring, rslot, H0, H1, H2, H3); ring_st(ring, rslot + P16_CPB, A0, A1, A2, A3); ring_st(ring, rslot + 2 * P16_CPB, B0, B1, B2, B3);
             }
+            rslot = rslot == (P16_SMCH - 1) * (3 * P16_CPB) ? 0u : rslot + 3 * P16_CPB;
             // row maximum (abpoa_align_simd.c:1107-1119): remember the first and the last chunk attaining it
             if (track) {
                 const unsigned cm = p_max(p_max3(H0, H1, H2), H3);
