@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="blocks in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--slab-rows-factor", type=float, default=0.0, help="DP workspace rows per query base (0 = engine default; tuning experiments)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -210,7 +211,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     batch = gen_batch(args.workload, seed=1000 + rank, n_blocks=args.blocks)
-    eng = engine.PoaEngine(device=local_rank, warps_per_block=args.warps, ctas_per_sm=args.ctas_per_sm)
+    eng = engine.PoaEngine(device=local_rank, warps_per_block=args.warps, ctas_per_sm=args.ctas_per_sm, slab_rows_factor=args.slab_rows_factor)
     params = engine.make_params(**params_kw)
     stream = torch.cuda.current_stream().cuda_stream
 

@@ -25,10 +25,20 @@ using namespace poa;
 // kernels
 // ------------------------------------------------------------------------------------------------
 #ifndef POA_MIN_BLOCKS
-#define POA_MIN_BLOCKS 12  // resident single-warp POA blocks per SM the register budget is sized for
+// Resident single-warp POA blocks per SM the register budget is sized for.  ptxas maps any hint of 13..16 to 128 registers
+// per thread (16 resident blocks); 13 gives the leanest chunk loop of those (368 instructions, no spill inside the row loop;
+// the 72-byte stack frame is touched once per sequence).  Measured on configs[2]: 12 x 168 registers 217.9, 13 x 152 214.0,
+// 14 x 144 208.7, 15 x 136 206.4, 16 x 128 221.1 Gcells/s (profiles/bench_r01_v10_occupancy_sweep.json).
+#define POA_MIN_BLOCKS 13
+#endif
+// POA_MAXNREG (optional): cap registers per thread directly instead of through the resident-block hint
+#ifdef POA_MAXNREG
+#define POA_KERNEL_BOUNDS __maxnreg__(POA_MAXNREG)
+#else
+#define POA_KERNEL_BOUNDS __launch_bounds__(NW * 32, POA_MIN_BLOCKS / NW)
 #endif
 template <int NW>
-__global__ void __launch_bounds__(NW * 32, POA_MIN_BLOCKS / NW) poa_b200_block_kernel(const __grid_constant__ DevParams P, const __grid_constant__ DevBatch B, const __grid_constant__ WsLayout L, char *ws_base, const __grid_constant__ DevOut O) {
+__global__ void POA_KERNEL_BOUNDS poa_b200_block_kernel(const __grid_constant__ DevParams P, const __grid_constant__ DevBatch B, const __grid_constant__ WsLayout L, char *ws_base, const __grid_constant__ DevOut O) {
     __shared__ Shared sh;
     extern __shared__ __align__(16) char dyn_smem[];  // NW == 1: P16_SMEM_BYTES, else p16_mw_smem_bytes<NW>()
     constexpr int dyn_bytes = NW == 1 ? P16_SMEM_BYTES : p16_mw_smem<NW>::bytes;
@@ -190,6 +200,9 @@ namespace {
 
 template <int NW>
 cudaError_t launch_nw(int n_ctas, cudaStream_t st, const DevParams &P, const DevBatch &B, const WsLayout &L, char *ws, const DevOut &O) {
+    // shared memory, not L1, is what limits resident POA blocks per SM (L1 hit rate of the row slab is ~5 %): ask for the
+    // largest shared-memory carve-out; set per launch because the attribute is per device context
+    cudaFuncSetAttribute(poa_b200_block_kernel<NW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     poa_b200_block_kernel<NW><<<n_ctas, NW * 32, NW == 1 ? P16_SMEM_BYTES : p16_mw_smem_bytes<NW>(), st>>>(P, B, L, ws, O);
     return cudaGetLastError();
 }

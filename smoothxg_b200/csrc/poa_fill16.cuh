@@ -53,9 +53,20 @@ POA_D unsigned p_lolo(unsigned a, unsigned b) { return __byte_perm(a, b, 0x5410u
 
 constexpr int P16_CW = 256;          // columns per chunk
 constexpr int P16_CPB = 512;         // bytes per chunk-plane
-constexpr int P16_SMCH = 6;          // chunks of the previous row kept in shared memory (H, E1, E2)
+#ifndef POA_P16_SMCH
+#define POA_P16_SMCH 6
+#endif
+#ifndef POA_P16_QCH
+#define POA_P16_QCH 4  // 16 resident blocks x (ring + profile stage + metadata + 1 KB reserved) must fit 228 KB of shared memory
+#endif
+#ifdef POA_EXTRA_PLANE  // experiment only: one more (never read) plane per row, to see whether DRAM writes bound the fill
+constexpr int P16_PLANES = 6;
+#else
+constexpr int P16_PLANES = 5;
+#endif
+constexpr int P16_SMCH = POA_P16_SMCH;  // chunks of the previous row kept in shared memory (H, E1, E2)
 constexpr int P16_RING_BYTES = P16_SMCH * 3 * P16_CPB;
-constexpr int P16_QCH = 6;           // profile chunks of the row in flight staged in shared memory
+constexpr int P16_QCH = POA_P16_QCH;   // profile chunks of the row in flight staged in shared memory
 constexpr int P16_QBUF_OFF = P16_RING_BYTES, P16_META_OFF = P16_QBUF_OFF + P16_QCH * P16_CPB;  // meta: 2 x 128 B + 128 B
 constexpr int P16_SMEM_BYTES = P16_META_OFF + 3 * 128;
 
@@ -322,9 +333,9 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
         }
         if (end < beg) end = beg;
         const int cb = beg >> 8, ce = end >> 8, nch = ce - cb + 1;
-        if (used + 5LL * nch > slab_units) { if (lane == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+        if (used + (long long)P16_PLANES * nch > slab_units) { if (lane == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
         const unsigned roff = (unsigned)used;
-        used += 5LL * nch;
+        used += (long long)P16_PLANES * nch;
         inband += end - beg + 1;
         edge_rows += (long long)ri.y * (end - beg + 1);
 
@@ -481,6 +492,9 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
             p16_st(dst + 2 * pstride, B0, B1, B2, B3);
             p16_st(dst + 3 * pstride, F10, F11, F12, F13);
             p16_st(dst + 4 * pstride, F20, F21, F22, F23);
+#ifdef POA_EXTRA_PLANE
+            p16_st(dst + 5 * pstride, F20, F21, F22, F23);
+#endif
             dst += P16_CPB;
             if (cur_res) {  // after every predecessor read of this chunk: a lane only ever touches its own slices
                 ring_st(ring, rslot, H0, H1, H2, H3); ring_st(ring, rslot + P16_CPB, A0, A1, A2, A3); ring_st(ring, rslot + 2 * P16_CPB, B0, B1, B2, B3);
