@@ -53,14 +53,20 @@ inline block_sequences dedup_sequences(const std::vector<std::string> &seqs, con
 }
 
 // Score preset smooth_and_lace picks from the block's estimated identity when -a is given (src/smooth.cpp:2028-2062;
-// the MinHash estimate itself, rkmh::hash_sequences / rkmh::compare :2005-2023, stays in smoothxg).  Returns false and
+// the MinHash estimate itself, rkmh::hash_sequences / rkmh::compare :2005-2023, is mash_b200_block_identity(), include/mash_b200.h).  Returns false and
 // leaves the scores alone below 0.90 ("use the set/default penalties").  Blocks with different presets go into one
 // batch per preset (the engine's parameters are per batch).
 inline bool adaptive_poa_preset(float est_identity_threshold, int &poa_m, int &poa_n, int &poa_g, int &poa_e, int &poa_q, int &poa_c) {
-    static const int presets[5][7] = {{99, 1, 19, 39, 3, 81, 1}, {98, 1, 13, 31, 3, 51, 1}, {97, 1, 9, 16, 2, 41, 1},
-                                      {95, 1, 7, 11, 2, 33, 1}, {90, 1, 4, 6, 2, 26, 1}};
-    for (const auto &p : presets)
-        if (est_identity_threshold >= (float)p[0] / 100.0f) { poa_m = p[1]; poa_n = p[2]; poa_g = p[3]; poa_e = p[4]; poa_q = p[5]; poa_c = p[6]; return true; }
+    // the reference compares the float with double literals (0.95f and 0.9f are below 0.95 and 0.9); same table as
+    // mash_b200_preset() (include/mash_b200.h), which also computes the estimate itself on the GPU
+    static const double thr[5] = {0.99, 0.98, 0.97, 0.95, 0.90};
+    static const int presets[5][6] = {{1, 19, 39, 3, 81, 1}, {1, 13, 31, 3, 51, 1}, {1, 9, 16, 2, 41, 1}, {1, 7, 11, 2, 33, 1}, {1, 4, 6, 2, 26, 1}};
+    for (int r = 0; r < 5; ++r)
+        if ((double)est_identity_threshold >= thr[r]) {
+            const int *p = presets[r];
+            poa_m = p[0]; poa_n = p[1]; poa_g = p[2]; poa_e = p[3]; poa_q = p[4]; poa_c = p[5];
+            return true;
+        }
     return false;
 }
 

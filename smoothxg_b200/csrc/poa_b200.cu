@@ -187,6 +187,8 @@ struct poa_b200_batch {
     std::vector<int> h_hdr;
     // workspace
     char *d_ws = nullptr;
+    char *d_inputs = nullptr;  // one pooled allocation holding every d_* array above
+    size_t inputs_cap = 0;
     long long ws_bytes = 0;
     WsLayout layout{};
     int n_ctas = 0, nw = 1;
@@ -217,9 +219,7 @@ cudaError_t launch_kernel(int nw, int n_ctas, cudaStream_t st, const DevParams &
 }
 
 void free_batch_device(poa_b200_batch *b) {
-    cudaFree(b->d_block_seq_off); cudaFree(b->d_seq_off); cudaFree(b->d_seq_len); cudaFree(b->d_weight);
-    cudaFree(b->d_order); cudaFree(b->d_bases); cudaFree(b->d_hdr); cudaFree(b->d_counter);
-    cudaFree(b->d_arena_used); cudaFree(b->d_phase);
+    if (b->d_inputs) { b->eng->dev_pool.give(b->d_inputs, b->inputs_cap); b->d_inputs = nullptr; }  // all d_* input arrays live in it
     b->eng->dev_pool.give(b->d_ws, (size_t)b->ws_bytes); b->d_ws = nullptr;
     for (auto &a : b->arenas) b->eng->dev_pool.give(a.d, a.cap_bytes);
     b->arenas.clear();
@@ -265,15 +265,19 @@ Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int lev
     const long long edges = std::min<long long>(max_bases + max_seq, level >= 2 ? (1LL << 60) : 3 * nmax);
     s.pool_growth = 8 * edges + 64;
     long long row_bytes = vecs_per_row * 5 * (may32 ? 32 : 16);
-    if (b->dp.p16_ok) {  // chunked rows of the packed 16-bit fill: whole 256-column chunks, 5 planes x 512 B each
-        long long p16_bytes = (width / 256 + 2) * 2560;  // worst case: a partial chunk at either end
+    if (b->dp.p16_ok) {  // chunked rows of the packed 16-bit fill: whole 256-column chunks, P16_PLANES (H, E1, E2) x 512 B each
+        const long long chunk_bytes = (long long)P16_PLANES * P16_CPB;
+        long long p16_bytes = (width / 256 + 2) * chunk_bytes;  // worst case: a partial chunk at either end
         if (level == 0) {
             // first guess: a band-wide row touches band/256 + 1 chunks on average (measured 3.46 for 743-column bands,
             // whose rows are clipped at the matrix edges); 12 % headroom, overflow is retried at the next level
             const long long band = wb >= 0 ? std::min<long long>(max_len + 1, 2 * (wb + (long long)(b->dp.wf * max_len)) + 1) : max_len + 1;
-            p16_bytes = (long long)((band / 256.0 + 1.0) * 1.12 * 2560.0);
+            p16_bytes = (long long)((band / 256.0 + 1.0) * 1.12 * (double)chunk_bytes);
         }
-        row_bytes = std::max(row_bytes, p16_bytes);
+        // With match = 1 (smoothxg's default and every -a preset) p16_eligible() holds whenever the int16 test of
+        // abpoa_align_simd.c:1293-1302 does, so a block that cannot reach the int32 regime is sized for packed rows alone;
+        // the generic 5-plane rows only matter for int32 rows.  A misjudged block is re-run at the next level.
+        row_bytes = (level == 0 && !may32) ? p16_bytes : std::max(row_bytes, p16_bytes);
     }
     s.slab_bytes = rows * row_bytes;
     return s;
@@ -520,16 +524,24 @@ int poa_b200_batch_upload(poa_b200_engine_t *eng, const poa_b200_params_t *param
     CUB(cudaEventCreate(&b->ev0)); CUB(cudaEventCreate(&b->ev1));
     cudaEvent_t h0, h1;
     CUB(cudaEventCreate(&h0)); CUB(cudaEventCreate(&h1));
-    CUB(cudaMalloc(&b->d_block_seq_off, sizeof(long long) * (size_t)(n_blocks + 1)));
-    CUB(cudaMalloc(&b->d_seq_off, sizeof(long long) * (size_t)(n_seqs + 1)));
-    CUB(cudaMalloc(&b->d_seq_len, sizeof(int) * (size_t)std::max<int64_t>(n_seqs, 1)));
-    CUB(cudaMalloc(&b->d_weight, sizeof(int) * (size_t)std::max<int64_t>(n_seqs, 1)));
-    CUB(cudaMalloc(&b->d_bases, (size_t)std::max<int64_t>(n_bases, 1)));
-    CUB(cudaMalloc(&b->d_order, sizeof(int) * (size_t)std::max<int64_t>(n_blocks, 1)));
-    CUB(cudaMalloc(&b->d_hdr, sizeof(int) * HDR_WORDS * (size_t)std::max<int64_t>(n_blocks, 1)));
-    CUB(cudaMalloc(&b->d_counter, sizeof(int)));
-    CUB(cudaMalloc(&b->d_arena_used, sizeof(unsigned long long)));
-    CUB(cudaMalloc(&b->d_phase, sizeof(unsigned long long) * PH_N));
+    {
+        // every per-batch input / bookkeeping array is carved from ONE pooled device allocation: cudaMalloc / cudaFree per
+        // call cost up to hundreds of milliseconds each inside the end-to-end path (cudaFree synchronises the device)
+        const size_t nb1 = (size_t)std::max<int64_t>(n_blocks, 1), ns1 = (size_t)std::max<int64_t>(n_seqs, 1);
+        size_t off = 0;
+        auto carve = [&off](size_t bytes) { const size_t at = off; off += (bytes + 255) & ~(size_t)255; return at; };
+        const size_t o_bso = carve(sizeof(long long) * (size_t)(n_blocks + 1)), o_so = carve(sizeof(long long) * (size_t)(n_seqs + 1));
+        const size_t o_sl = carve(sizeof(int) * ns1), o_wt = carve(sizeof(int) * ns1), o_ba = carve((size_t)std::max<int64_t>(n_bases, 1));
+        const size_t o_or = carve(sizeof(int) * nb1), o_hd = carve(sizeof(int) * HDR_WORDS * nb1), o_ct = carve(sizeof(int));
+        const size_t o_au = carve(sizeof(unsigned long long)), o_ph = carve(sizeof(unsigned long long) * PH_N);
+        b->d_inputs = (char *)eng->dev_pool.take(off, &b->inputs_cap);
+        if (!b->d_inputs) { set_err(POA_B200_ENOMEM, "input cudaMalloc failed"); return fail(POA_B200_ENOMEM); }
+        char *base = b->d_inputs;
+        b->d_block_seq_off = (long long *)(base + o_bso); b->d_seq_off = (long long *)(base + o_so);
+        b->d_seq_len = (int *)(base + o_sl); b->d_weight = (int *)(base + o_wt); b->d_bases = (uint8_t *)(base + o_ba);
+        b->d_order = (int *)(base + o_or); b->d_hdr = (int *)(base + o_hd); b->d_counter = (int *)(base + o_ct);
+        b->d_arena_used = (unsigned long long *)(base + o_au); b->d_phase = (unsigned long long *)(base + o_ph);
+    }
     CUB(cudaMemsetAsync(b->d_phase, 0, sizeof(unsigned long long) * PH_N, st));
     CUB(cudaMemsetAsync(b->d_hdr, 0xff, sizeof(int) * HDR_WORDS * (size_t)std::max<int64_t>(n_blocks, 1), st));
     CUB(cudaEventRecord(h0, st));

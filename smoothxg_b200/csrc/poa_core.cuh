@@ -897,8 +897,11 @@ POA_D const S *bt_cell(const Ws &w, const int4 &pm, int plane, int j) {
 // ends here (H == 0), 2 = dead end
 // MODE 0 convex (abpoa_align_simd.c:309-458), 1 affine (:196-307: no second gap piece, F1 is plane 2), 2 linear (:116-194:
 // match, then deletion, then insertion, no state)
+// Rows of the packed 16-bit fill (LAY16) hold no F planes: when the walk reaches the insertion test there, bt_step()
+// returns 3 without having changed anything, the warp recomputes {F1[j], F2[j], F1[j-1], F2[j-1]} of the row
+// (p16_row_f(), poa_fill16.cuh) and calls again with them in `fv`.
 template <typename S, bool LAY16, int MODE>
-POA_D int bt_step(Shared &sh, const DevParams &P, const uint8_t *q, int &i, int &j, int &id, int &cur_op) {
+POA_D int bt_step(Shared &sh, const DevParams &P, const uint8_t *q, int &i, int &j, int &id, int &cur_op, const int *fv = nullptr) {
     Ws &w = sh.ws;
     const int inf_min = inf_min_of<S>(P);
     const int local = P.local;
@@ -971,20 +974,22 @@ POA_D int bt_step(Shared &sh, const DevParams &P, const uint8_t *q, int &i, int 
             }
         }
         if (hit == 0 && (cur_op & OP_F)) {
+            if (LAY16 && fv == nullptr) return 3;
             const bool inl = j - 1 >= rm.y;  // left neighbour inside this row's band?
             const int hl = inl ? (int)*bt_cell<S, LAY16>(w, rm, 0, j - 1) : inf_min;
             constexpr int PF1 = MODE == 0 ? 3 : 2;
-            const int F1j = *bt_cell<S, LAY16>(w, rm, PF1, j), F2j = MODE == 0 ? (int)*bt_cell<S, LAY16>(w, rm, 4, j) : inf_min;
+            const int F1j = LAY16 ? fv[0] : (int)*bt_cell<S, LAY16>(w, rm, PF1, j);
+            const int F2j = LAY16 ? fv[1] : (MODE == 0 ? (int)*bt_cell<S, LAY16>(w, rm, 4, j) : inf_min);
             if (cur_op & OP_F1) {
                 if (!(cur_op & OP_M) || Hj == F1j) {
-                    const int f1l = inl ? (int)*bt_cell<S, LAY16>(w, rm, PF1, j - 1) : inf_min;
+                    const int f1l = LAY16 ? fv[2] : (inl ? (int)*bt_cell<S, LAY16>(w, rm, PF1, j - 1) : inf_min);
                     if ((int)(S)(hl - oe1) == F1j) { cur_op = OP_M | OP_E; hit = 1; }
                     else if ((int)(S)(f1l - e1) == F1j) { cur_op = OP_F1; hit = 1; }
                 }
             }
             if (MODE == 0 && hit == 0 && (cur_op & OP_F2)) {
                 if (!(cur_op & OP_M) || Hj == F2j) {
-                    const int f2l = inl ? (int)*bt_cell<S, LAY16>(w, rm, 4, j - 1) : inf_min;
+                    const int f2l = LAY16 ? fv[3] : (inl ? (int)*bt_cell<S, LAY16>(w, rm, 4, j - 1) : inf_min);
                     if ((int)(S)(hl - oe2) == F2j) { cur_op = OP_M | OP_E; hit = 1; }
                     else if ((int)(S)(f2l - e2) == F2j) { cur_op = OP_F2; hit = 1; }
                 }
@@ -1052,7 +1057,21 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
             sh.bcast[0] = ti; sh.bcast[1] = tj; sh.bcast[2] = top; sh.bcast[3] = rc;
         }
         poa_sync_warp();
-        const int rc = sh.bcast[3];
+        int rc = sh.bcast[3];
+#if POA_WARP == 32
+        if (LAY16 && rc == 3) {  // insertion test on a row without stored F planes: recompute them (all lanes), then redo the step
+            poa_sync_warp();
+            int fv[4];
+            p16_row_f(sh, P, qlen, i, j, fv);
+            if (lane == 0) {
+                int ti = i, tj = j, tid_ = id, top = cur_op;
+                const int rc2 = bt_step<S, LAY16, MODE>(sh, P, q, ti, tj, tid_, top, fv);
+                sh.bcast[0] = ti; sh.bcast[1] = tj; sh.bcast[2] = top; sh.bcast[3] = rc2;
+            }
+            poa_sync_warp();
+            rc = sh.bcast[3];
+        }
+#endif
         i = sh.bcast[0]; j = sh.bcast[1]; cur_op = sh.bcast[2]; n = sh.n_cigar;
         poa_sync_warp();
         if (rc == 2) return;

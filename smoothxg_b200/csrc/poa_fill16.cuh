@@ -11,12 +11,12 @@
 //    for register 0) and both halves run the horizontal-gap recurrences at once;
 //  * F1/F2 are computed exactly: a 4-cell chain per lane, then a max-plus scan of the 64 lane-halves
 //    (G = F + e*position turns the decaying recurrence into a running maximum), then a per-cell fix-up;
-//  * a row is stored as [plane][chunk][lane][4 words] = 512-byte chunk-planes, so every predecessor read and
+//  * a row is stored as [plane H,E1,E2][chunk][lane][4 words] = 512-byte chunk-planes, so every predecessor read and
 //    every store is one fully coalesced 128-bit access per lane, and rows of different bands line up without
 //    shifts because chunks are in absolute column coordinates.
 //
 // Cells of a stored chunk that lie outside the row's band [beg,end] hold inf_min in the H, E1 and E2 planes
-// (what successors and the traceback may read); the F planes are only ever read inside the band.
+// (what successors and the traceback may read); the F planes are not stored at all (see P16_PLANES).
 #if POA_WARP == 32
 
 #ifdef POA_HOST_EMU
@@ -59,10 +59,13 @@ constexpr int P16_CPB = 512;         // bytes per chunk-plane
 #ifndef POA_P16_QCH
 #define POA_P16_QCH 4  // 16 resident blocks x (ring + profile stage + metadata + 1 KB reserved) must fit 228 KB of shared memory
 #endif
-#ifdef POA_EXTRA_PLANE  // experiment only: one more (never read) plane per row, to see whether DRAM writes bound the fill
-constexpr int P16_PLANES = 6;
+// Stored planes per row: H, E1, E2 -- what successor rows and the traceback's M / E moves read.  The horizontal-gap planes
+// F1 / F2 are NOT stored: no later row reads them, and the traceback needs them only on the rare insertion steps, where
+// p16_row_f() below recomputes them for one row with the fill's own arithmetic (2 of 5 planes = 40 % of the DP's DRAM writes).
+#ifdef POA_EXTRA_PLANE  // experiment only: one more (never read) plane per row, to see how far DRAM writes bound the fill
+constexpr int P16_PLANES = 4;
 #else
-constexpr int P16_PLANES = 5;
+constexpr int P16_PLANES = 3;
 #endif
 constexpr int P16_SMCH = POA_P16_SMCH;  // chunks of the previous row kept in shared memory (H, E1, E2)
 constexpr int P16_RING_BYTES = P16_SMCH * 3 * P16_CPB;
@@ -216,7 +219,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
             end0 = imin(qlen, imax(0, rr[0]) + bw);
         } else end0 = qlen;
         const int nch = (end0 >> 8) + 1;
-        if (5LL * nch > slab_units) { if (lane == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+        if ((long long)P16_PLANES * nch > slab_units) { if (lane == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
         if (lane == 0) rowmeta[0] = poa_make_int4(0, 0, end0, 0);
         for (int c = 0; c < nch; ++c) {
             unsigned v[5][4];
@@ -232,10 +235,10 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
                 }
                 for (int p = 0; p < 5; ++p) v[p][r] = p_pack(x[0][p], x[1][p]);
             }
-            for (int p = 0; p < 5; ++p)
+            for (int p = 0; p < 3; ++p)  // H, E1, E2 (row 0 is never a traceback row: the walk stops at i == 0)
                 p16_st(slab + ((long long)p * nch + c) * P16_CPB + lane * 16, v[p][0], v[p][1], v[p][2], v[p][3]);
         }
-        used = 5LL * nch;
+        used = (long long)P16_PLANES * nch;
         inband += end0 + 1;
         sync_block<NW>();
     }
@@ -274,7 +277,12 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
         // or the 4-element window holding it (byte / reduction-updated arrays)
         int idx = n1;
         if (lane == 1) idx = np0_n1; else if (lane == 3) idx = n1 + 1;
+#ifdef POA_Q_AHEAD
+        if (lane == 2) idx = n1 + 1;  // base of the row after n1: its profile chunks are staged while n1 is still being evaluated
+        const bool live = lane == 1 ? np0_n1 < cur : ((lane == 3 || lane == 2) ? n1 + 1 < rows : true);
+#else
         const bool live = lane == 1 ? np0_n1 < cur : (lane == 3 ? n1 + 1 < rows : true);
+#endif
         if (gkind == 1 && live) cpa16(sm, slot, gsrc + (size_t)(unsigned)idx * 16, false);
         else if (gkind == 2) cpa16(sm, slot, gsrc + (size_t)(unsigned)(idx & ~3) * 4, true);
         else if (gkind == 3 && live) cpa4(sm, slot, gsrc + (lane == 2 ? (size_t)(unsigned)(idx & ~3) : (size_t)(unsigned)idx * 4));
@@ -282,16 +290,39 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
     int np0 = fp[rows > 1 ? 1 : 0];  // first predecessor of the row about to be evaluated
     gather(1, np0, 1);
     cpa_commit();
+#ifdef POA_Q_AHEAD
+    // Profile chunks are staged ONE ROW AHEAD: row i+1's copies are issued when row i's chunk loop ends (its base arrives with
+    // row i's metadata, the chunk range is guessed from row i's band), so they have the whole row boundary to land.  cp.async
+    // groups alternate G (metadata of the next row, committed at the top of a row) and Q (profile of the next row, committed
+    // after the chunk loop; empty after the last row): every wait below leaves exactly the youngest group in flight.
+    int rb_next = rows > 1 ? (int)rbase[1] : 0, scb_next = 0, sce_next = -1;
+    auto stage_profile = [&](int rbx, const int4 &pmeta) {
+        scb_next = pmeta.y >> 8; sce_next = imin(imin((pmeta.z >> 8) + 1, scb_next + P16_QCH - 1), nchq - 1);
+        const char *qg = qp + (size_t)(unsigned)(rbx * nchq + scb_next) * P16_CPB + lane * 16;
+        for (int k = 0; k <= sce_next - scb_next; ++k) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qg + (size_t)k * P16_CPB, false);
+    };
+    if (rows > 1) stage_profile(rb_next, prev_meta);
+    cpa_commit();
+#endif
 
     // ---- rows in index order (abpoa_align_simd.c:1205-1221)
     for (int i = 1; i < rows; ++i) {
+#ifdef POA_Q_AHEAD
+        cpa_wait_pending(1);  // this row's metadata (G) has landed; its profile (Q, younger) may still be in flight
+#else
         cpa_wait_pending(0);
+#endif
         sync_block<NW>();  // the slot was filled by other lanes' copies
         const unsigned slot = P16_META_OFF + (unsigned)(i & 1) * 128;
         const uint4 ri_u = ring_ld(sm, slot), npm_u = ring_ld(sm, slot + 16);
         const int4 ri = poa_make_int4((int)ri_u.x, (int)ri_u.y, (int)ri_u.z, (int)ri_u.w);  // {in_off, in_n, out_off, out_n}
         const int4 npm = poa_make_int4((int)npm_u.x, (int)npm_u.y, (int)npm_u.z, (int)npm_u.w);
+#ifdef POA_Q_AHEAD
+        const int rb = rb_next, p0 = np0;
+        rb_next = (ring_ld32(sm, slot + 32) >> (8 * ((i + 1) & 3))) & 0xff;  // base of row i + 1 (garbage after the last row: unused)
+#else
         const int rb = (ring_ld32(sm, slot + 32) >> (8 * (i & 3))) & 0xff, p0 = np0;
+#endif
         const int nnp0 = i + 1 < rows ? ring_ld32(sm, slot + 36) : 0;
         const int r = ring_ld32(sm, slot + 40);
         int ml = ring_ld32(sm, slot + 48 + 4 * (i & 3)), mr = ring_ld32(sm, slot + 64 + 4 * (i & 3));
@@ -305,12 +336,18 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
         np0 = nnp0;
         // profile chunks of this row: staged now for the chunk range the previous row covered plus one (bands move
         // slowly), so the copies overlap the band computation below; corrected after it if the guess was wrong
+#ifdef POA_Q_AHEAD
+        int scb = scb_next, sce = sce_next;  // staged when the previous row's chunk loop ended
+        int qpend = 1;                       // groups that may stay in flight when the first chunk reads the profile: this row's G
+#else
         int scb = prev_meta.y >> 8, sce = imin(imin((prev_meta.z >> 8) + 1, scb + P16_QCH - 1), nchq - 1);
         {
             const char *qg = qp + (size_t)(unsigned)(rb * nchq + scb) * P16_CPB + lane * 16;
             for (int k = 0; k <= sce - scb; ++k) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qg + (size_t)k * P16_CPB, false);
             cpa_commit();
         }
+        const int qpend = 0;
+#endif
         // second predecessor's row descriptor, once per row (every chunk needs it; a third one is rare)
         int pk1 = -1;
         int4 pm1 = pm0;
@@ -355,6 +392,9 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
             for (int k = 0; k < nch; ++k) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qrow + (size_t)(unsigned)(cb + k) * P16_CPB, false);
             cpa_commit();
             scb = cb; qst = true;
+#ifdef POA_Q_AHEAD
+            qpend = 0;  // the corrected copies are now the youngest group
+#endif
         }
         char *dst = slab_lane + (size_t)roff * P16_CPB;
         const size_t pstride = (size_t)(unsigned)nch * P16_CPB;
@@ -430,7 +470,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
             if (local && c == 0 && lane == 0) M0 = p_max(M0, p_pack(0, inf_min));  // abpoa_align_simd.c:974 (`first` = 0)
             // H~ = max(M + profile, E1, E2) (abpoa_align_simd.c:1032-1050); the profile chunk is read as late as possible
             uint4 qv;
-            if (qst) { if (c == cb) cpa_wait_pending(0); qv = ring_ld(sm, P16_QBUF_OFF + (unsigned)(c - scb) * P16_CPB + lane * 16); }
+            if (qst) { if (c == cb) cpa_wait_pending(qpend); qv = ring_ld(sm, P16_QBUF_OFF + (unsigned)(c - scb) * P16_CPB + lane * 16); }
             else qv = p16_ld(qrow + (size_t)(unsigned)c * P16_CPB);
             unsigned H0 = p_max3(p_add(M0, qv.x), A0, B0), H1 = p_max3(p_add(M1, qv.y), A1, B1);
             unsigned H2 = p_max3(p_add(M2, qv.z), A2, B2), H3 = p_max3(p_add(M3, qv.w), A3, B3);
@@ -490,10 +530,8 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
             p16_st(dst, H0, H1, H2, H3);
             p16_st(dst + pstride, A0, A1, A2, A3);
             p16_st(dst + 2 * pstride, B0, B1, B2, B3);
-            p16_st(dst + 3 * pstride, F10, F11, F12, F13);
-            p16_st(dst + 4 * pstride, F20, F21, F22, F23);
 #ifdef POA_EXTRA_PLANE
-            p16_st(dst + 5 * pstride, F20, F21, F22, F23);
+            p16_st(dst + 3 * pstride, F20, F21, F22, F23);
 #endif
             dst += P16_CPB;
             if (cur_res) {  // after every predecessor read of this chunk: a lane only ever touches its own slices
@@ -511,6 +549,10 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
         prev_meta = poa_make_int4((int)roff, beg, end, 0);
         prev_res = cur_res;
         if (lane == 0) rowmeta[i] = prev_meta;
+#ifdef POA_Q_AHEAD
+        if (i + 1 < rows) stage_profile(rb_next, prev_meta);  // the profile stage is free: this row's last chunk has read it
+        cpa_commit();                                         // Q of row i + 1 (an empty group after the last row)
+#endif
         if (track) {
             // first / last column holding the row maximum: bit r of a lane's mask = low-half cell r equals it, bit 4+r = high half
             const unsigned pat = p_pack(rmx, rmx);
@@ -535,7 +577,11 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
             prev_left = left; prev_right = right;
             if (local && rmx > best_score) { best_score = rmx; best_i = i; best_j = left; }  // abpoa_align_simd.c:1208-1210
             if (wb >= 0) {  // abpoa_align_simd.c:1121-1130; reductions without a return value: nothing to wait for
+#ifdef POA_Q_AHEAD
+                cpa_wait_pending(1);  // the staged successor rows (G); the next row's profile (Q) stays in flight
+#else
                 cpa_wait_pending(0);
+#endif
                 if (lane < ri.w) { const int out_row = ring_ld32(sm, P16_META_OFF + 256 + lane * 4); poa_red_max(&mprr[out_row], right + 1); poa_red_min(&mplr[out_row], left + 1); }
                 for (int k = lane + POA_WARP; k < ri.w; k += POA_WARP) {
                     const int o = pool_row[ri.z + k];
@@ -545,6 +591,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
         }
         // no barrier here: the next row starts with one (after its cp.async wait)
     }
+    cpa_wait_pending(0);
     sync_block<NW>();
     // ---- global best (abpoa_align_simd.c:1092-1105)
     if (lane == 0) {
@@ -562,6 +609,112 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
         sh.inband += inband; sh.edge_rows += edge_rows;
     }
     sync_block<NW>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// F1 / F2 of row i at columns j and j - 1, for the traceback's insertion steps (abpoa_align_simd.c:420-445 reads
+// dp_f1[j], dp_f1[j-1], dp_f2[j], dp_f2[j-1]).  The fill does not store the F planes; this re-runs its arithmetic --
+// the same packed operations in the same order -- for chunks beg >> 8 .. j >> 8 of that one row: predecessors' H / E1 / E2
+// from the slab, the profile from qp[] (both still in place while the alignment is traced back).  One warp; every lane
+// returns the same four values {F1[j], F2[j], F1[j-1], F2[j-1]}; the j - 1 entries are inf_min when j - 1 < beg, which is
+// what the traceback substitutes there.  Cost: one row (3-4 chunks) per insertion step, about 0.1 % of the fill's work.
+POA_DN void p16_row_f(Shared &sh, const DevParams &P, int qlen, int i, int j, int *out) {
+    Ws &w = sh.ws;
+    const int lane = poa_tid() % POA_WARP;
+    const int inf_min = inf_min_of<short>(P);
+    const bool local = P.local != 0;
+    const int e1 = P.e1, e2 = P.e2, oe1 = P.oe1, oe2 = P.oe2;
+    const int emax = imax(e1, e2);
+    const int negl = -32768 + 8 * emax + 8;
+    const unsigned INFP = p_pack(inf_min, inf_min), NEGLP = p_pack(negl, negl);
+    const unsigned NOE1 = p_pack(-oe1, -oe1), NOE2 = p_pack(-oe2, -oe2), NE1 = p_pack(-e1, -e1), NE2 = p_pack(-e2, -e2);
+    const unsigned NE1_2 = p_add(NE1, NE1), NE1_3 = p_add(NE1_2, NE1);
+    const unsigned NE2_2 = p_add(NE2, NE2), NE2_3 = p_add(NE2_2, NE2);
+    const unsigned OFF1 = p_pack(e1 * 4 * (lane + 1), e1 * 4 * (lane + 33)), NOFF1 = p_pack(-e1 * 4 * lane, -e1 * 4 * (lane + 32));
+    const unsigned OFF2 = p_pack(e2 * 4 * (lane + 1), e2 * 4 * (lane + 33)), NOFF2 = p_pack(-e2 * 4 * lane, -e2 * 4 * (lane + 32));
+    const unsigned NCW1 = p_pack(-e1 * P16_CW, -e1 * P16_CW), NCW2 = p_pack(-e2 * P16_CW, -e2 * P16_CW);
+    const int f0_1 = imax(inf_min - oe1, inf_min - e1), f0_2 = imax(inf_min - oe2, inf_min - e2);
+    const int nchq = (qlen >> 8) + 1;
+    const int4 rm = w.rowmeta[i], ri = w.rowinfo[i];
+    const int beg = rm.y, end = rm.z, cb = beg >> 8, ce = end >> 8, rb = w.rbase[i];
+    const char *slab = w.slab, *slab_lane = slab + lane * 16;
+    const char *qrow = w.qp + (size_t)(unsigned)(rb * nchq) * P16_CPB + lane * 16;
+    unsigned carry1 = p_pack(f0_1 + e1 * (beg - cb * P16_CW), f0_1 + e1 * (beg - cb * P16_CW));
+    unsigned carry2 = p_pack(f0_2 + e2 * (beg - cb * P16_CW), f0_2 + e2 * (beg - cb * P16_CW));
+    int res[4] = {inf_min, inf_min, inf_min, inf_min};
+    const int cj = j >> 8;
+    for (int c = cb; c <= cj; ++c) {
+        const int c0 = c * P16_CW;
+        unsigned M0 = INFP, M1 = INFP, M2 = INFP, M3 = INFP, A0 = INFP, A1 = INFP, A2 = INFP, A3 = INFP, B0 = INFP, B1 = INFP, B2 = INFP, B3 = INFP;
+        for (int k = 0; k < ri.y; ++k) {  // predecessors (abpoa_align_simd.c:966-1029)
+            const int pk = w.pool_row[ri.x + k];
+            const int4 pm = w.rowmeta[pk];
+            const int pcb = pm.y >> 8, pce = pm.z >> 8;
+            if (c >= pcb && c <= pce + 1) {
+                const unsigned pn_ = (unsigned)(pce - pcb + 1), idx = (unsigned)pm.x + (unsigned)(c - pcb);
+                int prevlast = inf_min;
+                if (c > pcb) prevlast = *reinterpret_cast<const short *>(slab + (size_t)idx * P16_CPB - 2);
+                if (c <= pce) {
+                    const uint4 h = p16_ld(slab_lane + (size_t)idx * P16_CPB);
+                    const uint4 a = p16_ld(slab_lane + (size_t)(idx + pn_) * P16_CPB);
+                    const uint4 b = p16_ld(slab_lane + (size_t)(idx + 2 * pn_) * P16_CPB);
+                    const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
+                    const unsigned s0 = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot;
+                    M0 = p_max(M0, s0); M1 = p_max(M1, h.x); M2 = p_max(M2, h.y); M3 = p_max(M3, h.z);
+                    A0 = p_max(A0, a.x); A1 = p_max(A1, a.y); A2 = p_max(A2, a.z); A3 = p_max(A3, a.w);
+                    B0 = p_max(B0, b.x); B1 = p_max(B1, b.y); B2 = p_max(B2, b.z); B3 = p_max(B3, b.w);
+                } else if (lane == 0) {
+                    M0 = p_max(M0, p_pack(prevlast, inf_min));
+                }
+            }
+        }
+        if (local && c == 0 && lane == 0) M0 = p_max(M0, p_pack(0, inf_min));
+        const uint4 qv = p16_ld(qrow + (size_t)(unsigned)c * P16_CPB);
+        unsigned H0 = p_max3(p_add(M0, qv.x), A0, B0), H1 = p_max3(p_add(M1, qv.y), A1, B1);
+        unsigned H2 = p_max3(p_add(M2, qv.z), A2, B2), H3 = p_max3(p_add(M3, qv.w), A3, B3);
+        if ((c == cb && beg > c0) || (c == ce && end < c0 + P16_CW - 1)) {
+            const int brel = imax(beg - c0, 0), erel = imin(end - c0, P16_CW - 1);
+            const unsigned da = p_pack(lane * 4 - brel, 128 + lane * 4 - brel), db = p_pack(erel - lane * 4, erel - 128 - lane * 4);
+            const unsigned m0 = p_signmask(p_min(da, db));
+            const unsigned m1 = p_signmask(p_min(p_add(da, 0x00010001u), p_add(db, 0xffffffffu)));
+            const unsigned m2 = p_signmask(p_min(p_add(da, 0x00020002u), p_add(db, 0xfffefffeu)));
+            const unsigned m3 = p_signmask(p_min(p_add(da, 0x00030003u), p_add(db, 0xfffdfffdu)));
+            H0 = (H0 & ~m0) | (INFP & m0); H1 = (H1 & ~m1) | (INFP & m1);
+            H2 = (H2 & ~m2) | (INFP & m2); H3 = (H3 & ~m3) | (INFP & m3);
+        }
+        unsigned F1[4], F2[4];
+        {
+            const unsigned l1 = p_add(H0, NOE1), l2 = p_addmax(l1, NE1, p_add(H1, NOE1)), l3 = p_addmax(l2, NE1, p_add(H2, NOE1));
+            const unsigned lout = p_addmax(l3, NE1, p_add(H3, NOE1));
+            const unsigned k1 = p_add(H0, NOE2), k2 = p_addmax(k1, NE2, p_add(H1, NOE2)), k3 = p_addmax(k2, NE2, p_add(H2, NOE2));
+            const unsigned kout = p_addmax(k3, NE2, p_add(H3, NOE2));
+            unsigned g1 = p_add(lout, OFF1), g2 = p_add(kout, OFF2);
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned u1 = (unsigned)poa_shfl_up((int)g1, d), u2 = (unsigned)poa_shfl_up((int)g2, d);
+                g1 = p_max(g1, u1); g2 = p_max(g2, u2);
+            }
+            unsigned x1 = (unsigned)poa_shfl_up((int)g1, 1), x2 = (unsigned)poa_shfl_up((int)g2, 1);
+            const unsigned t1 = (unsigned)poa_shfl((int)g1, 31), t2 = (unsigned)poa_shfl((int)g2, 31);
+            if (lane == 0) { x1 = NEGLP; x2 = NEGLP; }
+            x1 = p_max3(x1, p_lolo(NEGLP, t1), carry1);
+            x2 = p_max3(x2, p_lolo(NEGLP, t2), carry2);
+            const unsigned fin1 = p_add(x1, NOFF1), fin2 = p_add(x2, NOFF2);
+            carry1 = p_add(p_max3(t1, p_swap(t1), carry1), NCW1);
+            carry2 = p_add(p_max3(t2, p_swap(t2), carry2), NCW2);
+            F1[0] = fin1; F1[1] = p_addmax(fin1, NE1, l1); F1[2] = p_addmax(fin1, NE1_2, l2); F1[3] = p_addmax(fin1, NE1_3, l3);
+            F2[0] = fin2; F2[1] = p_addmax(fin2, NE2, k1); F2[2] = p_addmax(fin2, NE2_2, k2); F2[3] = p_addmax(fin2, NE2_3, k3);
+        }
+        for (int t = 0; t < 2; ++t) {  // columns j and j - 1 that fall into this chunk
+            const int x = j - t;
+            if ((x >> 8) != c || x < beg) continue;
+            const int u = x & 255, src = (u & 127) >> 2, r = u & 3;
+            const unsigned f1 = r == 0 ? F1[0] : r == 1 ? F1[1] : r == 2 ? F1[2] : F1[3];
+            const unsigned f2 = r == 0 ? F2[0] : r == 1 ? F2[1] : r == 2 ? F2[2] : F2[3];
+            const int v1 = (u >> 7) ? p_hi(f1) : p_lo(f1), v2 = (u >> 7) ? p_hi(f2) : p_lo(f2);
+            res[2 * t] = poa_shfl(v1, src); res[2 * t + 1] = poa_shfl(v2, src);
+        }
+    }
+    out[0] = res[0]; out[1] = res[1]; out[2] = res[2]; out[3] = res[3];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -646,7 +799,7 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
             end0 = imin(qlen, imax(0, rr[0]) + bw);
         } else end0 = qlen;
         const int nch = (end0 >> 8) + 1;
-        if (5LL * nch > slab_units) { if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+        if ((long long)P16_PLANES * nch > slab_units) { if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
         if (tid == 0) rowmeta[0] = poa_make_int4(0, 0, end0, 0);
         for (int c = wid; c < nch; c += NW) {
             unsigned v[5][4];
@@ -662,10 +815,10 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
                 }
                 for (int p = 0; p < 5; ++p) v[p][r] = p_pack(x[0][p], x[1][p]);
             }
-            for (int p = 0; p < 5; ++p)
+            for (int p = 0; p < 3; ++p)  // H, E1, E2 (row 0 is never a traceback row: the walk stops at i == 0)
                 p16_st(slab + ((long long)p * nch + c) * P16_CPB + lane * 16, v[p][0], v[p][1], v[p][2], v[p][3]);
         }
-        used = 5LL * nch;
+        used = (long long)P16_PLANES * nch;
         inband += end0 + 1;
         sync_block<NW>();
     }
@@ -704,9 +857,9 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
         }
         if (end < beg) end = beg;
         const int cb = beg >> 8, ce = end >> 8, nch = ce - cb + 1;
-        if (used + 5LL * nch > slab_units) { if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+        if (used + (long long)P16_PLANES * nch > slab_units) { if (tid == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
         const unsigned roff = (unsigned)used;
-        used += 5LL * nch;
+        used += (long long)P16_PLANES * nch;
         inband += end - beg + 1;
         edge_rows += (long long)ri.y * (end - beg + 1);
         int cf1 = f0_1 + e1 * (beg - cb * P16_CW), cf2 = f0_2 + e2 * (beg - cb * P16_CW);  // F entering column cb*256
@@ -820,7 +973,6 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
                 }
                 char *dst = slab_lane + (size_t)(roff + (unsigned)(c - cb)) * P16_CPB;
                 p16_st(dst, H0, H1, H2, H3); p16_st(dst + pstride, A0, A1, A2, A3); p16_st(dst + 2 * pstride, B0, B1, B2, B3);
-                p16_st(dst + 3 * pstride, F10, F11, F12, F13); p16_st(dst + 4 * pstride, F20, F21, F22, F23);
                 if (cur_res) {
                     ring_st(ring, cslot, H0, H1, H2, H3); ring_st(ring, cslot + P16_CPB, A0, A1, A2, A3); ring_st(ring, cslot + 2 * P16_CPB, B0, B1, B2, B3);
                     if (lane == 31) lastH[(i & 1) * 64 + (c & 63)] = p_hi(H3);

@@ -4,7 +4,15 @@
 #include <iostream>
 #include <sstream>
 #include "poa_b200_smooth.hpp"
-int main() {
+int main(int argc, char **argv) {
+    if (argc > 1) {  // preset mode: thresholds on the command line -> "m n g e q c" or "-" per line (src/smooth.cpp:2026-2062)
+        for (int a = 1; a < argc; ++a) {
+            int m = 0, n = 0, g = 0, e = 0, q = 0, c = 0;
+            if (poa_b200::adaptive_poa_preset(std::stof(argv[a]), m, n, g, e, q, c)) printf("%d %d %d %d %d %d\n", m, n, g, e, q, c);
+            else printf("-\n");
+        }
+        return 0;
+    }
     std::vector<std::string> seqs, names; std::vector<bool> revs;
     std::string line;
     while (std::getline(std::cin, line)) {

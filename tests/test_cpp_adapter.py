@@ -38,6 +38,9 @@ def test_dedup_and_encoding_on_cpu():
     inp = "a\t+\tACGT\nb\t-\tACGTN\nc\t+\tACGT\nd\t-\tACGT\ne\t+\tacgu\nf\t+\tACGTN\n"
     out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.strip().split("\n")
     assert out == ["3 a+ c+ d- 0123", "2 b- f+ 01234", "1 e+ 0123"]
+    # adaptive_poa_preset: the reference compares the float estimate with double literals (0.95f < 0.95, 0.9f < 0.9)
+    out = subprocess.run([exe, "0.995", "0.99", "0.98", "0.975", "0.95", "0.9500001", "0.9", "0.9000001", "0.7"], capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    assert out == ["1 19 39 3 81 1", "1 19 39 3 81 1", "1 13 31 3 51 1", "1 9 16 2 41 1", "1 4 6 2 26 1", "1 7 11 2 33 1", "-", "1 4 6 2 26 1", "-"]
 
 
 @pytest.mark.gpu
