@@ -139,7 +139,11 @@ POA_D int p16_ldcg(const int *p) { return __ldcg(p); }
 #endif
 POA_D void p16_st(char *p, unsigned a, unsigned b, unsigned c, unsigned d) {
     uint4 u; u.x = a; u.y = b; u.z = c; u.w = d;
+#if defined(POA_ST_CS) && !defined(POA_HOST_EMU)
+    __stcs(reinterpret_cast<uint4 *>(p), u);  // row planes are written once and (the ring aside) read much later or never: evict first
+#else
     *reinterpret_cast<uint4 *>(p) = u;
+#endif
 }
 
 // Can this alignment run in packed 16-bit arithmetic without any intermediate leaving the int16 range?
