@@ -19,6 +19,7 @@
 #include <utility>
 #include <vector>
 
+#include "mash_b200.h"
 #include "poa_b200.h"
 
 namespace poa_b200 {
@@ -68,6 +69,27 @@ inline bool adaptive_poa_preset(float est_identity_threshold, int &poa_m, int &p
             return true;
         }
     return false;
+}
+
+// Batched form of the estimate itself (src/smooth.cpp:1982-2023): `ranges[b]` = the raw strings of block b's path ranges
+// (the XG walk :1987-1992, before padding / orientation / de-duplication), upper case.  Returns est_identity_threshold per
+// block, -1 where fewer than two strings have 8*kmer_size bases (the reference then keeps the user's scores).  Runs on the
+// GPU (include/mash_b200.h); blocks deeper than max_block_depth_for_padding_more (:1984) are the caller's to leave out.
+inline std::vector<float> estimate_block_identity(int device, const std::vector<std::vector<std::string>> &ranges, int kmer_size = 17) {
+    std::vector<int64_t> block_seq_off(1, 0), seq_off(1, 0);
+    std::vector<int32_t> seq_len;
+    std::string bases;
+    for (auto &blk : ranges) {
+        for (auto &s : blk) { bases += s; seq_len.push_back((int32_t)s.size()); seq_off.push_back((int64_t)bases.size()); }
+        block_seq_off.push_back((int64_t)seq_len.size());
+    }
+    std::vector<float> thr(ranges.size(), -1.0f);
+    if (ranges.empty()) return thr;
+    if (bases.empty()) bases.push_back('N');
+    const int rc = mash_b200_block_identity(device, kmer_size, (int64_t)ranges.size(), block_seq_off.data(), seq_len.data(), seq_off.data(),
+                                            bases.data(), thr.data(), nullptr, nullptr, nullptr, nullptr);
+    if (rc != MASH_B200_OK) throw std::runtime_error(std::string("poa_b200: identity estimate failed: ") + mash_b200_last_error());
+    return thr;
 }
 
 struct step_t { int32_t node_id; bool is_rev; };            // odgi handle: id + orientation

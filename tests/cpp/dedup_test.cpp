@@ -5,6 +5,20 @@
 #include <sstream>
 #include "poa_b200_smooth.hpp"
 int main(int argc, char **argv) {
+    if (argc > 1 && std::string(argv[1]) == "identity") {  // stdin: "block seq" lines -> one threshold per block, or the error text
+        std::vector<std::vector<std::string>> ranges;
+        std::string line;
+        while (std::getline(std::cin, line)) {
+            std::istringstream is(line); size_t b; std::string q;
+            if (!(is >> b >> q)) continue;
+            if (ranges.size() <= b) ranges.resize(b + 1);
+            ranges[b].push_back(q);
+        }
+        try {
+            for (float t : poa_b200::estimate_block_identity(0, ranges)) printf("%.9g\n", t);
+        } catch (const std::exception &e) { printf("error: %s\n", e.what()); return 3; }
+        return 0;
+    }
     if (argc > 1) {  // preset mode: thresholds on the command line -> "m n g e q c" or "-" per line (src/smooth.cpp:2026-2062)
         for (int a = 1; a < argc; ++a) {
             int m = 0, n = 0, g = 0, e = 0, q = 0, c = 0;

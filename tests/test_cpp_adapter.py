@@ -43,6 +43,42 @@ def test_dedup_and_encoding_on_cpu():
     assert out == ["1 19 39 3 81 1", "1 19 39 3 81 1", "1 13 31 3 51 1", "1 9 16 2 41 1", "1 4 6 2 26 1", "1 7 11 2 33 1", "-", "1 4 6 2 26 1", "-"]
 
 
+def _identity_exe():
+    exe = os.path.join(os.path.dirname(EXE), "dedup_test")
+    src = os.path.join(ROOT, "tests", "cpp", "dedup_test.cpp")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L", LIBDIR, "-lpoa_b200", f"-Wl,-rpath,{LIBDIR}"])
+    return exe
+
+
+def _identity_input():
+    from tests.mash_cases import make_cases
+    blocks = [seqs for _, k, seqs in make_cases(seed=31, n=10) if k == 17 and seqs]
+    return blocks, "".join(f"{b} {s}\n" for b, seqs in enumerate(blocks) for s in seqs)
+
+
+def test_identity_estimate_has_no_cpu_path():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    _, inp = _identity_input()
+    out = subprocess.run([_identity_exe(), "identity"], input=inp, capture_output=True, text=True)
+    assert out.returncode == 3 and "identity estimate failed" in out.stdout
+
+
+@pytest.mark.gpu
+def test_identity_estimate_through_the_adapter():
+    """poa_b200::estimate_block_identity (the batched src/smooth.cpp:1982-2023) == the oracle, bit for bit."""
+    from oracle.mash import MashOracle
+    blocks, inp = _identity_input()
+    out = subprocess.run([_identity_exe(), "identity"], input=inp, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    got = [np.float32(x) for x in out.stdout.split()]
+    ora = MashOracle()
+    want = [ora.block(seqs, 17)[1] for seqs in blocks]
+    assert got == [np.float32(-1.0) if w is None else w for w in want]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("padding,local,cons", [(0, 0, "Consensus_0"), (5, 0, "-"), (3, 1, "cons")])
 def test_adapter_matches_ctypes_path(padding, local, cons):
