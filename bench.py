@@ -139,6 +139,25 @@ def cpu_reference(batch, params_kw, n_sample: int, threads: int):
     return sub, time.perf_counter() - t0, "port", "scalar"
 
 
+def identity_estimate_leg(batch, device: int, n_blocks: int = 2000) -> dict:
+    """The step in front of the POA (include/mash_b200.h): the --adaptive-poa-params identity estimate on
+    the first n_blocks blocks of the same shard, host strings in, thresholds out; outside the timed POA region and never
+    fatal for the headline line."""
+    try:
+        from smoothxg_b200 import adaptive
+        fb = adaptive.from_codes(batch.select(range(min(n_blocks, batch.n_blocks))))
+        adaptive.block_identity(fb, device=device)
+        t0 = time.perf_counter()
+        r = adaptive.block_identity(fb, device=device)
+        secs = time.perf_counter() - t0
+        stt = r["stats"]
+        return {"value": fb.n_blocks / secs, "unit": "blocks/s", "blocks": fb.n_blocks, "ms": secs * 1e3,
+                "device_ms": {k: round(stt[k], 2) for k in ("h2d_ms", "hash_ms", "sort_ms", "compare_ms", "d2h_ms", "host_ms")},
+                "gpu_launches": stt["kernel_launches"], "min_threshold": float(r["threshold"].min()), "max_threshold": float(r["threshold"].max())}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -324,6 +343,8 @@ def main():
             line["cpu_baseline"] = {"value": sub_cells / secs / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
                                     "blocks_per_s": sub.n_blocks / secs,
                                     "sample": f"first {sub.n_blocks} blocks of the shard, abPOA v1.5.4 {simd} via oracle/_ref, OpenMP dynamic over blocks, {secs:.1f} s"}
+        if world == 1 and not args.no_e2e and args.workload == "10000x32x2kb":
+            line["next_rows"] = {"adaptive_identity_estimate": identity_estimate_leg(batch, local_rank)}
         print(json.dumps(line))
     eng.close()
     if world > 1:

@@ -86,12 +86,30 @@ struct PinnedPool {
         }
         void *p = nullptr;
         size_t want = bytes + bytes / 8 + 4096;
-        if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (cudaMallocHost(&p, want) != cudaSuccess) {
+            // page-locking can fail where pageable memory is still plentiful (locked-memory limits, many ranks on one host):
+            // drop the pooled buffers and retry, then fall back to ordinary host memory (the copy is staged by the driver)
+            cudaGetLastError();
+            trim();
+            if (cudaMallocHost(&p, want) != cudaSuccess) {
+                cudaGetLastError();
+                p = malloc(want);
+                if (!p) return nullptr;
+                std::lock_guard<std::mutex> lk(mu);
+                pageable.push_back(p);
+            }
+        }
         *cap = want;
         return p;
     }
     void give(void *p, size_t cap) { std::lock_guard<std::mutex> lk(mu); free_list.emplace_back(p, cap); }
-    ~PinnedPool() { for (auto &e : free_list) cudaFreeHost(e.first); }
+    void release(void *p) {
+        auto it = std::find(pageable.begin(), pageable.end(), p);
+        if (it != pageable.end()) { pageable.erase(it); free(p); } else cudaFreeHost(p);
+    }
+    void trim() { std::lock_guard<std::mutex> lk(mu); for (auto &e : free_list) release(e.first); free_list.clear(); }
+    ~PinnedPool() { for (auto &e : free_list) release(e.first); }
+    std::vector<void *> pageable;  // buffers that came from malloc()
 };
 
 // Same idea for device memory: cudaMalloc/cudaFree of tens of GB per batch would sit inside every
