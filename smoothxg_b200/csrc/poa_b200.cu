@@ -282,7 +282,8 @@ Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int lev
     s.nmax = nmax; s.max_bases = max_bases; s.max_len = max_len; s.max_seq = max_seq;
     const long long edges = std::min<long long>(max_bases + max_seq, level >= 2 ? (1LL << 60) : 3 * nmax);
     s.pool_growth = 8 * edges + 64;
-    long long row_bytes = vecs_per_row * 5 * (may32 ? 32 : 16);
+    const int gen_planes = b->dp.gap_mode == 0 ? 3 : (b->dp.gap_mode == 1 ? 2 : 1);  // stored planes of the generic fill (H + E planes)
+    long long row_bytes = vecs_per_row * gen_planes * (may32 ? 32 : 16);
     if (b->dp.p16_ok) {  // chunked rows of the packed 16-bit fill: whole 256-column chunks, P16_PLANES (H, E1, E2) x 512 B each
         const long long chunk_bytes = (long long)P16_PLANES * P16_CPB;
         long long p16_bytes = (width / 256 + 2) * chunk_bytes;  // worst case: a partial chunk at either end
@@ -294,7 +295,7 @@ Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int lev
         }
         // With match = 1 (smoothxg's default and every -a preset) p16_eligible() holds whenever the int16 test of
         // abpoa_align_simd.c:1293-1302 does, so a block that cannot reach the int32 regime is sized for packed rows alone;
-        // the generic 5-plane rows only matter for int32 rows.  A misjudged block is re-run at the next level.
+        // the generic rows only matter for int32 rows.  A misjudged block is re-run at the next level.
         row_bytes = (level == 0 && !may32) ? p16_bytes : std::max(row_bytes, p16_bytes);
     }
     s.slab_bytes = rows * row_bytes;

@@ -594,8 +594,9 @@ POA_D const S *cell_ptr(const Ws &w, const int4 &pm, int plane, int j) {
     return reinterpret_cast<const S *>(w.slab) + ((long long)pm.x + (long long)plane * nv) * 8 + (j - vb * 8);
 }
 
-// MODE: abpoa_set_gap_mode (abpoa_align.c:87-91) -- 0 convex (five planes H,E1,E2,F1,F2; simd_abpoa_cg_dp
+// MODE: abpoa_set_gap_mode (abpoa_align.c:87-91) -- 0 convex (the reference's five planes H,E1,E2,F1,F2; simd_abpoa_cg_dp
 // abpoa_align_simd.c:935-1074), 1 affine (H,E1,F1; simd_abpoa_ag_dp :817-933), 2 linear (H; simd_abpoa_lg_dp :727-815).
+// Only H and the E planes are stored here (see NPL below).
 // What the affine kernel does differently from "convex with one piece" is restated on purpose: F1 is fed by
 // M + profile alone (:908), the stored E1 is reset where F1 strictly won the cell (:926,:930), local mode does
 // not clamp E1, and the first cell of a row's first vector stores F1 = (M + profile) - oe1 of its own column
@@ -603,7 +604,9 @@ POA_D const S *cell_ptr(const Ws &w, const int4 &pm, int plane, int j) {
 // after the horizontal pass (:813).
 template <int NW, typename S, int MODE>
 POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, long long slab_vecs) {
-    constexpr int NPL = MODE == 0 ? 5 : (MODE == 1 ? 3 : 1);
+    // planes STORED per row: H, E1, E2 (convex) / H, E1 (affine) / H (linear).  The F planes are evaluated but never stored:
+    // no later row reads them, and the traceback recomputes them for one row on its insertion steps (generic_row_f()).
+    constexpr int NPL = MODE == 0 ? 3 : (MODE == 1 ? 2 : 1);
     constexpr int NT = NW * POA_WARP;
     Ws &w = sh.ws;
     const int tid = poa_tid();
@@ -658,8 +661,7 @@ POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, lon
             VecIO<S>::store(p, H);
             if (MODE == 0) {
                 VecIO<S>::store(p + (long long)nv * 8, E1); VecIO<S>::store(p + 2LL * nv * 8, E2);
-                VecIO<S>::store(p + 3LL * nv * 8, F1); VecIO<S>::store(p + 4LL * nv * 8, F2);
-            } else if (MODE == 1) { VecIO<S>::store(p + (long long)nv * 8, E1); VecIO<S>::store(p + 2LL * nv * 8, F1); }
+            } else if (MODE == 1) VecIO<S>::store(p + (long long)nv * 8, E1);
         }
         used = (long long)NPL * nv;
         inband += end0 + 1;
@@ -815,8 +817,8 @@ POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, lon
                 VecIO<S>::store(p, H);
                 if (MODE == 0) {
                     VecIO<S>::store(p + (long long)nv * 8, E1); VecIO<S>::store(p + 2LL * nv * 8, E2);
-                    VecIO<S>::store(p + 3LL * nv * 8, F1); VecIO<S>::store(p + 4LL * nv * 8, F2);
-                } else if (MODE == 1) { VecIO<S>::store(p + (long long)nv * 8, E1); VecIO<S>::store(p + 2LL * nv * 8, F1); }
+                } else if (MODE == 1) VecIO<S>::store(p + (long long)nv * 8, E1);
+                (void)F1; (void)F2;
             }
         }
         if (tid == 0) w.rowmeta[i] = poa_make_int4((int)roff, beg, end, 0);
@@ -866,6 +868,70 @@ POA_DN void fill(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, lon
     sync_block<NW>();
 }
 
+// F1 / F2 of row i at columns j and j - 1 for rows of the generic fill (the traceback's insertion test,
+// abpoa_align_simd.c:420-445 convex, :283-297 affine).  fill<>() evaluates F[j] = (S)(max(carry, max over in-band cells
+// k < j of (Hh[k] - oe + e*(k+1))) - e*j) with Hh = max(M + profile, E1in, E2in) (convex) or M + profile (affine) and
+// carry = f0 + e*beg; this re-evaluates exactly that expression for one row, the cells k dealt to the lanes of the
+// traceback warp (predecessor cells straight from the slab), and a max-reduction in place of the scan.  The affine
+// kernel's first band cell stores (M + profile) - oe1 of its own column (:898,:908).  out = {F1[j], F2[j], F1[j-1], F2[j-1]}
+// (F2 = inf_min for affine; the j - 1 entries are inf_min when j - 1 < beg, as the traceback substitutes).
+template <typename S, int MODE>
+POA_DN void generic_row_f(Shared &sh, const DevParams &P, const uint8_t *q, int i, int j, int *out) {
+    Ws &w = sh.ws;
+    const int lane = poa_tid() % POA_WARP;
+    const int inf_min = inf_min_of<S>(P);
+    const int local = P.local;
+    const int e1 = P.e1, e2 = P.e2, oe1 = P.oe1, oe2 = P.oe2;
+    const int pn = sizeof(S) == 2 ? P.pn16 : P.pn32;
+    const int4 rm = w.rowmeta[i], ri = w.rowinfo[i];
+    const int beg = rm.y;
+    const int *mrow = P.mat + 5 * w.rbase[i];
+    const S *slab = reinterpret_cast<const S *>(w.slab);
+    auto hh_at = [&](int k) {  // Hh of column k: what feeds the horizontal gaps of the cells to its right
+        int M = inf_min, E1 = inf_min, E2 = inf_min;
+        for (int t = 0; t < ri.y; ++t) {  // predecessors (abpoa_align_simd.c:966-1029)
+            const int4 pm = w.rowmeta[w.pool_row[ri.x + t]];
+            const int pvb = pm.y >> 3, pve = pm.z >> 3, pnv = pve - pvb + 1;
+            const S *pH = slab + (long long)pm.x * 8;
+            const int v = k >> 3;
+            if (v >= pvb && v <= pve) {
+                if (MODE != 2) E1 = imax(E1, (int)pH[((long long)(v - pvb) + pnv) * 8 + (k & 7)]);
+                if (MODE == 0) E2 = imax(E2, (int)pH[((long long)(v - pvb) + 2LL * pnv) * 8 + (k & 7)]);
+            }
+            if (k >= 1) {
+                const int vm = (k - 1) >> 3;
+                if (vm >= pvb && vm <= pve) M = imax(M, (int)pH[(long long)(vm - pvb) * 8 + ((k - 1) & 7)]);
+            }
+        }
+        if (local && k == 0) M = imax(M, 0);  // abpoa_align_simd.c:974
+        const int sc = k == 0 ? 0 : mrow[q[k - 1]];
+        const int hm = (S)(M + sc);
+        return MODE == 0 ? imax(imax(hm, E1), E2) : hm;
+    };
+    int g1a = NEG_INF32, g1b = NEG_INF32, g2a = NEG_INF32, g2b = NEG_INF32;  // over k < j (a) and k < j - 1 (b)
+    for (int k = beg + lane; k < j; k += POA_WARP) {
+        const int hh = hh_at(k);
+        const int c1 = hh - oe1 + e1 * (k + 1), c2 = hh - oe2 + e2 * (k + 1);
+        g1a = imax(g1a, c1); g2a = imax(g2a, c2);
+        if (k < j - 1) { g1b = imax(g1b, c1); g2b = imax(g2b, c2); }
+    }
+    g1a = poa_redux_max(g1a); g1b = poa_redux_max(g1b); g2a = poa_redux_max(g2a); g2b = poa_redux_max(g2b);
+    const int f0_1 = imax((int)(S)(inf_min - oe1), (int)(S)(inf_min - e1));
+    const int f0_2 = imax((int)(S)(inf_min - oe2), (int)(S)(inf_min - e2));
+    const int carry1 = MODE == 0 ? f0_1 + e1 * beg : (int)(S)(inf_min - oe1) + e1 * beg;
+    const int carry2 = f0_2 + e2 * beg;
+    int F1j = (S)(imax(carry1, g1a) - e1 * j), F1l = inf_min, F2j = inf_min, F2l = inf_min;
+    if (j - 1 >= beg) F1l = (S)(imax(carry1, g1b) - e1 * (j - 1));
+    if (MODE == 0) {
+        F2j = (S)(imax(carry2, g2a) - e2 * j);
+        if (j - 1 >= beg) F2l = (S)(imax(carry2, g2b) - e2 * (j - 1));
+    } else {  // affine: the row's first band cell
+        if (j == beg) F1j = (beg % pn == 0) ? (int)(S)(hh_at(beg) - oe1) : (int)(S)(inf_min - oe1);
+        if (j - 1 == beg) F1l = (beg % pn == 0) ? (int)(S)(hh_at(beg) - oe1) : (int)(S)(inf_min - oe1);
+    }
+    out[0] = F1j; out[1] = F2j; out[2] = F1l; out[3] = F2l;
+}
+
 #include "poa_fill16.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -897,9 +963,9 @@ POA_D const S *bt_cell(const Ws &w, const int4 &pm, int plane, int j) {
 // ends here (H == 0), 2 = dead end
 // MODE 0 convex (abpoa_align_simd.c:309-458), 1 affine (:196-307: no second gap piece, F1 is plane 2), 2 linear (:116-194:
 // match, then deletion, then insertion, no state)
-// Rows of the packed 16-bit fill (LAY16) hold no F planes: when the walk reaches the insertion test there, bt_step()
-// returns 3 without having changed anything, the warp recomputes {F1[j], F2[j], F1[j-1], F2[j-1]} of the row
-// (p16_row_f(), poa_fill16.cuh) and calls again with them in `fv`.
+// Rows hold no F planes: when the walk reaches the insertion test, bt_step() returns 3 without having changed anything,
+// the warp recomputes {F1[j], F2[j], F1[j-1], F2[j-1]} of the row (p16_row_f() in poa_fill16.cuh for packed rows,
+// generic_row_f() otherwise) and calls again with them in `fv`.
 template <typename S, bool LAY16, int MODE>
 POA_D int bt_step(Shared &sh, const DevParams &P, const uint8_t *q, int &i, int &j, int &id, int &cur_op, const int *fv = nullptr) {
     Ws &w = sh.ws;
@@ -974,22 +1040,20 @@ POA_D int bt_step(Shared &sh, const DevParams &P, const uint8_t *q, int &i, int 
             }
         }
         if (hit == 0 && (cur_op & OP_F)) {
-            if (LAY16 && fv == nullptr) return 3;
+            if (fv == nullptr) return 3;  // no F planes are stored: the caller recomputes them for this row and calls again
             const bool inl = j - 1 >= rm.y;  // left neighbour inside this row's band?
             const int hl = inl ? (int)*bt_cell<S, LAY16>(w, rm, 0, j - 1) : inf_min;
-            constexpr int PF1 = MODE == 0 ? 3 : 2;
-            const int F1j = LAY16 ? fv[0] : (int)*bt_cell<S, LAY16>(w, rm, PF1, j);
-            const int F2j = LAY16 ? fv[1] : (MODE == 0 ? (int)*bt_cell<S, LAY16>(w, rm, 4, j) : inf_min);
+            const int F1j = fv[0], F2j = MODE == 0 ? fv[1] : inf_min;
             if (cur_op & OP_F1) {
                 if (!(cur_op & OP_M) || Hj == F1j) {
-                    const int f1l = LAY16 ? fv[2] : (inl ? (int)*bt_cell<S, LAY16>(w, rm, PF1, j - 1) : inf_min);
+                    const int f1l = fv[2];
                     if ((int)(S)(hl - oe1) == F1j) { cur_op = OP_M | OP_E; hit = 1; }
                     else if ((int)(S)(f1l - e1) == F1j) { cur_op = OP_F1; hit = 1; }
                 }
             }
             if (MODE == 0 && hit == 0 && (cur_op & OP_F2)) {
                 if (!(cur_op & OP_M) || Hj == F2j) {
-                    const int f2l = LAY16 ? fv[3] : (inl ? (int)*bt_cell<S, LAY16>(w, rm, 4, j - 1) : inf_min);
+                    const int f2l = fv[3];
                     if ((int)(S)(hl - oe2) == F2j) { cur_op = OP_M | OP_E; hit = 1; }
                     else if ((int)(S)(f2l - e2) == F2j) { cur_op = OP_F2; hit = 1; }
                 }
@@ -1058,11 +1122,13 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
         }
         poa_sync_warp();
         int rc = sh.bcast[3];
-#if POA_WARP == 32
-        if (LAY16 && rc == 3) {  // insertion test on a row without stored F planes: recompute them (all lanes), then redo the step
+        if (rc == 3) {  // insertion test: the row's F planes are not stored; recompute them (all lanes), then redo the step
             poa_sync_warp();
             int fv[4];
-            p16_row_f(sh, P, qlen, i, j, fv);
+#if POA_WARP == 32
+            if (LAY16) p16_row_f(sh, P, qlen, i, j, fv); else
+#endif
+            generic_row_f<S, MODE>(sh, P, q, i, j, fv);
             if (lane == 0) {
                 int ti = i, tj = j, tid_ = id, top = cur_op;
                 const int rc2 = bt_step<S, LAY16, MODE>(sh, P, q, ti, tj, tid_, top, fv);
@@ -1071,7 +1137,6 @@ POA_DN void backtrack(Shared &sh, const DevParams &P, const uint8_t *q, int qlen
             poa_sync_warp();
             rc = sh.bcast[3];
         }
-#endif
         i = sh.bcast[0]; j = sh.bcast[1]; cur_op = sh.bcast[2]; n = sh.n_cigar;
         poa_sync_warp();
         if (rc == 2) return;
