@@ -44,6 +44,8 @@ def main():
     ora = Oracle()
     emus = {"1 lane": _Checker(C.CDLL(os.path.join(ROOT, "tests/emu/_build/libpoa_emu.so")), "emu_poa_block", "emu_free"),
             "32 lanes": _Checker(C.CDLL(os.path.join(ROOT, "tests/emu/_build/libpoa_emu32.so")), "emu_poa_block", "emu_free")}
+    if os.environ.get("FUZZ_X4"):  # four warps of 32 lanes per POA block: the multi-warp fills, cross-warp barriers included
+        emus["4 x 32 lanes"] = _Checker(C.CDLL(os.path.join(ROOT, "tests/emu/_build/libpoa_emu32x4.so")), "emu_poa_block", "emu_free")
     ref = None
     try:
         from oracle.oracle import RefAbpoa
