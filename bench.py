@@ -41,7 +41,12 @@ WORKLOADS = {
     "10000x32x2kb": (10000, 32, 2000, 0.02),
     "1000x16x1kb": (1000, 16, 1000, 0.02),
     "100x256x8kb": (100, 256, 8000, 0.02),   # BASELINE.json configs[3], deep-block stress (int32 scores once rows > 16 361)
+    # SURVEY 8(d) variants of the headline batch (not headline lines): the -a preset regimes and real-block-like long indels
+    "10000x32x2kb_d0.1": (10000, 32, 2000, 0.001),
+    "10000x32x2kb_d5": (10000, 32, 2000, 0.05),
+    "10000x32x2kb_indel": (10000, 32, 2000, 0.02),   # + one 50-500 bp insertion or deletion per copy with probability 0.3
 }
+EXTRA = {"10000x32x2kb_indel": dict(indel_prob=0.3, indel_len=(50, 500))}
 METRIC = "poa_dp_inband_gcells_per_s"
 UNIT = "Gcells/s"
 
@@ -55,7 +60,7 @@ def gen_batch(workload: str, seed: int, n_blocks: int | None = None):
     if os.path.exists(cache):
         z = np.load(cache)
         return synth.PoaBatch(z["bso"], z["sl"], z["so"], z["ba"], z["wt"])
-    b = synth.make_batch(n_blocks=nb, n_seqs=ns, length=L, divergence=d, seed=seed)
+    b = synth.make_batch(n_blocks=nb, n_seqs=ns, length=L, divergence=d, seed=seed, **EXTRA.get(workload, {}))
     try:
         np.savez(cache, bso=b.block_seq_off, sl=b.seq_len, so=b.seq_off, ba=b.bases, wt=b.weight)
     except OSError:
@@ -183,7 +188,10 @@ def main():
     params_kw = dict(local=False, banded=True, out_cons=True, out_msa=False)
     config = {"workload": f"synthetic {nb} blocks x {ns} seqs x {L} bp per GPU, {div:.0%} divergence, global, adaptive band wb=311 wf=0.03, "
                           f"convex gaps 1,4,6,2,26,1 (BASELINE.json configs[2])" if args.workload == "10000x32x2kb" else
-                          f"synthetic {nb} blocks x {ns} seqs x {L} bp per GPU (BASELINE.json configs[{1 if args.workload == '1000x16x1kb' else 3}])",
+                          (f"synthetic {nb} blocks x {ns} seqs x {L} bp per GPU (BASELINE.json configs[{1 if args.workload == '1000x16x1kb' else 3}])"
+                           if args.workload in ("1000x16x1kb", "100x256x8kb") else
+                           f"synthetic {nb} blocks x {ns} seqs x {L} bp per GPU, {div:.1%} divergence{', long indels' if args.workload in EXTRA else ''} "
+                           f"(SURVEY 8d variant of configs[2], not a headline line)"),
               "blocks_per_gpu": nb, "seqs_per_block": ns, "seq_len": L, "divergence": div,
               "l2": "inputs + per-block workspaces are tens of GB per step, far larger than the 126 MB L2 (no flush needed)",
               "sharding": "static, one 10k-block shard per rank, no data-path collective"}

@@ -17,5 +17,10 @@ for w in 1 2 4; do
   python bench.py --workload 1000x16x1kb --warps $w --steps 3 --warmup 2 --no-cpu --no-e2e > gpurun_out/r02s_config1_w$w.json 2> gpurun_out/r02s_config1_w$w.err
   python -c "import json; d=json.load(open('gpurun_out/r02s_config1_w$w.json')); print('CONFIG1 warps $w', round(d['value'],1), round(d['blocks_per_s'],1))"
 done
+# SURVEY 8(d) variants of the headline batch: the -a preset regimes (0.1 % and 5 % divergence) and long indels
+for w in 10000x32x2kb_d0.1 10000x32x2kb_d5 10000x32x2kb_indel; do
+  python bench.py --workload $w --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02s_$w.json 2> gpurun_out/r02s_$w.err
+  python -c "import json; d=json.load(open('gpurun_out/r02s_$w.json')); print('VARIANT $w', round(d['value'],1), round(d['blocks_per_s'],1), d['engine']['retried_blocks'], round(d['p_bar'],3))"
+done
 python bench.py > gpurun_out/r02s_bench.json 2> gpurun_out/r02s_bench.err
 cat gpurun_out/r02s_bench.json
