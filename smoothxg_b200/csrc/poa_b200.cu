@@ -193,6 +193,8 @@ struct poa_b200_batch {
     std::vector<long long> h_block_seq_off;
     std::vector<long long> h_block_bases;  // total bases per block
     std::vector<int> h_block_maxlen;
+    std::vector<int> h_block_minlen;      // shortest sequence of the block
+    std::vector<long long> h_block_excess;  // sum over sequences of max(0, length - median length): bases that long insertions add
     // device input
     long long *d_block_seq_off = nullptr, *d_seq_off = nullptr;
     int *d_seq_len = nullptr, *d_weight = nullptr, *d_order = nullptr;
@@ -251,11 +253,13 @@ struct Sizing {
 
 // Workspace sizing for a set of blocks.  level 0 = typical (fast path), 1 = 4x, 2 = worst case.
 Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int level, double rows_factor) {
-    long long max_bases = 1, max_len = 1, max_seq = 1;
+    long long max_bases = 1, max_len = 1, max_seq = 1, max_excess = 0, max_spread = 0;
     for (int id : blocks) {
         max_bases = std::max(max_bases, b->h_block_bases[id]);
         max_len = std::max<long long>(max_len, b->h_block_maxlen[id]);
         max_seq = std::max<long long>(max_seq, b->h_block_seq_off[id + 1] - b->h_block_seq_off[id]);
+        max_excess = std::max(max_excess, b->h_block_excess[id]);
+        max_spread = std::max<long long>(max_spread, b->h_block_maxlen[id] - b->h_block_minlen[id]);
     }
     const long long worst_nodes = std::max<long long>(max_bases + 2, max_seq + 2);
     long long nmax, rows;
@@ -266,11 +270,17 @@ Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int lev
         // graph rows per query base: ~1.5 for 32 sequences at 2 % divergence, ~3.6 for 256: deep blocks get a
         // proportionally larger first guess so that they are not all re-run
         double f = rows_factor * (level == 1 ? 4.0 : 1.0) * (1.0 + (double)std::max<long long>(0, max_seq - 32) / 128.0);
-        rows = std::min<long long>(worst_nodes, (long long)(f * max_len) + 64);
+        // Long insertions / deletions (real blocks; the long-indel variant of the benchmark re-ran 23 % of its blocks before
+        // this term existed): an insertion of d bases adds d rows and lengthens its sequence by d, so the bases in excess of
+        // the block's median length estimate the extra rows, and the length spread the extra band width (the band follows
+        // both the longest-path position and the arg-max columns, which an indel of d pulls d columns apart -- on the rows
+        // near it only, hence a fraction of the spread).  Sized from that variant's measured cells per row; overflow still
+        // falls back to the automatic re-run.
+        rows = std::min<long long>(worst_nodes, (long long)(f * max_len) + 64 + max_excess);
         nmax = std::min<long long>(worst_nodes, rows + max_len / 2 + 64);
         if (wb >= 0) {
             long long w = wb + (long long)(b->dp.wf * max_len);
-            width = std::min<long long>(max_len + 1, 2 * w + 1 + (level == 1 ? max_len / 2 : max_len / 8) + 32);
+            width = std::min<long long>(max_len + 1, 2 * w + 1 + (level == 1 ? max_len / 2 : max_len / 8) + 32 + max_spread / 2);
         }
     }
     nmax = std::max<long long>(nmax, 1024);
@@ -290,7 +300,7 @@ Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int lev
         if (level == 0) {
             // first guess: a band-wide row touches band/256 + 1 chunks on average (measured 3.46 for 743-column bands,
             // whose rows are clipped at the matrix edges); 12 % headroom, overflow is retried at the next level
-            const long long band = wb >= 0 ? std::min<long long>(max_len + 1, 2 * (wb + (long long)(b->dp.wf * max_len)) + 1) : max_len + 1;
+            const long long band = wb >= 0 ? std::min<long long>(max_len + 1, 2 * (wb + (long long)(b->dp.wf * max_len)) + 1 + max_spread / 3) : max_len + 1;
             p16_bytes = (long long)((band / 256.0 + 1.0) * 1.12 * (double)chunk_bytes);
         }
         // With match = 1 (smoothxg's default and every -a preset) p16_eligible() holds whenever the int16 test of
@@ -525,16 +535,25 @@ int poa_b200_batch_upload(poa_b200_engine_t *eng, const poa_b200_params_t *param
     b->h_block_seq_off.assign(block_seq_off, block_seq_off + (n_blocks ? n_blocks + 1 : 0));
     if (n_blocks == 0) b->h_block_seq_off.assign(1, 0);
     b->h_block_bases.resize((size_t)n_blocks); b->h_block_maxlen.resize((size_t)n_blocks);
+    b->h_block_minlen.resize((size_t)n_blocks); b->h_block_excess.resize((size_t)n_blocks);
+    std::vector<int> lens_tmp;
     for (int64_t i = 0; i < n_blocks; ++i) {
         int64_t s0 = block_seq_off[i], s1 = block_seq_off[i + 1];
         if (s1 < s0) { delete b; return set_err(POA_B200_EARG, "block_seq_off not monotone"); }
-        int ml = 0;
+        int ml = 0, mn = s1 > s0 ? INT32_MAX : 0;
         for (int64_t s = s0; s < s1; ++s) {
             if (seq_len[s] < 0 || seq_off[s + 1] - seq_off[s] != seq_len[s]) { delete b; return set_err(POA_B200_EARG, "seq_off/seq_len mismatch"); }
-            ml = std::max(ml, seq_len[s]);
+            ml = std::max(ml, seq_len[s]); mn = std::min(mn, seq_len[s]);
+        }
+        long long excess = 0;
+        if (s1 - s0 > 1) {
+            lens_tmp.assign(seq_len + s0, seq_len + s1);
+            std::nth_element(lens_tmp.begin(), lens_tmp.begin() + (long)(lens_tmp.size() / 2), lens_tmp.end());
+            const int med = lens_tmp[lens_tmp.size() / 2];
+            for (int64_t s = s0; s < s1; ++s) excess += std::max(0, seq_len[s] - med);
         }
         b->h_block_bases[(size_t)i] = seq_off[s1] - seq_off[s0];
-        b->h_block_maxlen[(size_t)i] = ml;
+        b->h_block_maxlen[(size_t)i] = ml; b->h_block_minlen[(size_t)i] = mn; b->h_block_excess[(size_t)i] = excess;
         if (b->h_block_bases[(size_t)i] > (1LL << 30)) { delete b; return set_err(POA_B200_EARG, "block too large"); }
     }
     auto fail = [&](int code) { free_batch_device(b); delete b; return code; };
