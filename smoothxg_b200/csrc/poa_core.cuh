@@ -586,8 +586,9 @@ POA_D int inf_min_of(const DevParams &P) {  // abpoa_align_simd.c:1295 / :1299
 }
 
 // Row r of the current alignment is stored band-only: rowmeta[r] = {first vector index in the slab,
-// beg, end, 0}; five planes (H, E1, E2, F1, F2) of nv = (end>>3)-(beg>>3)+1 vectors each follow one
-// another.  Cells of those vectors that lie outside [beg,end] hold inf_min in every plane.
+// beg, end, 0}; the stored planes (H, E1, E2 for convex gaps; H, E1 affine; H linear -- never the F planes) of
+// nv = (end>>3)-(beg>>3)+1 vectors each follow one another.  Cells of those vectors that lie outside [beg,end] hold
+// inf_min in every plane.
 template <typename S>
 POA_D const S *cell_ptr(const Ws &w, const int4 &pm, int plane, int j) {
     int vb = pm.y >> 3, nv = (pm.z >> 3) - vb + 1;
