@@ -118,6 +118,22 @@ def test_abi_exports_and_host_entry_points():
     assert adaptive.pair_offsets(fb, 11).tolist() == [0, 3, 3, 3, 6]
 
 
+def test_argument_errors_are_reported_not_fatal():
+    """The reference exits the process on errors of this path; the ABI returns MASH_B200_EARG with a message."""
+    from smoothxg_b200 import adaptive, engine
+    lib = engine.load_library()
+    adaptive.pair_offsets(adaptive.flatten([["A" * 200]]))  # binds the argtypes
+    fb = adaptive.flatten([["ACGT" * 100, "ACGT" * 90]])
+    thr = np.zeros(1, dtype=np.float32)
+    args = lambda k, nb=1, bases=fb.bases.ctypes.data: (0, k, nb, fb.block_seq_off.ctypes.data, fb.seq_len.ctypes.data, fb.seq_off.ctypes.data,
+                                                        bases, thr.ctypes.data, None, None, None, None)
+    for bad in (args(0), args(33), args(17, -1), args(17, 1, None)):
+        assert lib.mash_b200_block_identity(*bad) == 7
+        assert lib.mash_b200_last_error()
+    st = adaptive.MashStats()
+    assert lib.mash_b200_block_identity(0, 17, 0, None, None, None, None, None, None, None, None, C.byref(st)) == 0 and st.n_pairs == 0  # empty batch
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
