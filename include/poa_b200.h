@@ -107,7 +107,7 @@ typedef struct poa_b200_block_view {
 } poa_b200_block_view_t;
 
 typedef struct poa_b200_stats {
-    double  kernel_ms;       /* device time of the POA kernel(s) of the last launch (CUDA events on the launch stream) */
+    double  kernel_ms;       /* device time of the batch's POA kernel launches, re-runs of overflowed blocks included (CUDA events on the launch stream) */
     double  h2d_ms, d2h_ms;
     int64_t inband_cells;    /* summed over blocks */
     int64_t edge_row_cells;  /* sum over evaluated rows of (predecessor count x band width): p-bar = this / inband_cells */

@@ -376,9 +376,9 @@ int run_launch(poa_b200_batch *b, const std::vector<int> &blocks, int level, cud
     DevOut O;
     O.hdr = b->d_hdr; O.arena = ar.d; O.arena_used = b->d_arena_used; O.arena_cap = ar.cap;
     O.phase = b->d_phase; O.counter = b->d_counter;
-    if (record_events) CU(cudaEventRecord(b->ev0, st));
+    CU(cudaEventRecord(b->ev0, st));  // every launch is timed: re-runs of overflowed blocks count towards stats.kernel_ms
     CU(launch_kernel(nw, (int)n_ctas, st, b->dp, B, L, b->d_ws, O));
-    if (record_events) CU(cudaEventRecord(b->ev1, st));
+    CU(cudaEventRecord(b->ev1, st));
     b->n_pending = (int)order.size();
     b->stats.kernel_launches += 1;
     if (record_events) { b->stats.n_ctas = (int)n_ctas; b->stats.warps_per_block = nw; b->stats.workspace_bytes = need; }
@@ -413,10 +413,10 @@ int finish_locked(poa_b200_batch *b, cudaStream_t st) {
         std::vector<int> f_ws, f_ar;
         int rc = collect(b, blocks, st, f_ws, f_ar);
         if (rc) return rc;
-        if (round == 0) {
+        {   // collect() has synchronised the stream: ev0 / ev1 bracket the launch just collected (main launch or a re-run)
             float ms = 0;
             CU(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
-            b->stats.kernel_ms = ms;
+            b->stats.kernel_ms = round == 0 ? ms : b->stats.kernel_ms + ms;
         }
         if (f_ws.empty() && f_ar.empty()) { blocks.clear(); break; }
         if (!f_ws.empty()) level = std::min(level + 1, 2);
