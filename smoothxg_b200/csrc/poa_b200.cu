@@ -769,27 +769,38 @@ int poa_b200_block_graph(const poa_b200_block_view_t *v, int32_t padding_len, in
     for (int i = 0; i < n; ++i) { in_off[(size_t)i + 1] = in_off[(size_t)i] + v->in_n[i]; out_off[(size_t)i + 1] = out_off[(size_t)i] + v->out_n[i]; }
     // read paths with the padding trimmed (:2520-2531), node coverage
     std::vector<char> covered((size_t)n, 0);
-    int64_t poff = 0;
-    for (int i = 0; i < ns; ++i) {
-        const int len = v->path_len[i];
-        for (int j = padding_len; j < len - padding_len; ++j) {
-            const int id = v->path_node[poff + j];
-            g->path_node.push_back(id - 1);
-            covered[(size_t)id] = 1;
+    {
+        int64_t keep = 0, at = 0;
+        for (int i = 0; i < ns; ++i) keep += std::max(0, v->path_len[i] - 2 * padding_len);
+        g->path_node.reserve((size_t)keep + (size_t)std::max(v->cons_len, 0));
+        g->path_off.reserve((size_t)ns + 2);
+        for (int i = 0; i < ns; ++i) {
+            const int len = v->path_len[i];
+            for (int j = padding_len; j < len - padding_len; ++j) {
+                const int id = v->path_node[at + j];
+                g->path_node.push_back(id - 1);
+                covered[(size_t)id] = 1;
+            }
+            g->path_off.push_back((int64_t)g->path_node.size());
+            at += len;
         }
-        g->path_off.push_back((int64_t)g->path_node.size());
-        poff += len;
     }
     if (include_consensus) {  // :2534-2549: only nodes some read still covers
         for (int i = 0; i < v->cons_len; ++i) { const int id = v->cons_node[i]; if (covered[(size_t)id]) g->path_node.push_back(id - 1); }
         g->path_off.push_back((int64_t)g->path_node.size());
     }
-    // edges some path walks (either direction walks the same edge)
-    std::vector<std::pair<int, int>> used;
+    // edges some path walks: one flag per out-edge, set by looking the step's target up in its source's (short) out list.
+    // Consecutive consensus nodes need not be adjacent once uncovered nodes were dropped: such a pair matches no edge.
+    std::vector<char> out_used((size_t)out_off[(size_t)n], 0);
+    auto out_slot = [&](int a, int b) -> int64_t {  // abPOA ids
+        for (int64_t k = out_off[(size_t)a]; k < out_off[(size_t)a + 1]; ++k) if (v->out_id[k] == b) return k;
+        return -1;
+    };
     for (size_t p = 0; p + 1 < g->path_off.size(); ++p)
-        for (int64_t k = g->path_off[p]; k + 1 < g->path_off[p + 1]; ++k) used.emplace_back(g->path_node[(size_t)k], g->path_node[(size_t)k + 1]);
-    std::sort(used.begin(), used.end());
-    used.erase(std::unique(used.begin(), used.end()), used.end());
+        for (int64_t k = g->path_off[p]; k + 1 < g->path_off[p + 1]; ++k) {
+            const int64_t e = out_slot(g->path_node[(size_t)k] + 1, g->path_node[(size_t)k + 1] + 1);
+            if (e >= 0) out_used[(size_t)e] = 1;
+        }
     // Kahn walk from the source in out_id order = node / edge creation order of build_odgi_abPOA (:2463-2511)
     static const char code2base[6] = {'A', 'C', 'G', 'T', 'N', '-'};
     std::vector<int> indeg((size_t)n), queue; queue.reserve((size_t)n);
@@ -807,7 +818,8 @@ int poa_b200_block_graph(const poa_b200_block_view_t *v, int32_t padding_len, in
             for (int64_t k = in_off[(size_t)cur]; k < in_off[(size_t)cur + 1]; ++k) {
                 const int pre = v->in_id[k];
                 if (pre == 0) continue;
-                if (std::binary_search(used.begin(), used.end(), std::make_pair(pre - 1, cur - 1))) { g->edge_from.push_back(pre - 1); g->edge_to.push_back(cur - 1); }
+                const int64_t e = out_slot(pre, cur);
+                if (e >= 0 && out_used[(size_t)e]) { g->edge_from.push_back(pre - 1); g->edge_to.push_back(cur - 1); }
             }
         }
         for (int64_t k = out_off[(size_t)cur]; k < out_off[(size_t)cur + 1]; ++k) {
