@@ -485,7 +485,16 @@ void poa_b200_encode_bases(const char *ascii, int64_t n, uint8_t *codes) {
             t['T'] = t['t'] = t['U'] = t['u'] = 3;
         }
     } tab;
-    for (int64_t i = 0; i < n; ++i) codes[i] = tab.t[(unsigned char)ascii[i]];
+    const uint8_t *t = tab.t;  // local copy of the pointer: no guard check of the function-local static inside the loop
+    int64_t i = 0;
+    for (; i + 8 <= n; i += 8) {  // eight independent lookups per iteration, one 8-byte store
+        uint64_t w;
+        memcpy(&w, ascii + i, 8);
+        const uint64_t o = (uint64_t)t[w & 0xff] | (uint64_t)t[(w >> 8) & 0xff] << 8 | (uint64_t)t[(w >> 16) & 0xff] << 16 | (uint64_t)t[(w >> 24) & 0xff] << 24
+                         | (uint64_t)t[(w >> 32) & 0xff] << 32 | (uint64_t)t[(w >> 40) & 0xff] << 40 | (uint64_t)t[(w >> 48) & 0xff] << 48 | (uint64_t)t[w >> 56] << 56;
+        memcpy(codes + i, &o, 8);
+    }
+    for (; i < n; ++i) codes[i] = t[(unsigned char)ascii[i]];
 }
 
 int poa_b200_engine_create(int device, const poa_b200_engine_opts_t *opts, poa_b200_engine_t **out) {
