@@ -55,7 +55,7 @@ def main():
     t0, n_ref, n_unsup = time.time(), 0, 0
     for c in range(n_cases):
         p = random_params(rng)
-        L = int(rng.integers(20, 700))
+        L = int(rng.integers(20, int(os.environ.get("FUZZ_LMAX", "700"))))  # FUZZ_LMAX=2500: rows of several chunks with a real band
         batch = synth.make_batch(n_blocks=1, n_seqs=int(rng.integers(2, 9)), length=L, divergence=float(rng.choice([0.0, 0.02, 0.1, 0.3])),
                                  seed=int(rng.integers(1 << 30)), indel_prob=float(rng.choice([0.0, 0.3, 0.8])), indel_len=(5, max(6, L // 3)),
                                  n_frac=float(rng.choice([0.0, 0.0, 0.05])), dup_weights=bool(rng.integers(0, 2)))
