@@ -69,7 +69,10 @@ typedef struct poa_b200_engine_opts {
     int32_t warps_per_block;   /* CUDA warps cooperating on one POA block: 1, 2, 4 or 8; 0 = choose from the batch size */
     int32_t ctas_per_sm;       /* resident POA blocks per SM; 0 = occupancy-derived default */
     int32_t emit_cigar;        /* 1: also return per-sequence graph cigars (debug / parity instrumentation) */
-    int32_t flags;             /* bit 0: disable the packed 16-bit fill (A/B testing; results are identical either way) */
+    int32_t flags;             /* bit 0: disable the packed 16-bit fill (A/B testing; results are identical either way);
+                                * bits 4-5: SIMD width of the abPOA build whose vector-granular band-start rounding is reproduced
+                                * (deps/abPOA/src/abpoa_align_simd.c:949-960): 0 = AVX-512BW (32 int16 lanes; the default, and what the
+                                * golden vectors were pinned with), 1 = AVX2 (16), 2 = SSE4.1 / NEON (8) */
     double  slab_rows_factor;  /* DP workspace rows per query base before a retry is needed; 0 = default (1.7) */
     int64_t device_mem_budget; /* bytes of HBM the engine may use for workspaces; 0 = 70 % of free memory */
 } poa_b200_engine_opts_t;
@@ -131,10 +134,14 @@ void poa_b200_encode_bases(const char *ascii, int64_t n, uint8_t *codes);
 
 int  poa_b200_engine_create(int device, const poa_b200_engine_opts_t *opts, poa_b200_engine_t **out);
 void poa_b200_engine_destroy(poa_b200_engine_t *eng);
+/* Give the engine's pooled device and pinned host buffers back to the driver (they are otherwise kept between batches so
+ * that steady-state calls do no cudaMalloc / cudaMallocHost).  Call it before another user of the same GPU needs the memory. */
+int  poa_b200_engine_trim(poa_b200_engine_t *eng);
 
 /* One-shot, host buffers in / host result out (what the smoothxg loop body calls once per batch):
  *   block_seq_off[n_blocks+1] -> index into seq_len/weight;  seq_off[n_seqs+1] -> index into bases;
- *   bases = codes 0..4 (ab_char26_table encoding, deps/abPOA/src/abpoa_seq.c:15-32);
+ *   bases = codes 0..4 (ab_char26_table encoding, deps/abPOA/src/abpoa_seq.c:15-32); a code above 4 -- which that
+ *   table cannot produce -- is treated as 4 (N), clamped on the device right after the upload;
  *   weight[n_seqs] = dedup multiplicity of each sequence (src/smooth.cpp:332-336). */
 int  poa_b200_run_batch(poa_b200_engine_t *eng, const poa_b200_params_t *params, int64_t n_blocks,
                         const int64_t *block_seq_off, const int32_t *seq_len, const int64_t *seq_off,
@@ -166,6 +173,11 @@ int  poa_b200_batch_device_result(poa_b200_batch_t *batch, int32_t arena_idx, co
 /* Build a host result from header and arena words (copied) as produced on any GPU. */
 int  poa_b200_result_from_parts(int64_t n_blocks, const int32_t *hdr, const int32_t *arena, int64_t arena_words,
                                 poa_b200_result_t **result);
+/* Same, but the arena words are still in device memory on `eng`'s GPU (rank 0 after the NCCL gather of every rank's
+ * bodies): ONE device-to-host copy on `stream` (NULL = the engine's) straight into the result's pooled pinned buffer, no
+ * second host copy.  hdr is a host array with body offsets already rebased onto d_arena. */
+int  poa_b200_result_from_device_parts(poa_b200_engine_t *eng, int64_t n_blocks, const int32_t *hdr, const int32_t *d_arena,
+                                       int64_t arena_words, void *stream, poa_b200_result_t **result);
 void poa_b200_batch_free(poa_b200_batch_t *batch);
 int  poa_b200_batch_stats(const poa_b200_batch_t *batch, poa_b200_stats_t *stats);
 
@@ -197,6 +209,11 @@ void poa_b200_graph_free(poa_b200_graph_t *graph);
 
 int64_t poa_b200_result_n_blocks(const poa_b200_result_t *res);
 int  poa_b200_result_block(const poa_b200_result_t *res, int64_t block, poa_b200_block_view_t *view);
+/* Checksum of one finished block's graph: FNV-1a 64 over node_n (int32), then per node its base (one byte), out ids and
+ * out weights (int32 each, final order) -- the same byte stream a checker can hash straight from abPOA's abpoa_graph_t
+ * (node_n, node[i].base, node[i].out_id, node[i].out_edge_weight; deps/abPOA/include/abpoa.h:98-118), so that large samples
+ * can be compared block by block without materialising either graph in the harness.  Pure host code. */
+int  poa_b200_result_block_hash(const poa_b200_result_t *res, int64_t block, uint64_t *hash);
 int  poa_b200_result_stats(const poa_b200_result_t *res, poa_b200_stats_t *stats);
 void poa_b200_result_free(poa_b200_result_t *res);
 

@@ -53,6 +53,21 @@ __global__ void POA_KERNEL_BOUNDS poa_b200_block_kernel(const __grid_constant__ 
     }
 }
 
+// Base codes index the 5x5 score matrix on the device: anything above 4 (the reference's own encoder cannot produce it,
+// abpoa_seq.c:15-32) is clamped to 4 = N once, right after the upload, instead of being trusted in every kernel.
+__global__ void poa_b200_sanitize_bases_kernel(uint8_t *bases, long long n) {
+    const long long n16 = n / 16;
+    uint4 *v = reinterpret_cast<uint4 *>(bases);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+        uint4 u = v[i];
+        const uint4 o = u;
+        u.x = __vminu4(u.x, 0x04040404u); u.y = __vminu4(u.y, 0x04040404u); u.z = __vminu4(u.z, 0x04040404u); u.w = __vminu4(u.w, 0x04040404u);
+        if (u.x != o.x || u.y != o.y || u.z != o.z || u.w != o.w) v[i] = u;
+    }
+    for (long long i = n16 * 16 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        if (bases[i] > 4) bases[i] = 4;
+}
+
 namespace poa {
 thread_local std::string g_last_error;
 int set_err(int code, const std::string &msg) { g_last_error = msg; return code; }
@@ -205,6 +220,7 @@ struct poa_b200_batch {
     std::vector<Arena> arenas;
     std::vector<int> arena_of;
     std::vector<int> h_hdr;
+    std::vector<long long> need_words;  // per block: body words the kernel reported when the block overflowed an arena (0 = unknown)
     // workspace
     char *d_ws = nullptr;
     char *d_inputs = nullptr;  // one pooled allocation holding every d_* array above
@@ -214,6 +230,7 @@ struct poa_b200_batch {
     int n_ctas = 0, nw = 1;
     int n_pending = 0;  // blocks in the launch in flight
     bool launched = false, finished = false;
+    std::string retry_error;  // why a re-run of overflowed blocks could not be launched (those blocks keep their error status)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     poa_b200_stats_t stats{};
 };
@@ -251,7 +268,9 @@ struct Sizing {
     long long nmax, max_bases, max_len, max_seq, pool_growth, slab_bytes;
 };
 
-// Workspace sizing for a set of blocks.  level 0 = typical (fast path), 1 = 4x, 2 = worst case.
+// Workspace sizing for a set of blocks.  level 0 = typical (fast path), 1 = 4x rows, 2 = 16x rows at full width,
+// 3 (LEVEL_WORST) = worst case (one row per input base, full width).
+constexpr int LEVEL_WORST = 3;
 Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int level, double rows_factor) {
     long long max_bases = 1, max_len = 1, max_seq = 1, max_excess = 0, max_spread = 0;
     for (int id : blocks) {
@@ -265,11 +284,11 @@ Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int lev
     long long nmax, rows;
     const int wb = b->dp.local ? -1 : b->dp.wb;
     long long width = max_len + 1;
-    if (level >= 2) { nmax = worst_nodes; rows = worst_nodes; }
+    if (level >= LEVEL_WORST) { nmax = worst_nodes; rows = worst_nodes; }
     else {
         // graph rows per query base: ~1.5 for 32 sequences at 2 % divergence, ~3.6 for 256: deep blocks get a
         // proportionally larger first guess so that they are not all re-run
-        double f = rows_factor * (level == 1 ? 4.0 : 1.0) * (1.0 + (double)std::max<long long>(0, max_seq - 32) / 128.0);
+        double f = rows_factor * (level == 1 ? 4.0 : (level == 2 ? 16.0 : 1.0)) * (1.0 + (double)std::max<long long>(0, max_seq - 32) / 128.0);
         // Long insertions / deletions (real blocks; the long-indel variant of the benchmark re-ran 23 % of its blocks before
         // this term existed): an insertion of d bases adds d rows and lengthens its sequence by d, so the bases in excess of
         // the block's median length estimate the extra rows, and the length spread the extra band width (the band follows
@@ -280,7 +299,7 @@ Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int lev
         nmax = std::min<long long>(worst_nodes, rows + max_len / 2 + 64);
         if (wb >= 0) {
             long long w = wb + (long long)(b->dp.wf * max_len);
-            width = std::min<long long>(max_len + 1, 2 * w + 1 + (level == 1 ? max_len / 2 : max_len / 8) + 32 + max_spread / 2);
+            width = level >= 2 ? max_len + 1 : std::min<long long>(max_len + 1, 2 * w + 1 + (level == 1 ? max_len / 2 : max_len / 8) + 32 + max_spread / 2);
         }
     }
     nmax = std::max<long long>(nmax, 1024);
@@ -290,7 +309,7 @@ Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int lev
     const bool may32 = std::max<long long>(max_len * b->dp.match, len * b->dp.e1 + b->dp.o1) > (long long)INT16_MAX - b->dp.min_mis - b->dp.oe1 - b->dp.oe2;
     Sizing s;
     s.nmax = nmax; s.max_bases = max_bases; s.max_len = max_len; s.max_seq = max_seq;
-    const long long edges = std::min<long long>(max_bases + max_seq, level >= 2 ? (1LL << 60) : 3 * nmax);
+    const long long edges = std::min<long long>(max_bases + max_seq, level >= LEVEL_WORST ? (1LL << 60) : 3 * nmax);
     s.pool_growth = 8 * edges + 64;
     const int gen_planes = b->dp.gap_mode == 0 ? 3 : (b->dp.gap_mode == 1 ? 2 : 1);  // stored planes of the generic fill (H + E planes)
     long long row_bytes = vecs_per_row * gen_planes * (may32 ? 32 : 16);
@@ -334,6 +353,7 @@ int run_launch(poa_b200_batch *b, const std::vector<int> &blocks, int level, cud
     CU(cudaMemGetInfo(&free_b, &total_b));
     long long budget = eng->opts.device_mem_budget > 0 ? eng->opts.device_mem_budget
                      : (long long)((double)(free_b + (size_t)b->ws_bytes + eng->dev_pool.pooled_bytes()) * 0.70);
+    if (L.stride > budget) return set_err(POA_B200_ENOMEM, "one block's workspace exceeds the device memory budget");
     n_ctas = std::max<long long>(1, std::min<long long>(n_ctas, budget / std::max<long long>(L.stride, 1)));
     const long long need = n_ctas * L.stride;
     if (need > b->ws_bytes) {
@@ -348,7 +368,8 @@ int run_launch(poa_b200_batch *b, const std::vector<int> &blocks, int level, cud
     long long est_words = 0;
     for (int id : blocks) {
         long long tb = b->h_block_bases[id], ns = b->h_block_seq_off[id + 1] - b->h_block_seq_off[id], ml = b->h_block_maxlen[id];
-        long long n_est = level >= 2 ? tb + 2 : std::min<long long>(tb + 2, (level == 1 ? 8 : 3) * ml + 64);
+        if (b->need_words[(size_t)id] > 0) { est_words += b->need_words[(size_t)id]; continue; }  // overflowed an arena before: the kernel reported its exact size
+        long long n_est = level >= LEVEL_WORST ? tb + 2 : std::min<long long>(tb + 2, (level == 0 ? 3 : (level == 1 ? 8 : 24)) * ml + 64);
         long long wds = 12 * n_est + tb + 3 * ns + 64;
         if (b->dp.out_msa) wds += (ns + 1) * n_est / 4 + 8;
         if (b->dp.emit_cigar) wds += 2 * (tb + ns * n_est);
@@ -398,9 +419,22 @@ int collect(poa_b200_batch *b, const std::vector<int> &blocks, cudaStream_t st, 
         int st_ = b->h_hdr[(size_t)id * HDR_WORDS + H_STATUS];
         if (st_ == ST_OK) b->arena_of[id] = ai;
         else if (st_ == ST_ESLAB) failed_ws.push_back(id);
-        else if (st_ == ST_EARENA) failed_arena.push_back(id);
+        else if (st_ == ST_EARENA) {
+            failed_arena.push_back(id);
+            const int *h = &b->h_hdr[(size_t)id * HDR_WORDS];
+            b->need_words[(size_t)id] = (long long)((unsigned long long)(unsigned)h[H_OFF_LO] | ((unsigned long long)(unsigned)h[H_OFF_HI] << 32));
+        }
     }
     return POA_B200_OK;
+}
+
+// one past the last arena word of a finished block's body, from its header
+unsigned long long block_body_end(const int *h) {
+    const unsigned long long off = (unsigned long long)(unsigned)h[H_OFF_LO] | ((unsigned long long)(unsigned)h[H_OFF_HI] << 32);
+    const unsigned long long words = 4ull * (unsigned)h[H_N_NODE] + 2ull * (unsigned)h[H_IN_TOT] + 2ull * (unsigned)h[H_OUT_TOT] + (unsigned)h[H_ALN_TOT]
+                                   + 3ull * (unsigned)h[H_N_SEQ] + (unsigned)h[H_PATH_TOT] + (unsigned)(h[H_CONS_LEN] > 0 ? h[H_CONS_LEN] : 0) + 2ull * (unsigned)h[H_CIG_TOT]
+                                   + ((unsigned long long)(unsigned)h[H_MSA_ROWS] * (unsigned)(h[H_MSA_LEN] > 0 ? h[H_MSA_LEN] : 0) + 3) / 4;
+    return off + words;
 }
 
 int finish_locked(poa_b200_batch *b, cudaStream_t st) {
@@ -409,7 +443,7 @@ int finish_locked(poa_b200_batch *b, cudaStream_t st) {
     std::vector<int> blocks((size_t)b->n_blocks);
     for (int64_t i = 0; i < b->n_blocks; ++i) blocks[(size_t)i] = (int)i;
     int level = 0;
-    for (int round = 0; round < 6 && !blocks.empty(); ++round) {
+    for (int round = 0; round < 8 && !blocks.empty(); ++round) {
         std::vector<int> f_ws, f_ar;
         int rc = collect(b, blocks, st, f_ws, f_ar);
         if (rc) return rc;
@@ -419,15 +453,23 @@ int finish_locked(poa_b200_batch *b, cudaStream_t st) {
             b->stats.kernel_ms = round == 0 ? ms : b->stats.kernel_ms + ms;
         }
         if (f_ws.empty() && f_ar.empty()) { blocks.clear(); break; }
-        if (!f_ws.empty()) level = std::min(level + 1, 2);
+        // workspace overflow: next sizing level.  Arena overflow alone keeps the workspace level: the re-run's arena is sized
+        // from the exact body sizes the kernel wrote into the failed blocks' headers (need_words).
+        if (!f_ws.empty()) { if (level == LEVEL_WORST) break; ++level; }
         std::vector<int> again(f_ws);
         again.insert(again.end(), f_ar.begin(), f_ar.end());
         std::sort(again.begin(), again.end());
         b->stats.retried_blocks += (int)again.size();
-        // arena overflow: the next launch gets its own arena sized from the next level's estimate
-        rc = run_launch(b, again, f_ws.empty() ? std::max(level, 1) : level, st, false);
-        if (rc) return rc;
+        rc = run_launch(b, again, level, st, false);
+        while (rc == POA_B200_ENOMEM && !f_ws.empty() && level < LEVEL_WORST) rc = run_launch(b, again, ++level, st, false);  // a huge level-2 slab may not fit where the worst case does not either; try anyway
         blocks = again;
+        if (rc) {
+            // The re-run could not be launched (out of device memory, CUDA error).  Blocks that did finish keep their
+            // results: the remaining ones stay marked ESLAB / EARENA and the call reports POA_B200_EBLOCK.
+            b->retry_error = poa::g_last_error;
+            blocks.clear();
+            break;
+        }
     }
     if (!blocks.empty()) {
         std::vector<int> f_ws, f_ar;
@@ -516,6 +558,15 @@ int poa_b200_engine_create(int device, const poa_b200_engine_opts_t *opts, poa_b
     return POA_B200_OK;
 }
 
+int poa_b200_engine_trim(poa_b200_engine_t *eng) {
+    if (!eng) return set_err(POA_B200_EARG, "NULL engine");
+    std::lock_guard<std::mutex> lk(eng->mu);
+    CU(cudaSetDevice(eng->device));
+    eng->dev_pool.trim();
+    eng->pinned->trim();
+    return POA_B200_OK;
+}
+
 void poa_b200_engine_destroy(poa_b200_engine_t *eng) {
     if (!eng) return;
     cudaSetDevice(eng->device);
@@ -528,6 +579,8 @@ int poa_b200_batch_upload(poa_b200_engine_t *eng, const poa_b200_params_t *param
                           const uint8_t *bases, const int32_t *weight, poa_b200_batch_t **out) {
     if (!eng || !params || !out || n_blocks < 0 || (n_blocks > 0 && (!block_seq_off || !seq_off)))
         return set_err(POA_B200_EARG, "NULL argument");
+    if (n_blocks > 0 && block_seq_off[n_blocks] > 0 && (!seq_len || !weight)) return set_err(POA_B200_EARG, "seq_len / weight is NULL");
+    if (n_blocks > 0 && block_seq_off[n_blocks] > 0 && seq_off[block_seq_off[n_blocks]] > 0 && !bases) return set_err(POA_B200_EARG, "bases is NULL");
     *out = nullptr;
     int rc = check_params(*params);
     if (rc) return rc;
@@ -569,7 +622,11 @@ int poa_b200_batch_upload(poa_b200_engine_t *eng, const poa_b200_params_t *param
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(POA_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); return fail(POA_B200_ECUDA); } } while (0)
     cudaStream_t st = eng->stream;
     CUB(cudaEventCreate(&b->ev0)); CUB(cudaEventCreate(&b->ev1));
-    cudaEvent_t h0, h1;
+    cudaEvent_t h0 = nullptr, h1 = nullptr;
+    auto fail0 = fail;
+    auto fail_ev = [&](int code) { if (h0) cudaEventDestroy(h0); if (h1) cudaEventDestroy(h1); return fail0(code); };
+#undef CUB
+#define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(POA_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); return fail_ev(POA_B200_ECUDA); } } while (0)
     CUB(cudaEventCreate(&h0)); CUB(cudaEventCreate(&h1));
     {
         // every per-batch input / bookkeeping array is carved from ONE pooled device allocation: cudaMalloc / cudaFree per
@@ -582,7 +639,7 @@ int poa_b200_batch_upload(poa_b200_engine_t *eng, const poa_b200_params_t *param
         const size_t o_or = carve(sizeof(int) * nb1), o_hd = carve(sizeof(int) * HDR_WORDS * nb1), o_ct = carve(sizeof(int));
         const size_t o_au = carve(sizeof(unsigned long long)), o_ph = carve(sizeof(unsigned long long) * PH_N);
         b->d_inputs = (char *)eng->dev_pool.take(off, &b->inputs_cap);
-        if (!b->d_inputs) { set_err(POA_B200_ENOMEM, "input cudaMalloc failed"); return fail(POA_B200_ENOMEM); }
+        if (!b->d_inputs) { set_err(POA_B200_ENOMEM, "input cudaMalloc failed"); return fail_ev(POA_B200_ENOMEM); }
         char *base = b->d_inputs;
         b->d_block_seq_off = (long long *)(base + o_bso); b->d_seq_off = (long long *)(base + o_so);
         b->d_seq_len = (int *)(base + o_sl); b->d_weight = (int *)(base + o_wt); b->d_bases = (uint8_t *)(base + o_ba);
@@ -599,7 +656,11 @@ int poa_b200_batch_upload(poa_b200_engine_t *eng, const poa_b200_params_t *param
         CUB(cudaMemcpyAsync(b->d_seq_len, seq_len, sizeof(int) * (size_t)n_seqs, cudaMemcpyHostToDevice, st));
         CUB(cudaMemcpyAsync(b->d_weight, weight, sizeof(int) * (size_t)n_seqs, cudaMemcpyHostToDevice, st));
     }
-    if (n_bases) CUB(cudaMemcpyAsync(b->d_bases, bases, (size_t)n_bases, cudaMemcpyHostToDevice, st));
+    if (n_bases) {
+        CUB(cudaMemcpyAsync(b->d_bases, bases, (size_t)n_bases, cudaMemcpyHostToDevice, st));
+        poa_b200_sanitize_bases_kernel<<<std::max(1, eng->n_sm * 4), 256, 0, st>>>(b->d_bases, (long long)n_bases);
+        CUB(cudaGetLastError());
+    }
     CUB(cudaEventRecord(h1, st));
     CUB(cudaStreamSynchronize(st));
     float ms = 0;
@@ -609,6 +670,7 @@ int poa_b200_batch_upload(poa_b200_engine_t *eng, const poa_b200_params_t *param
     b->stats.h2d_bytes = (int64_t)(sizeof(long long) * (size_t)(n_blocks + 1 + n_seqs + 1) + 8 * (size_t)n_seqs + (size_t)n_bases);
     b->h_hdr.assign((size_t)n_blocks * HDR_WORDS, -1);
     b->arena_of.assign((size_t)n_blocks, -1);
+    b->need_words.assign((size_t)n_blocks, 0);
 #undef CUB
     *out = b;
     return POA_B200_OK;
@@ -676,7 +738,8 @@ int poa_b200_batch_download(poa_b200_batch_t *b, void *stream, poa_b200_result_t
     if (r->emit_cigar) r->cigar_cache.resize((size_t)r->n_blocks);
     *out = r;
     for (int64_t i = 0; i < r->n_blocks; ++i)
-        if (r->hdr[(size_t)i * HDR_WORDS + H_STATUS] != ST_OK) return set_err(POA_B200_EBLOCK, "one or more blocks failed; see per-block status");
+        if (r->hdr[(size_t)i * HDR_WORDS + H_STATUS] != ST_OK)
+            return set_err(POA_B200_EBLOCK, "one or more blocks failed; see per-block status" + (b->retry_error.empty() ? std::string() : " (re-run not launched: " + b->retry_error + ")"));
     return POA_B200_OK;
 }
 
@@ -710,11 +773,43 @@ int poa_b200_result_from_parts(int64_t n_blocks, const int32_t *hdr, const int32
     for (int64_t i = 0; i < n_blocks; ++i) {
         const int *h = &r->hdr[(size_t)i * HDR_WORDS];
         if (h[H_STATUS] != ST_OK) continue;
-        unsigned long long off = (unsigned long long)(unsigned)h[H_OFF_LO] | ((unsigned long long)(unsigned)h[H_OFF_HI] << 32);
-        unsigned long long words = 4ull * (unsigned)h[H_N_NODE] + 2ull * (unsigned)h[H_IN_TOT] + 2ull * (unsigned)h[H_OUT_TOT] + (unsigned)h[H_ALN_TOT]
-                                 + 3ull * (unsigned)h[H_N_SEQ] + (unsigned)h[H_PATH_TOT] + (unsigned)(h[H_CONS_LEN] > 0 ? h[H_CONS_LEN] : 0) + 2ull * (unsigned)h[H_CIG_TOT]
-                                 + ((unsigned long long)(unsigned)h[H_MSA_ROWS] * (unsigned)(h[H_MSA_LEN] > 0 ? h[H_MSA_LEN] : 0) + 3) / 4;
-        if (off + words > (unsigned long long)arena_words) { delete r; return set_err(POA_B200_EARG, "block body outside the arena"); }
+        if (block_body_end(h) > (unsigned long long)arena_words) { delete r; return set_err(POA_B200_EARG, "block body outside the arena"); }
+    }
+    *out = r;
+    return POA_B200_OK;
+}
+
+int poa_b200_result_from_device_parts(poa_b200_engine_t *eng, int64_t n_blocks, const int32_t *hdr, const int32_t *d_arena,
+                                       int64_t arena_words, void *stream, poa_b200_result_t **out) {
+    if (!eng || !out || n_blocks < 0 || (n_blocks > 0 && !hdr) || arena_words < 0 || (arena_words > 0 && !d_arena)) return set_err(POA_B200_EARG, "bad argument");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(eng->mu);
+    CU(cudaSetDevice(eng->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : eng->stream;
+    poa_b200_result *r = new (std::nothrow) poa_b200_result();
+    if (!r) return set_err(POA_B200_ENOMEM, "result alloc");
+    r->pinned = eng->pinned;
+    r->n_blocks = n_blocks;
+    r->hdr.assign(hdr, hdr + n_blocks * HDR_WORDS);
+    r->arena_of.assign((size_t)n_blocks, 0);
+    size_t cap = 0;
+    int *h = (int *)r->pinned->take((size_t)std::max<int64_t>(arena_words, 1) * 4, &cap);
+    if (!h) { delete r; return set_err(POA_B200_ENOMEM, "cudaMallocHost failed for the result buffer"); }
+    r->arenas.push_back(h); r->arena_caps.push_back(cap); r->arena_words.push_back((unsigned long long)arena_words);
+    cudaEvent_t d0, d1;
+    CU(cudaEventCreate(&d0)); CU(cudaEventCreate(&d1));
+    CU(cudaEventRecord(d0, st));
+    if (arena_words) CU(cudaMemcpyAsync(h, d_arena, (size_t)arena_words * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(d1, st));
+    CU(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, d0, d1);
+    cudaEventDestroy(d0); cudaEventDestroy(d1);
+    r->stats.d2h_ms = ms; r->stats.d2h_bytes = arena_words * 4 + n_blocks * HDR_WORDS * 4;
+    for (int64_t i = 0; i < n_blocks; ++i) {  // same validation as poa_b200_result_from_parts
+        const int *hh = &r->hdr[(size_t)i * HDR_WORDS];
+        if (hh[H_STATUS] != ST_OK) continue;
+        if (block_body_end(hh) > (unsigned long long)arena_words) { poa_b200_result_free(r); return set_err(POA_B200_EARG, "block body outside the arena"); }
     }
     *out = r;
     return POA_B200_OK;
@@ -876,6 +971,30 @@ int poa_b200_result_block(const poa_b200_result_t *res, int64_t blk, poa_b200_bl
     v->in_total = in_tot; v->out_total = out_tot; v->aln_total = aln_tot; v->path_total = path_tot; v->cigar_total = cig_tot;
     v->inband_cells = (int64_t)((unsigned long long)(unsigned)h[H_INBAND_LO] | ((unsigned long long)(unsigned)h[H_INBAND_HI] << 32));
     v->cigar = reinterpret_cast<const uint64_t *>(cig);  // lo word first: little-endian uint64, 4-byte aligned
+    return POA_B200_OK;
+}
+
+int poa_b200_result_block_hash(const poa_b200_result_t *res, int64_t blk, uint64_t *hash) {
+    if (!hash) return set_err(POA_B200_EARG, "NULL argument");
+    poa_b200_block_view_t v;
+    int rc = poa_b200_result_block(res, blk, &v);
+    if (rc) return rc;
+    if (v.status != POA_B200_OK) return set_err(POA_B200_EBLOCK, "block has no result");
+    // FNV-1a over what abPOA holds for the graph: node_n (int), then per node its base (one byte), out_id[] and
+    // out_edge_weight[] (ints) -- the byte stream oracle/ref_shim.c:ref_poa_batch_timed hashes from abpoa_graph_t
+    uint64_t h = 1469598103934665603ULL;
+    auto mix = [&h](const void *d, size_t n) { const uint8_t *p = (const uint8_t *)d; for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ULL; } };
+    const int32_t n = v.n_node;
+    mix(&n, sizeof(n));
+    int64_t at = 0;
+    for (int i = 0; i < n; ++i) {
+        const uint8_t b = (uint8_t)v.base[i];
+        mix(&b, 1);
+        mix(v.out_id + at, sizeof(int32_t) * (size_t)v.out_n[i]);
+        mix(v.out_w + at, sizeof(int32_t) * (size_t)v.out_n[i]);
+        at += v.out_n[i];
+    }
+    *hash = h;
     return POA_B200_OK;
 }
 

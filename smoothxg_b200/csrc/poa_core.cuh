@@ -1540,7 +1540,10 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
                               + 2LL * n_seq + 2LL * cig_tot + (msa_bytes + 3) / 4;
         if (tid == 0) {
             unsigned long long off = poa_atomic_add(O.arena_used, (unsigned long long)words);
-            if (off + (unsigned long long)words > O.arena_cap) sh.err = ST_EARENA;
+            if (off + (unsigned long long)words > O.arena_cap) {
+                sh.err = ST_EARENA;  // the host re-runs the block with an arena sized from this exact figure
+                hdr[H_OFF_LO] = (int)(unsigned)((unsigned long long)words & 0xffffffffull); hdr[H_OFF_HI] = (int)(unsigned)((unsigned long long)words >> 32);
+            }
             sh.bcast[0] = (int)(off & 0xffffffffull); sh.bcast[1] = (int)(off >> 32);
         }
         sync_block<NW>();

@@ -28,7 +28,12 @@ inline void build_params(const poa_b200_params_t &p, const poa_b200_engine_opts_
     d.local = p.align_mode == 1;
     d.wb = p.wb; d.wf = p.wf;
     d.out_cons = p.out_cons ? 1 : 0; d.out_msa = p.out_msa ? 1 : 0;
-    d.pn16 = 32; d.pn32 = 16;
+    // lane counts of the reference build whose vector-granular band-start rule is reproduced (abpoa_align_simd.c:949-960):
+    // flags bits 4-5 = 0 AVX-512BW (32 / 16 lanes, what -march=native gives on the hosts this was pinned on), 1 AVX2 (16 / 8),
+    // 2 SSE4.1 / NEON (8 / 4).  The survey found results identical across the three on every fixture; the option exists so
+    // that a maintainer on a narrower host can match their own build bit for bit should a case ever differ.
+    const int isa = (o.flags >> 4) & 3;
+    d.pn16 = isa == 1 ? 16 : (isa == 2 ? 8 : 32); d.pn32 = d.pn16 / 2;
     d.emit_cigar = o.emit_cigar ? 1 : 0;
     // packed 16-bit fill (poa_fill16.cuh): every intermediate must stay inside int16, i.e. the slack abPOA
     // builds into inf_min (512 * max(e1,e2), abpoa_align_simd.c:1295) must cover one mismatch, one gap open

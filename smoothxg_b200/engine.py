@@ -27,11 +27,11 @@ H_OFF_LO, H_OFF_HI = 11, 12  # header slots holding a block body's word offset i
 
 ABI_SYMBOLS = [
     "poa_b200_abi_version", "poa_b200_strerror", "poa_b200_last_error",
-    "poa_b200_encode_bases", "poa_b200_engine_create", "poa_b200_engine_destroy",
+    "poa_b200_encode_bases", "poa_b200_engine_create", "poa_b200_engine_destroy", "poa_b200_engine_trim",
     "poa_b200_run_batch", "poa_b200_poa_block",
     "poa_b200_batch_upload", "poa_b200_batch_launch", "poa_b200_batch_download", "poa_b200_batch_finish",
-    "poa_b200_batch_free", "poa_b200_batch_stats", "poa_b200_batch_device_result", "poa_b200_result_from_parts",
-    "poa_b200_result_n_blocks", "poa_b200_result_block", "poa_b200_result_stats", "poa_b200_result_free",
+    "poa_b200_batch_free", "poa_b200_batch_stats", "poa_b200_batch_device_result", "poa_b200_result_from_parts", "poa_b200_result_from_device_parts",
+    "poa_b200_result_n_blocks", "poa_b200_result_block", "poa_b200_result_block_hash", "poa_b200_result_stats", "poa_b200_result_free",
     "poa_b200_block_graph", "poa_b200_graph_view", "poa_b200_graph_free",
 ]
 
@@ -131,6 +131,7 @@ def load_library() -> C.CDLL:
     lib.poa_b200_engine_create.argtypes = [C.c_int, C.POINTER(EngineOpts), C.POINTER(vp)]
     lib.poa_b200_engine_destroy.argtypes = [vp]
     lib.poa_b200_engine_destroy.restype = None
+    lib.poa_b200_engine_trim.argtypes = [vp]
     batch_args = [vp, C.POINTER(PoaParams), i64, vp, vp, vp, vp, vp, C.POINTER(vp)]
     lib.poa_b200_run_batch.argtypes = batch_args
     lib.poa_b200_batch_upload.argtypes = batch_args
@@ -143,9 +144,11 @@ def load_library() -> C.CDLL:
     lib.poa_b200_batch_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.poa_b200_batch_device_result.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i32), C.POINTER(vp)]
     lib.poa_b200_result_from_parts.argtypes = [i64, vp, vp, i64, C.POINTER(vp)]
+    lib.poa_b200_result_from_device_parts.argtypes = [vp, i64, vp, vp, i64, vp, C.POINTER(vp)]
     lib.poa_b200_result_n_blocks.argtypes = [vp]
     lib.poa_b200_result_n_blocks.restype = i64
     lib.poa_b200_result_block.argtypes = [vp, i64, C.POINTER(_BlockView)]
+    lib.poa_b200_result_block_hash.argtypes = [vp, i64, C.POINTER(C.c_uint64)]
     lib.poa_b200_block_graph.argtypes = [C.POINTER(_BlockView), i32, i32, C.POINTER(vp)]
     lib.poa_b200_graph_view.argtypes = [vp, C.POINTER(_GraphView)]
     lib.poa_b200_graph_free.argtypes = [vp]
@@ -235,6 +238,12 @@ class PoaResult:
                          _arr(v.aln_n, n), _arr(v.aln_id, v.aln_total),
                          _arr(v.path_len, s), _arr(v.path_node, v.path_total), _arr(v.cons_node, max(v.cons_len, 0)),
                          msa, _arr(v.best_score, s), _arr(v.n_cigar, s), cig, int(v.inband_cells))
+
+    def block_hash(self, i: int) -> int:
+        """FNV-1a of block i's graph (poa_b200_result_block_hash): comparable with oracle/ref_shim.c's per-block hash."""
+        h = C.c_uint64()
+        _check(self._lib, self._lib.poa_b200_result_block_hash(self._h, i, C.byref(h)))
+        return int(h.value)
 
     def block_graph(self, i: int, padding_len: int = 0, include_consensus: bool = True) -> BlockGraph:
         """The per-block graph smoothxg's build_odgi_abPOA would leave behind (poa_b200_block_graph)."""
@@ -356,6 +365,14 @@ class PoaEngine:
         _check(self._lib, self._lib.poa_b200_batch_upload(self._h, C.byref(params), *a, C.byref(h)))
         return DeviceBatch(self._lib, h, keep)
 
+    def result_from_device(self, hdr: np.ndarray, d_arena_ptr: int, arena_words: int, stream: int | None = None) -> PoaResult:
+        """Host result from host headers + arena words resident on this engine's GPU (poa_b200_result_from_device_parts)."""
+        hdr = np.ascontiguousarray(hdr, dtype=np.int32)
+        r = C.c_void_p()
+        _check(self._lib, self._lib.poa_b200_result_from_device_parts(self._h, hdr.shape[0] // HDR_WORDS, hdr.ctypes.data, C.c_void_p(d_arena_ptr),
+                                                                       int(arena_words), C.c_void_p(stream or 0), C.byref(r)))
+        return PoaResult(self._lib, r)
+
     def poa_block(self, seqs, weights, params: PoaParams) -> PoaResult:
         """abpoa_poa-shaped convenience call for one block (poa_b200_poa_block)."""
         seqs = [_c(s, np.uint8) for s in seqs]
@@ -365,6 +382,10 @@ class PoaEngine:
         r = C.c_void_p()
         _check(self._lib, self._lib.poa_b200_poa_block(self._h, C.byref(params), n, ptrs, lens.ctypes.data, wts.ctypes.data, C.byref(r)))
         return PoaResult(self._lib, r)
+
+    def trim(self):
+        """Return pooled device / pinned buffers to the driver (poa_b200_engine_trim)."""
+        _check(self._lib, self._lib.poa_b200_engine_trim(self._h))
 
     def close(self):
         if self._h:

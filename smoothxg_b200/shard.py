@@ -3,8 +3,8 @@
 Blocks are independent POA problems (the reference's loop over them is a plain OpenMP parallel-for,
 src/smooth.cpp:1931), so there is no exchange during compute.  Each rank (one process per GPU) aligns
 its shard; the per-block result bodies then travel to rank 0 in ONE variable-size gather
-(all_gather of sizes + gather of padded buffers; NCCL over NVLink on GPUs, gloo in the CPU tests) and are
-re-ordered by block id.  The assignment is fixed before launch (cost-balanced LPT on sum(len)^2), so
+(all_gather of sizes + one grouped, size-exact send/recv into a flat buffer; NCCL over NVLink on GPUs, gloo in the
+CPU tests) and are re-ordered by block id through their headers.  The assignment is fixed before launch (cost-balanced LPT on sum(len)^2), so
 results are bit-identical for any GPU count.
 """
 from __future__ import annotations
@@ -68,22 +68,41 @@ def rebase_local(hdr: np.ndarray, arena_words: list, block_arena: np.ndarray) ->
     return h.reshape(-1)
 
 
-def gather_to_root(t, dist, root: int = 0):
-    """Variable-length gather of a 1-D tensor to `root`: one all_gather of sizes, one gather of padded buffers."""
+def gather_exact(t, dist, root: int = 0):
+    """Size-exact variable-length gather of a 1-D tensor to `root`: one all_gather of element counts, then ONE grouped
+    exchange -- every other rank sends exactly its payload, `root` receives each straight into its slice of one flat
+    buffer (nothing is padded to the largest payload, nothing is copied a second time on the device).  Returns
+    (flat buffer, [start offsets], [sizes]) on root, None elsewhere.  NCCL over NVLink on GPUs, gloo in the CPU tests."""
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
     n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
     sizes = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(sizes, n)
     sizes = [int(s.item()) for s in sizes]
-    m = max(max(sizes), 1)
-    pad = torch.zeros(m, dtype=t.dtype, device=t.device)
-    pad[:t.numel()] = t
-    bufs = [torch.empty(m, dtype=t.dtype, device=t.device) for _ in range(world)] if rank == root else None
-    dist.gather(pad, bufs, dst=root)
+    starts = [0] * world
+    for r in range(1, world):
+        starts[r] = starts[r - 1] + sizes[r - 1]
     if rank != root:
+        if t.numel():
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, t, root)]):
+                w.wait()
         return None
-    return [b[:s] for b, s in zip(bufs, sizes)]
+    buf = torch.empty(max(sum(sizes), 1), dtype=t.dtype, device=t.device)
+    ops = [dist.P2POp(dist.irecv, buf[starts[r]:starts[r] + sizes[r]], r) for r in range(world) if r != root and sizes[r]]
+    works = dist.batch_isend_irecv(ops) if ops else []
+    buf[starts[root]:starts[root] + sizes[root]].copy_(t)
+    for w in works:
+        w.wait()
+    return buf, starts, sizes
+
+
+def gather_to_root(t, dist, root: int = 0):
+    """Variable-length gather of a 1-D tensor to `root` as a list of per-rank tensors (views of gather_exact()'s buffer)."""
+    got = gather_exact(t, dist, root)
+    if got is None:
+        return None
+    buf, starts, sizes = got
+    return [buf[a:a + n] for a, n in zip(starts, sizes)]
 
 
 class _DevPtr:
@@ -93,41 +112,77 @@ class _DevPtr:
         self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i4", "data": (ptr, False), "version": 2}
 
 
+def plan(batch, world: int) -> list:
+    """The static assignment: block ids of every rank (ascending), fixed before launch."""
+    return lpt_shard(block_costs(batch), world)
+
+
+def gather_result(eng, dev, n_local: int, ids_by_rank, n_total: int, dist, stream=None, timings=None):
+    """The path's one exchange step: a finished device batch of this rank's shard -> PoaResult of the whole batch on rank 0
+    (None elsewhere).  Payload per rank = [headers | result bodies], exactly as the kernel left them in HBM; rank 0
+    receives every payload into one flat device buffer over NCCL, rebases the (tiny) headers on the host, and builds the
+    host result with a single device-to-host copy into pooled pinned memory (poa_b200_result_from_device_parts)."""
+    import time
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    d_hdr, d_arenas, block_arena = dev.device_result(n_local)
+    dv = torch.device("cuda", torch.cuda.current_device())
+    hdr_t = torch.as_tensor(_DevPtr(d_hdr, max(n_local, 1) * HDR_WORDS), device=dv)[:n_local * HDR_WORDS]
+    ar_t = [torch.as_tensor(_DevPtr(p, max(w, 1)), device=dv)[:w] for p, w in d_arenas]
+    if len(ar_t) > 1:  # re-run blocks sit in further arenas: rebase their offsets onto the concatenation (headers only, host)
+        h = rebase_local(hdr_t.cpu().numpy(), [w for _, w in d_arenas], block_arena)
+        hdr_t = torch.from_numpy(h).to(dv)
+    payload = torch.cat([hdr_t] + ar_t) if (n_local or ar_t) else torch.zeros(0, dtype=torch.int32, device=dv)
+    t0 = time.perf_counter()
+    got = gather_exact(payload, dist)
+    if timings is not None:
+        torch.cuda.synchronize()
+        timings["gather_ms"] = (time.perf_counter() - t0) * 1e3
+    if rank != 0:
+        return None
+    buf, starts, sizes = got
+    # headers of every rank: small strided device reads, rebased onto the flat buffer on the host
+    hdr = np.full(n_total * HDR_WORDS, -1, dtype=np.int32)
+    H = hdr.reshape(-1, HDR_WORDS)
+    for r in range(world):
+        ids = np.asarray(ids_by_rank[r], dtype=np.int64)
+        nl = ids.shape[0]
+        if nl == 0:
+            continue
+        h = buf[starts[r]:starts[r] + nl * HDR_WORDS].cpu().numpy().reshape(-1, HDR_WORDS).copy()
+        off = (h[:, H_OFF_LO].astype(np.int64) & 0xFFFFFFFF) | (h[:, H_OFF_HI].astype(np.int64) << 32)
+        off += starts[r] + nl * HDR_WORDS
+        h[:, H_OFF_LO] = (off & 0xFFFFFFFF).astype(np.uint32).view(np.int32)
+        h[:, H_OFF_HI] = (off >> 32).astype(np.int32)
+        H[ids] = h
+    t1 = time.perf_counter()
+    res = eng.result_from_device(hdr, buf.data_ptr(), sum(sizes), stream)
+    if timings is not None:
+        timings["d2h_ms"] = (time.perf_counter() - t1) * 1e3
+        timings["gathered_bytes"] = 4 * sum(sizes)
+    return res
+
+
+def run_shard(eng, sub, ids_by_rank, n_total: int, params, dist, stream=None, timings=None):
+    """One rank's part of a sharded call: host shard in (`sub` = batch.select(ids_by_rank[rank])), H2D, kernel, the gather;
+    the whole batch's PoaResult out on rank 0."""
+    import time
+    t0 = time.perf_counter()
+    dev = eng.upload(sub, params)
+    dev.launch(stream); dev.finish(stream)
+    if timings is not None:
+        st = dev.stats()
+        timings["h2d_ms"] = st["h2d_ms"]; timings["kernel_ms"] = st["kernel_ms"]; timings["compute_ms"] = (time.perf_counter() - t0) * 1e3
+        timings["h2d_bytes"] = st["h2d_bytes"]
+    res = gather_result(eng, dev, sub.n_blocks, ids_by_rank, n_total, dist, stream, timings)
+    dev.close()
+    return res
+
+
 def run_sharded(eng, batch, params, dist=None, stream=None):
     """Align `batch` over all ranks of `dist` (None = single process).  Every rank passes the same batch;
     rank r aligns shard r.  Returns a PoaResult for the whole batch on rank 0 and None elsewhere."""
-    import torch
-    from . import engine
-    world = dist.get_world_size() if dist is not None else 1
-    rank = dist.get_rank() if dist is not None else 0
-    ids = lpt_shard(block_costs(batch), world)[rank]
-    sub = batch.select(ids)
-    dev = eng.upload(sub, params)
-    dev.launch(stream); dev.finish(stream)
-    d_hdr, d_arenas, block_arena = dev.device_result(sub.n_blocks)
-    dv = torch.device("cuda", torch.cuda.current_device())
-    hdr_t = torch.as_tensor(_DevPtr(d_hdr, max(sub.n_blocks, 1) * HDR_WORDS), device=dv)[:sub.n_blocks * HDR_WORDS]
-    ar_t = [torch.as_tensor(_DevPtr(p, max(w, 1)), device=dv)[:w] for p, w in d_arenas]
-    # offset fix-up is header-only and tiny, done on the host; bodies stay on the device
-    h = rebase_local(hdr_t.cpu().numpy(), [w for _, w in d_arenas], block_arena)
-    arena = torch.cat(ar_t) if len(ar_t) > 1 else (ar_t[0] if ar_t else torch.zeros(0, dtype=torch.int32, device=dv))
-    if world == 1:
-        a = arena.cpu().numpy()
-        dev.close()
-        hh, aa = merge_parts(batch.n_blocks, [(ids, h, a)])
-        return engine.result_from_parts(hh, aa)
-    payload = torch.cat([torch.from_numpy(np.concatenate([[ids.shape[0]], ids]).astype(np.int64)).view(torch.int32).to(dv),
-                         torch.from_numpy(h).to(dv), arena])
-    got = gather_to_root(payload, dist)
-    dev.close()
-    if rank != 0:
-        return None
-    parts = []
-    for g in got:
-        g = g.cpu().numpy()
-        n_local = int(g[:2].view(np.int64)[0])
-        gid = g[2:2 + 2 * n_local].view(np.int64)
-        hh = g[2 + 2 * n_local:2 + 2 * n_local + n_local * HDR_WORDS]
-        parts.append((gid, hh, g[2 + 2 * n_local + n_local * HDR_WORDS:]))
-    hh, aa = merge_parts(batch.n_blocks, parts)
-    return engine.result_from_parts(hh, aa)
+    if dist is None or dist.get_world_size() == 1:
+        return eng.run_batch(batch, params)
+    ids_by_rank = plan(batch, dist.get_world_size())
+    return run_shard(eng, batch.select(ids_by_rank[dist.get_rank()]), ids_by_rank, batch.n_blocks, params, dist, stream)

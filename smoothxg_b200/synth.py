@@ -47,8 +47,23 @@ class PoaBatch:
         return out
 
     def select(self, idx) -> "PoaBatch":
-        """Sub-batch with the given block ids, in the given order."""
-        return PoaBatch.from_blocks([(self.block_seqs(int(b)), self.block(int(b))[2]) for b in idx])
+        """Sub-batch with the given block ids, in the given order (vectorised: a shard of a 10 000-block batch in milliseconds)."""
+        idx = np.asarray(idx, dtype=np.int64).reshape(-1)
+        s0, s1 = self.block_seq_off[idx], self.block_seq_off[idx + 1]
+        nseq = s1 - s0
+        bso = np.zeros(idx.shape[0] + 1, dtype=np.int64)
+        np.cumsum(nseq, out=bso[1:])
+        seq_idx = np.repeat(s0 - bso[:-1], nseq) + np.arange(bso[-1], dtype=np.int64)
+        seq_len = np.ascontiguousarray(self.seq_len[seq_idx], dtype=np.int32)
+        seq_off = np.zeros(seq_len.shape[0] + 1, dtype=np.int64)
+        np.cumsum(seq_len, out=seq_off[1:])
+        b0 = self.seq_off[s0]
+        nb = self.seq_off[s1] - b0  # a block's sequences are consecutive, so its bases are one contiguous run
+        boff = np.zeros(idx.shape[0] + 1, dtype=np.int64)
+        np.cumsum(nb, out=boff[1:])
+        base_idx = np.repeat(b0 - boff[:-1], nb) + np.arange(boff[-1], dtype=np.int64)
+        return PoaBatch(bso, seq_len, seq_off, np.ascontiguousarray(self.bases[base_idx], dtype=np.uint8),
+                        np.ascontiguousarray(self.weight[seq_idx], dtype=np.int32))
 
     @staticmethod
     def from_blocks(blocks) -> "PoaBatch":

@@ -9,8 +9,32 @@ from smoothxg_b200.synth import PoaBatch
 PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "abpoa_golden.npz")
 
 
-def load_cases():
-    z = np.load(PATH)
+REAL_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "drb1_golden.npz")
+
+
+def load_real_cases():
+    """tests/golden/drb1_golden.npz (tests/golden/make_real_golden.py): the 17 real blocks smoothxg forms from its own test
+    data (DRB1-3123, -l 1100), exactly as handed to abPOA (padding, orientation, dedup weights), global-banded and local,
+    with the unmodified abPOA's dumps."""
+    return load_cases(REAL_PATH)
+
+
+def load_real_meta(name):
+    """Per block of a real case: (block id, padding, [(weight, strand flags, names)], final block graph text of the reference)."""
+    z = np.load(REAL_PATH)
+    out = []
+    for line, gfa in zip(z[f"{name}/meta"], z[f"{name}/final_gfa"]):
+        f = str(line).split("\t")
+        seqs = []
+        for rec in f[2:]:
+            w, revs, names = rec.split(":", 2)
+            seqs.append((int(w), [c == "1" for c in revs], names.split(",")))
+        out.append((int(f[0]), int(f[1]), seqs, str(gfa)))
+    return out
+
+
+def load_cases(path=PATH):
+    z = np.load(path)
     out = []
     for name in [str(n) for n in z["names"]]:
         batch = PoaBatch(z[f"{name}/bso"], z[f"{name}/sl"], z[f"{name}/so"], z[f"{name}/ba"], z[f"{name}/wt"])

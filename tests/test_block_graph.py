@@ -106,3 +106,23 @@ def test_block_graph_matches_build_odgi(wire, name, padding, cons):
                 assert np.array_equal(v.base[g.path(i) + 1].astype(np.uint8), seq)
             off += ln
     res.close()
+
+
+@pytest.mark.parametrize("name", ["abpoa_seq_fa_global", "edge_shapes", "syn_indel", "syn_local"])
+def test_block_hash_matches_unmodified_abpoa(wire, name):
+    """poa_b200_result_block_hash() hashes the same byte stream as oracle/ref_shim.c:ref_poa_batch_timed does from
+    abpoa_graph_t (node_n, base, out ids, out weights): bench.py compares its CPU sample with the GPU result this way."""
+    from oracle.oracle import RefAbpoa, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    _, batch, p, _ = CASES[name]
+    parts = []
+    for b in range(batch.n_blocks):
+        w = wire.poa_block(pd_params(p), *batch.block(b)).raw
+        parts.append((np.array([b]), w[:engine.HDR_WORDS], w[engine.HDR_WORDS:]))
+    hdr, arena = merge_parts(batch.n_blocks, parts)
+    res = engine.result_from_parts(hdr, arena)
+    _, want = RefAbpoa().batch_timed(pd_params(p), batch, n_threads=2, want_hash=True)
+    got = np.array([res.block_hash(b) for b in range(batch.n_blocks)], dtype=np.uint64)
+    assert np.array_equal(got, want)
+    res.close()

@@ -12,7 +12,7 @@ import pytest
 
 from oracle.oracle import _Checker
 from smoothxg_b200 import engine
-from tests.golden_io import load_cases, pd_params
+from tests.golden_io import load_cases, load_real_cases, pd_params
 from tests.helpers import view_to_dump
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -101,6 +101,23 @@ def test_emulated_device_logic_matches_golden(emu, name, batch, p, dumps):
         assert got is not None
         assert np.array_equal(got.compare_part(), dumps[b].compare_part()), f"{name} block {b}"
         assert got.edge_rows == dumps[b].edge_rows
+
+
+@pytest.mark.parametrize("mode,blocks", [("drb1_global", (0, 7, 16)), ("drb1_local", (3,))])
+def test_emulated_device_logic_on_real_blocks(emu, mode, blocks):
+    chk, _ = emu
+    _, batch, p, dumps = next(c for c in load_real_cases() if c[0] == mode)
+    for b in blocks:
+        got = chk.poa_block(pd_params(p), *batch.block(b))
+        assert got is not None
+        assert np.array_equal(got.compare_part(), dumps[b].compare_part()), f"{mode} block {b}"
+
+
+def test_emulated_warp_logic_on_a_real_block(emu32):
+    _, batch, p, dumps = next(c for c in load_real_cases() if c[0] == "drb1_global")
+    b = 4
+    got = emu32.poa_block(pd_params(p), *batch.block(b))
+    assert np.array_equal(got.compare_part(), dumps[b].compare_part())
 
 
 def test_result_accessors_on_wire_format(emu):

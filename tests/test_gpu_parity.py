@@ -8,7 +8,7 @@ import pytest
 from oracle.oracle import make_params as oracle_params
 from smoothxg_b200 import engine as E
 from smoothxg_b200 import shard, synth
-from tests.golden_io import engine_params, load_cases, pd_params
+from tests.golden_io import engine_params, load_cases, load_real_cases, pd_params
 from tests.helpers import first_diff, view_to_dump
 
 pytestmark = pytest.mark.gpu
@@ -30,6 +30,17 @@ def test_golden_vectors(warps):
     eng = E.PoaEngine(device=0, emit_cigar=True, warps_per_block=warps)
     for name, batch, p, dumps in CASES:
         _check_batch(eng, batch, engine_params(p), dumps, f"{name}/w{warps}")
+    eng.close()
+
+
+@pytest.mark.parametrize("warps", [1, 2, 4, 8])
+def test_real_drb1_blocks(warps):
+    """BASELINE configs[0]'s data on the abPOA path: the 17 blocks smoothxg forms from DRB1-3123 (-l 1100), exactly as handed
+    to abPOA -- global-banded (-A -Z) and local (-A) -- against the unmodified abPOA's dumps."""
+    eng = E.PoaEngine(device=0, emit_cigar=True, warps_per_block=warps)
+    for name, batch, p, dumps in load_real_cases():
+        st = _check_batch(eng, batch, engine_params(p), dumps, f"{name}/w{warps}")
+        assert st["inband_cells"] == sum(d.inband_cells for d in dumps)
     eng.close()
 
 

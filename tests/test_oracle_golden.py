@@ -3,9 +3,20 @@ the unmodified vendored abPOA -- graph, read paths, consensus, MSA, scores, ciga
 import numpy as np
 import pytest
 
-from tests.golden_io import load_cases, pd_params
+from tests.golden_io import load_cases, load_real_cases, pd_params
 
 CASES = load_cases()
+REAL = load_real_cases()
+
+
+@pytest.mark.parametrize("name,batch,p,dumps", REAL, ids=[c[0] for c in REAL])
+def test_oracle_matches_real_blocks(oracle, name, batch, p, dumps):
+    """Real DRB1 blocks as smoothxg hands them to abPOA (N padding, dedup weights, long predecessor edges, in-degree up to 6)."""
+    assert batch.n_blocks == 17 and int(batch.weight.max()) > 1 and int((batch.bases == 4).sum()) > 0
+    for b in range(batch.n_blocks):
+        got = oracle.poa_block(pd_params(p), *batch.block(b))
+        assert got is not None
+        assert np.array_equal(got.raw, dumps[b].raw), f"{name} block {b}"
 
 
 @pytest.mark.parametrize("name,batch,p,dumps", CASES, ids=[c[0] for c in CASES])
