@@ -81,7 +81,10 @@ typedef struct poa_b200_engine poa_b200_engine_t;
 typedef struct poa_b200_batch  poa_b200_batch_t;
 typedef struct poa_b200_result poa_b200_result_t;
 
-/* One block of a finished batch.  All pointers point into memory owned by the result. */
+/* One block of a finished batch.  All pointers point into memory owned by the result.  Results are held in a compact form
+ * (narrow integers, run-length coded paths: about 60 KB for a 32 x 2 kb block instead of 386 KB as flat int32 arrays -- this is
+ * what crosses PCIe and NVLink); poa_b200_result_block() expands a block into the flat arrays below the first time it is asked
+ * for and keeps the expansion until poa_b200_result_release_block() or poa_b200_result_free(). */
 typedef struct poa_b200_block_view {
     int32_t status;              /* POA_B200_OK or a per-block error */
     int32_t n_node;              /* abg->node_n, including source (0) and sink (1) */
@@ -184,8 +187,10 @@ int  poa_b200_batch_stats(const poa_b200_batch_t *batch, poa_b200_stats_t *stats
 /* ---- next stage: the per-block graph smoothxg builds from the POA result.
  * build_odgi_abPOA (reference src/smooth.cpp:2442-2574) turns abpoa_t into an odgi graph of 1-bp nodes
  * (odgi id = abPOA id - 1), embeds one path per read with `padding_len` steps trimmed at both ends, embeds the
- * consensus path restricted to nodes some read still covers, and drops every edge and node no path uses
- * (:2559-2573).  poa_b200_block_graph() produces exactly that graph as flat arrays (pure host code, no GPU):
+ * consensus path restricted to nodes some read still covers, and drops every node no path uses together with its edges
+ * (:2567-2573; the edge-dropping pass before it, :2559-2565, removes nothing: odgi's find_edges_exceeding_depth_limits with
+ * min_depth 1 only inspects edges that a path walks, deps/odgi/src/algorithms/depth.cpp:17-51 -- so an edge between two kept
+ * nodes stays even when no trimmed path walks it).  poa_b200_block_graph() produces exactly that graph as flat arrays (pure host code, no GPU):
  * nodes in the order build_odgi_abPOA creates them (Kahn walk from the source over out_id order, :2463-2511),
  * edges as (from, to) pairs of odgi ids in creation order, paths as step lists in the POA's forward
  * orientation -- for a read whose dup_is_revs flag is set the caller walks its list backwards and flips the
@@ -194,7 +199,7 @@ typedef struct poa_b200_graph_view {
     int32_t n_node;             /* nodes kept: covered by at least one trimmed read path */
     const int32_t *node_id;     /* [n_node] odgi id (abPOA id - 1) */
     const char    *node_base;   /* [n_node] 'A','C','G','T','N' (ab_nt256_table) */
-    int32_t n_edge;             /* edges kept: traversed by at least one path */
+    int32_t n_edge;             /* edges kept: both end nodes kept */
     const int32_t *edge_from;   /* [n_edge] odgi ids, forward strand both ends */
     const int32_t *edge_to;
     int32_t n_path;             /* n_seq, plus one when the consensus path was requested */
@@ -207,8 +212,34 @@ int  poa_b200_block_graph(const poa_b200_block_view_t *view, int32_t padding_len
 int  poa_b200_graph_view(const poa_b200_graph_t *graph, poa_b200_graph_view_t *view);
 void poa_b200_graph_free(poa_b200_graph_t *graph);
 
+/* ---- and the graph smooth_abpoa finally returns (reference src/smooth.cpp:545-620): the block graph above after
+ * odgi::algorithms::unchop (runs of 1-bp nodes that no path enters, leaves or branches inside become one node,
+ * deps/odgi/src/algorithms/unchop.cpp, simple_components.cpp, perfect_neighbors.cpp), renumbered 1..n in a topological order
+ * (apply_ordering(topological_order(..), compact), :557), with one edge per consecutive pair of path steps (:590-606) and the
+ * paths re-expressed over the merged nodes.  Node ids are ranks of OUR deterministic topological order (Kahn, ready nodes in
+ * creation order); the reference's ids come out of hash-map iteration order after unchop and are not a function of the block,
+ * so the two graphs are equal up to that renumbering: same node sequences, same edges, same path walks.  Pure host code.
+ * Paths as in poa_b200_block_graph: forward orientation, read order, the consensus path last. */
+typedef struct poa_b200_final_graph_view {
+    int32_t n_node;             /* node k (0-based) has id k + 1 */
+    const int64_t *seq_off;     /* [n_node + 1] offsets into seq */
+    const char    *seq;         /* concatenated node sequences */
+    int32_t n_edge;
+    const int32_t *edge_from;   /* [n_edge] node ids, forward strand both ends, sorted */
+    const int32_t *edge_to;
+    int32_t n_path;
+    const int64_t *path_off;    /* [n_path + 1] */
+    const int32_t *path_node;   /* node ids */
+} poa_b200_final_graph_view_t;
+int  poa_b200_block_final_graph(const poa_b200_block_view_t *view, int32_t padding_len, int32_t include_consensus,
+                                poa_b200_graph_t **graph);
+int  poa_b200_final_graph_view(const poa_b200_graph_t *graph, poa_b200_final_graph_view_t *view);
+
 int64_t poa_b200_result_n_blocks(const poa_b200_result_t *res);
 int  poa_b200_result_block(const poa_b200_result_t *res, int64_t block, poa_b200_block_view_t *view);
+/* Drop the flat expansion of one block (views of it become invalid); a consumer that streams through a large batch calls it
+ * after it has turned the block into its own graph. */
+void poa_b200_result_release_block(const poa_b200_result_t *res, int64_t block);
 /* Checksum of one finished block's graph: FNV-1a 64 over node_n (int32), then per node its base (one byte), out ids and
  * out weights (int32 each, final order) -- the same byte stream a checker can hash straight from abPOA's abpoa_graph_t
  * (node_n, node[i].base, node[i].out_id, node[i].out_edge_weight; deps/abPOA/include/abpoa.h:98-118), so that large samples

@@ -18,6 +18,8 @@
 #include "../../include/poa_b200.h"
 #include "poa_core.cuh"
 #include "poa_host.hpp"
+#include "poa_wire.hpp"
+#include <atomic>
 
 using namespace poa;
 
@@ -190,13 +192,23 @@ struct poa_b200_result {
     std::vector<unsigned long long> arena_words;
     poa_b200_stats_t stats{};
     int emit_cigar = 0;
-    std::vector<std::vector<uint64_t>> cigar_cache;  // lazily repacked cigars (lo/hi words -> uint64)
+    // Block bodies are stored narrow and run-length coded (WireLayout, poa_core.cuh); a block is decoded into the view's flat
+    // int32 arrays the first time it is looked at, lock-free (threads racing on one block both decode, one copy is kept).
+    mutable std::unique_ptr<std::atomic<poa::DecodedBlock *>[]> decoded;
+    void init_decoded() {
+        decoded.reset(new std::atomic<poa::DecodedBlock *>[(size_t)std::max<int64_t>(n_blocks, 1)]);
+        for (int64_t i = 0; i < std::max<int64_t>(n_blocks, 1); ++i) decoded[(size_t)i].store(nullptr, std::memory_order_relaxed);
+    }
+    ~poa_b200_result() {
+        if (decoded) for (int64_t i = 0; i < std::max<int64_t>(n_blocks, 1); ++i) delete decoded[(size_t)i].load(std::memory_order_relaxed);
+    }
 };
 
 struct poa_b200_graph {
     std::vector<int32_t> node_id, edge_from, edge_to, path_node;
     std::vector<char> node_base;
     std::vector<int64_t> path_off;
+    std::vector<int64_t> seq_off;  // final graphs only: node k spells node_base[seq_off[k] .. seq_off[k+1])
 };
 
 struct poa_b200_batch {
@@ -370,7 +382,9 @@ int run_launch(poa_b200_batch *b, const std::vector<int> &blocks, int level, cud
         long long tb = b->h_block_bases[id], ns = b->h_block_seq_off[id + 1] - b->h_block_seq_off[id], ml = b->h_block_maxlen[id];
         if (b->need_words[(size_t)id] > 0) { est_words += b->need_words[(size_t)id]; continue; }  // overflowed an arena before: the kernel reported its exact size
         long long n_est = level >= LEVEL_WORST ? tb + 2 : std::min<long long>(tb + 2, (level == 0 ? 3 : (level == 1 ? 8 : 24)) * ml + 64);
-        long long wds = 12 * n_est + tb + 3 * ns + 64;
+        // narrow, run-length coded bodies (WireLayout): ~4.5 words per node, a word per path run; level 0 assumes paths of few
+        // runs, an overflow is re-run with the exact size the kernel reports
+        long long wds = level == 0 ? 6 * n_est + tb / 4 + 5 * ns + 64 : 12 * n_est + 2 * tb + 5 * ns + 64;
         if (b->dp.out_msa) wds += (ns + 1) * n_est / 4 + 8;
         if (b->dp.emit_cigar) wds += 2 * (tb + ns * n_est);
         est_words += wds;
@@ -428,13 +442,11 @@ int collect(poa_b200_batch *b, const std::vector<int> &blocks, cudaStream_t st, 
     return POA_B200_OK;
 }
 
-// one past the last arena word of a finished block's body, from its header
+// one past the last arena word of a finished block's body, from its header; ~0 if the header is not a valid one
 unsigned long long block_body_end(const int *h) {
+    if (!wire_header_ok(h)) return ~0ull;
     const unsigned long long off = (unsigned long long)(unsigned)h[H_OFF_LO] | ((unsigned long long)(unsigned)h[H_OFF_HI] << 32);
-    const unsigned long long words = 4ull * (unsigned)h[H_N_NODE] + 2ull * (unsigned)h[H_IN_TOT] + 2ull * (unsigned)h[H_OUT_TOT] + (unsigned)h[H_ALN_TOT]
-                                   + 3ull * (unsigned)h[H_N_SEQ] + (unsigned)h[H_PATH_TOT] + (unsigned)(h[H_CONS_LEN] > 0 ? h[H_CONS_LEN] : 0) + 2ull * (unsigned)h[H_CIG_TOT]
-                                   + ((unsigned long long)(unsigned)h[H_MSA_ROWS] * (unsigned)(h[H_MSA_LEN] > 0 ? h[H_MSA_LEN] : 0) + 3) / 4;
-    return off + words;
+    return off + (unsigned long long)(unsigned)h[H_BODY_WORDS];
 }
 
 int finish_locked(poa_b200_batch *b, cudaStream_t st) {
@@ -716,6 +728,7 @@ int poa_b200_batch_download(poa_b200_batch_t *b, void *stream, poa_b200_result_t
     if (!r) return set_err(POA_B200_ENOMEM, "result alloc");
     r->pinned = b->eng->pinned;
     r->n_blocks = b->n_blocks; r->hdr = b->h_hdr; r->arena_of = b->arena_of; r->emit_cigar = b->dp.emit_cigar;
+    r->init_decoded();
     cudaEvent_t d0, d1;
     CU(cudaEventCreate(&d0)); CU(cudaEventCreate(&d1));
     CU(cudaEventRecord(d0, st));
@@ -735,7 +748,6 @@ int poa_b200_batch_download(poa_b200_batch_t *b, void *stream, poa_b200_result_t
     cudaEventDestroy(d0); cudaEventDestroy(d1);
     b->stats.d2h_ms = ms; b->stats.d2h_bytes = bytes;
     r->stats = b->stats;
-    if (r->emit_cigar) r->cigar_cache.resize((size_t)r->n_blocks);
     *out = r;
     for (int64_t i = 0; i < r->n_blocks; ++i)
         if (r->hdr[(size_t)i * HDR_WORDS + H_STATUS] != ST_OK)
@@ -765,6 +777,7 @@ int poa_b200_result_from_parts(int64_t n_blocks, const int32_t *hdr, const int32
     poa_b200_result *r = new (std::nothrow) poa_b200_result();
     if (!r) return set_err(POA_B200_ENOMEM, "result alloc");
     r->n_blocks = n_blocks;
+    r->init_decoded();
     r->hdr.assign(hdr, hdr + n_blocks * HDR_WORDS);
     r->arena_of.assign((size_t)n_blocks, 0);
     r->owned.assign(arena, arena + arena_words);
@@ -790,6 +803,7 @@ int poa_b200_result_from_device_parts(poa_b200_engine_t *eng, int64_t n_blocks, 
     if (!r) return set_err(POA_B200_ENOMEM, "result alloc");
     r->pinned = eng->pinned;
     r->n_blocks = n_blocks;
+    r->init_decoded();
     r->hdr.assign(hdr, hdr + n_blocks * HDR_WORDS);
     r->arena_of.assign((size_t)n_blocks, 0);
     size_t cap = 0;
@@ -893,18 +907,11 @@ int poa_b200_block_graph(const poa_b200_block_view_t *v, int32_t padding_len, in
         for (int i = 0; i < v->cons_len; ++i) { const int id = v->cons_node[i]; if (covered[(size_t)id]) g->path_node.push_back(id - 1); }
         g->path_off.push_back((int64_t)g->path_node.size());
     }
-    // edges some path walks: one flag per out-edge, set by looking the step's target up in its source's (short) out list.
-    // Consecutive consensus nodes need not be adjacent once uncovered nodes were dropped: such a pair matches no edge.
-    std::vector<char> out_used((size_t)out_off[(size_t)n], 0);
-    auto out_slot = [&](int a, int b) -> int64_t {  // abPOA ids
-        for (int64_t k = out_off[(size_t)a]; k < out_off[(size_t)a + 1]; ++k) if (v->out_id[k] == b) return k;
-        return -1;
-    };
-    for (size_t p = 0; p + 1 < g->path_off.size(); ++p)
-        for (int64_t k = g->path_off[p]; k + 1 < g->path_off[p + 1]; ++k) {
-            const int64_t e = out_slot(g->path_node[(size_t)k] + 1, g->path_node[(size_t)k + 1] + 1);
-            if (e >= 0) out_used[(size_t)e] = 1;
-        }
+    // Which edges survive: build_odgi_abPOA asks odgi for the edges of path depth < 1 and destroys them (:2559-2565), but
+    // find_edges_exceeding_depth_limits (deps/odgi/src/algorithms/depth.cpp:17-51) only ever looks at edges some path step
+    // walks, whose depth is >= 1 by construction, so with min_depth = 1 it returns nothing: NO edge is removed there.  Edges
+    // disappear only together with an uncovered node (:2567-2573, destroy_handle).  So every POA edge between two covered
+    // nodes is kept, walked or not -- and the unwalked ones matter: they keep unchop from merging their end nodes.
     // Kahn walk from the source in out_id order = node / edge creation order of build_odgi_abPOA (:2463-2511)
     static const char code2base[6] = {'A', 'C', 'G', 'T', 'N', '-'};
     std::vector<int> indeg((size_t)n), queue; queue.reserve((size_t)n);
@@ -921,9 +928,8 @@ int poa_b200_block_graph(const poa_b200_block_view_t *v, int32_t padding_len, in
             }
             for (int64_t k = in_off[(size_t)cur]; k < in_off[(size_t)cur + 1]; ++k) {
                 const int pre = v->in_id[k];
-                if (pre == 0) continue;
-                const int64_t e = out_slot(pre, cur);
-                if (e >= 0 && out_used[(size_t)e]) { g->edge_from.push_back(pre - 1); g->edge_to.push_back(cur - 1); }
+                if (pre == 0 || !covered[(size_t)pre] || !covered[(size_t)cur]) continue;
+                g->edge_from.push_back(pre - 1); g->edge_to.push_back(cur - 1);
             }
         }
         for (int64_t k = out_off[(size_t)cur]; k < out_off[(size_t)cur + 1]; ++k) {
@@ -932,6 +938,113 @@ int poa_b200_block_graph(const poa_b200_block_view_t *v, int32_t padding_len, in
         }
     }
     *out = g;
+    return POA_B200_OK;
+}
+
+int poa_b200_block_final_graph(const poa_b200_block_view_t *v, int32_t padding_len, int32_t include_consensus, poa_b200_graph_t **out) {
+    if (!out) return set_err(POA_B200_EARG, "bad argument");
+    *out = nullptr;
+    poa_b200_graph_t *g1 = nullptr;
+    int rc = poa_b200_block_graph(v, padding_len, include_consensus, &g1);  // 1-bp nodes, path-walked edges, trimmed paths
+    if (rc) return rc;
+    std::unique_ptr<poa_b200_graph> one(g1);
+    poa_b200_graph *g = new (std::nothrow) poa_b200_graph();
+    if (!g) return set_err(POA_B200_ENOMEM, "graph alloc");
+    const size_t n_path = one->path_off.size() - 1;
+    g->path_off.assign(1, 0);
+    g->seq_off.assign(1, 0);
+    const int n1 = (int)one->node_id.size();
+    if (n1 == 0) {
+        for (size_t p = 0; p < n_path; ++p) g->path_off.push_back(0);
+        *out = g;
+        return POA_B200_OK;
+    }
+    // dense index of the kept 1-bp nodes (odgi id -> position in creation order)
+    int max_id = 0;
+    for (int x : one->node_id) max_id = std::max(max_id, x);
+    std::vector<int> dense((size_t)max_id + 1, -1);
+    for (int k = 0; k < n1; ++k) dense[(size_t)one->node_id[(size_t)k]] = k;
+    // unchop (deps/odgi/src/algorithms/unchop.cpp, simple_components.cpp:27-60, perfect_neighbors.cpp:10-100): two nodes merge when
+    // every path step on the left one continues to the right one and every step on the right one comes from the left one
+    // -- no path starts, ends or branches between them.  NONE = no step seen yet, MANY = several targets or a path end.
+    const int NONE = -1, MANY = -2;
+    std::vector<int> nxt((size_t)n1, NONE), prv((size_t)n1, NONE);
+    auto note = [&](std::vector<int> &arr, int at, int to) { int &x = arr[(size_t)at]; x = (x == NONE || x == to) ? to : MANY; };
+    for (size_t p = 0; p < n_path; ++p) {
+        const int64_t a = one->path_off[p], b = one->path_off[p + 1];
+        if (a == b) continue;
+        prv[(size_t)dense[(size_t)one->path_node[(size_t)a]]] = MANY;       // a path starts here
+        nxt[(size_t)dense[(size_t)one->path_node[(size_t)(b - 1)]]] = MANY;  // a path ends here
+        for (int64_t k = a; k + 1 < b; ++k) {
+            const int u = dense[(size_t)one->path_node[(size_t)k]], w = dense[(size_t)one->path_node[(size_t)k + 1]];
+            note(nxt, u, w); note(prv, w, u);
+        }
+    }
+    // ... and the two are joined by the only edge leaving the left and the only edge entering the right one (simple_components.cpp:
+    // get_degree == 1 on both sides), counted over ALL kept edges, walked by a path or not
+    std::vector<int> outdeg((size_t)n1, 0), indeg1((size_t)n1, 0);
+    for (size_t e = 0; e < one->edge_from.size(); ++e) { ++outdeg[(size_t)dense[(size_t)one->edge_from[e]]]; ++indeg1[(size_t)dense[(size_t)one->edge_to[e]]]; }
+    auto linked = [&](int u) { const int w = nxt[(size_t)u]; return w >= 0 && prv[(size_t)w] == u && outdeg[(size_t)u] == 1 && indeg1[(size_t)w] == 1; };  // u and nxt[u] are one node
+    // merged nodes: chains of linked 1-bp nodes, discovered in creation order of their heads
+    std::vector<int> comp((size_t)n1, -1);
+    std::vector<int> head;  // first 1-bp node of every merged node
+    for (int k = 0; k < n1; ++k) {
+        const int pv = prv[(size_t)k];
+        if (pv >= 0 && nxt[(size_t)pv] == k && linked(pv)) continue;  // not a chain head
+        const int c = (int)head.size();
+        head.push_back(k);
+        for (int u = k;; u = nxt[(size_t)u]) { comp[(size_t)u] = c; if (!linked(u)) break; }
+    }
+    const int nc = (int)head.size();
+    // edges between merged nodes: every consecutive pair of path steps that crosses a chain boundary (src/smooth.cpp:590-606 creates
+    // an edge for every such pair, consensus steps included)
+    std::vector<std::pair<int, int>> edges;
+    for (size_t p = 0; p < n_path; ++p)
+        for (int64_t k = one->path_off[p]; k + 1 < one->path_off[p + 1]; ++k) {
+            const int u = dense[(size_t)one->path_node[(size_t)k]], w = dense[(size_t)one->path_node[(size_t)k + 1]];
+            if (!(linked(u) && nxt[(size_t)u] == w)) edges.emplace_back(comp[(size_t)u], comp[(size_t)w]);
+        }
+    std::sort(edges.begin(), edges.end());
+    edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+    // topological order (src/smooth.cpp:557: apply_ordering(topological_order(...), compact ids)): Kahn's algorithm, ready nodes
+    // taken in discovery order.  odgi's own tie-breaking keys on handle ranks that come out of a hash map after unchop, so
+    // the reference's ids are not a function of the block; any topological order gives an isomorphic graph.
+    std::vector<int> indeg((size_t)nc, 0), eoff((size_t)nc + 1, 0), rank((size_t)nc, -1), order;
+    for (auto &e : edges) { ++indeg[(size_t)e.second]; ++eoff[(size_t)e.first + 1]; }
+    for (int c = 0; c < nc; ++c) eoff[(size_t)c + 1] += eoff[(size_t)c];
+    order.reserve((size_t)nc);
+    for (int c = 0; c < nc; ++c) if (indeg[(size_t)c] == 0) order.push_back(c);
+    for (size_t qh = 0; qh < order.size(); ++qh) {
+        const int c = order[qh];
+        for (int e = eoff[(size_t)c]; e < eoff[(size_t)c + 1]; ++e) if (--indeg[(size_t)edges[(size_t)e].second] == 0) order.push_back(edges[(size_t)e].second);
+    }
+    if ((int)order.size() != nc) { delete g; return set_err(POA_B200_EINTERNAL, "block graph is not acyclic"); }
+    for (int r = 0; r < nc; ++r) rank[(size_t)order[(size_t)r]] = r;
+    // nodes in rank order: id = rank + 1, sequence = the chain's bases
+    g->node_id.resize((size_t)nc);
+    for (int r = 0; r < nc; ++r) {
+        g->node_id[(size_t)r] = r + 1;
+        for (int u = head[(size_t)order[(size_t)r]];; u = nxt[(size_t)u]) { g->node_base.push_back(one->node_base[(size_t)u]); if (!linked(u)) break; }
+        g->seq_off.push_back((int64_t)g->node_base.size());
+    }
+    for (auto &e : edges) { g->edge_from.push_back(rank[(size_t)e.first] + 1); g->edge_to.push_back(rank[(size_t)e.second] + 1); }
+    // paths: one step per merged node (a path that enters a chain walks all of it)
+    for (size_t p = 0; p < n_path; ++p) {
+        for (int64_t k = one->path_off[p]; k < one->path_off[p + 1]; ++k) {
+            const int u = dense[(size_t)one->path_node[(size_t)k]];
+            if (head[(size_t)comp[(size_t)u]] == u) g->path_node.push_back(rank[(size_t)comp[(size_t)u]] + 1);
+        }
+        g->path_off.push_back((int64_t)g->path_node.size());
+    }
+    *out = g;
+    return POA_B200_OK;
+}
+
+int poa_b200_final_graph_view(const poa_b200_graph_t *g, poa_b200_final_graph_view_t *v) {
+    if (!g || !v || g->seq_off.empty()) return set_err(POA_B200_EARG, "not a final graph");
+    v->n_node = (int32_t)g->node_id.size(); v->seq_off = g->seq_off.data(); v->seq = g->node_base.data();
+    v->n_edge = (int32_t)g->edge_from.size(); v->edge_from = g->edge_from.data(); v->edge_to = g->edge_to.data();
+    v->n_path = (int32_t)g->path_off.size() - 1; v->path_off = g->path_off.data(); v->path_node = g->path_node.data();
     return POA_B200_OK;
 }
 
@@ -957,21 +1070,35 @@ int poa_b200_result_block(const poa_b200_result_t *res, int64_t blk, poa_b200_bl
     const int ai = res->arena_of[(size_t)blk];
     if (ai < 0 || ai >= (int)res->arenas.size()) return set_err(POA_B200_EARG, "block has no result body");
     const unsigned long long off = (unsigned long long)(unsigned)h[H_OFF_LO] | ((unsigned long long)(unsigned)h[H_OFF_HI] << 32);
-    const int *o = res->arenas[(size_t)ai] + off;
-    const int n = h[H_N_NODE], ns = h[H_N_SEQ];
+    if (block_body_end(h) > res->arena_words[(size_t)ai]) return set_err(POA_B200_EARG, "block body outside the arena");
+    std::atomic<poa::DecodedBlock *> &slot = res->decoded[(size_t)blk];
+    poa::DecodedBlock *d = slot.load(std::memory_order_acquire);
+    if (!d) {
+        d = new (std::nothrow) poa::DecodedBlock();
+        if (!d) return set_err(POA_B200_ENOMEM, "decode buffer");
+        if (!wire_decode(h, res->arenas[(size_t)ai] + off, *d)) { delete d; return set_err(POA_B200_EARG, "corrupt block body"); }
+        poa::DecodedBlock *expect = nullptr;
+        if (!slot.compare_exchange_strong(expect, d, std::memory_order_acq_rel)) { delete d; d = expect; }
+    }
+    const int32_t *o = d->buf.data();
+    const int n = h[H_N_NODE];
     const long long in_tot = h[H_IN_TOT], out_tot = h[H_OUT_TOT], aln_tot = h[H_ALN_TOT], path_tot = h[H_PATH_TOT], cig_tot = h[H_CIG_TOT];
     v->n_node = n; v->cons_len = h[H_CONS_LEN]; v->msa_len = h[H_MSA_LEN]; v->msa_rows = h[H_MSA_ROWS];
-    v->base = o; v->in_n = v->base + n; v->in_id = v->in_n + n; v->in_w = v->in_id + in_tot;
-    v->out_n = v->in_w + in_tot; v->out_id = v->out_n + n; v->out_w = v->out_id + out_tot;
-    v->aln_n = v->out_w + out_tot; v->aln_id = v->aln_n + n;
-    v->path_len = v->aln_id + aln_tot; v->path_node = v->path_len + ns; v->cons_node = v->path_node + path_tot;
-    v->best_score = v->cons_node + (v->cons_len > 0 ? v->cons_len : 0); v->n_cigar = v->best_score + ns;
-    const int *cig = v->n_cigar + ns;
-    v->msa = reinterpret_cast<const uint8_t *>(cig + 2 * cig_tot);
+    v->base = o + d->base; v->in_n = o + d->in_n; v->in_id = o + d->in_id; v->in_w = o + d->in_w;
+    v->out_n = o + d->out_n; v->out_id = o + d->out_id; v->out_w = o + d->out_w;
+    v->aln_n = o + d->aln_n; v->aln_id = o + d->aln_id;
+    v->path_len = o + d->path_len; v->path_node = o + d->path_node; v->cons_node = o + d->cons_node;
+    v->best_score = o + d->best; v->n_cigar = o + d->ncig;
+    v->msa = d->msa;
+    v->cigar = reinterpret_cast<const uint64_t *>(d->cig);  // lo word first: little-endian uint64, 4-byte aligned
     v->in_total = in_tot; v->out_total = out_tot; v->aln_total = aln_tot; v->path_total = path_tot; v->cigar_total = cig_tot;
     v->inband_cells = (int64_t)((unsigned long long)(unsigned)h[H_INBAND_LO] | ((unsigned long long)(unsigned)h[H_INBAND_HI] << 32));
-    v->cigar = reinterpret_cast<const uint64_t *>(cig);  // lo word first: little-endian uint64, 4-byte aligned
     return POA_B200_OK;
+}
+
+void poa_b200_result_release_block(const poa_b200_result_t *res, int64_t blk) {
+    if (!res || blk < 0 || blk >= res->n_blocks || !res->decoded) return;
+    delete res->decoded[(size_t)blk].exchange(nullptr, std::memory_order_acq_rel);
 }
 
 int poa_b200_result_block_hash(const poa_b200_result_t *res, int64_t blk, uint64_t *hash) {

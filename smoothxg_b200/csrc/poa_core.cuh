@@ -102,7 +102,54 @@ constexpr int MAX_WARPS = 8;
 enum { ST_OK = 0, ST_ESLAB = 1, ST_EARENA = 2, ST_EINTERNAL = 3, ST_EUNSUP = 4 };
 // result header slots
 enum { H_STATUS = 0, H_N_NODE, H_N_SEQ, H_CONS_LEN, H_MSA_LEN, H_MSA_ROWS, H_IN_TOT, H_OUT_TOT, H_ALN_TOT,
-       H_PATH_TOT, H_CIG_TOT, H_OFF_LO, H_OFF_HI, H_INBAND_LO, H_INBAND_HI, H_EDGE_LO, H_EDGE_HI, H_WORDS };
+       H_PATH_TOT, H_CIG_TOT, H_OFF_LO, H_OFF_HI, H_INBAND_LO, H_INBAND_HI, H_EDGE_LO, H_EDGE_HI,
+       H_BODY_WORDS /* int32 words of the block body */, H_FORMAT /* WIRE_* */, H_RUN_TOT /* path runs, consensus included */, H_WORDS };
+static_assert(H_WORDS == HDR_WORDS, "header slots");
+
+// ------------------------------------------------------------------------------------------------
+// Result body of one block in the arena ("wire format"): what travels device -> host and GPU -> GPU.
+// A POA result is mostly small numbers and mostly consecutive node ids, so it is stored narrow:
+//   * bases and aligned-group sizes as bytes; degrees, node ids and edge weights as 16-bit values whenever the block allows
+//     it (fewer than 65 536 nodes, total sequence weight and every sequence length below 65 536 -- WIRE_NARROW), else 32-bit;
+//   * the per-read node paths and the consensus path run-length coded: a read's path through the graph is a chain of runs
+//     of consecutive node ids (the nodes one earlier read created in one piece), so (first node id, position in the read) per
+//     run replaces one id per base -- 32 x 2 000 ids become a few hundred runs.
+// 32 x 2 kb blocks shrink from 386 KB to about 60 KB: that is the D2H copy inside every end-to-end call and the payload of the
+// multi-GPU gather.  wire_layout() gives the word offset of every section from the header's totals; the kernel writes through
+// it (poa_block) and the host decodes through it (poa_wire.hpp) into the flat int32 arrays of poa_b200_block_view_t.
+// ------------------------------------------------------------------------------------------------
+enum { WIRE_NARROW = 1, WIRE_WIDE = 3 };
+struct WireLayout {
+    long long o_base, o_aln_n, o_in_n, o_out_n, o_in_id, o_in_w, o_out_id, o_out_w, o_aln_id;  // word offsets from the body start
+    long long o_plen, o_best, o_ncig, o_nrun, o_runs, o_cig, o_msa, words;
+};
+#ifdef POA_HOST_EMU
+#define POA_HD static inline
+#else
+#define POA_HD __host__ __device__ __forceinline__
+#endif
+POA_HD void wire_layout(WireLayout &W, long long n, long long n_seq, long long in_tot, long long out_tot, long long aln_tot, long long run_tot,
+                       long long cig_tot, long long msa_bytes, int format) {
+    const long long ew = format == WIRE_WIDE ? 4 : 2;
+    long long o = 0;
+    W.o_base = o; o += (n + 3) >> 2;
+    W.o_aln_n = o; o += (n + 3) >> 2;
+    W.o_in_n = o; o += (n * ew + 3) >> 2;
+    W.o_out_n = o; o += (n * ew + 3) >> 2;
+    W.o_in_id = o; o += (in_tot * ew + 3) >> 2;
+    W.o_in_w = o; o += (in_tot * ew + 3) >> 2;
+    W.o_out_id = o; o += (out_tot * ew + 3) >> 2;
+    W.o_out_w = o; o += (out_tot * ew + 3) >> 2;
+    W.o_aln_id = o; o += (aln_tot * ew + 3) >> 2;
+    W.o_plen = o; o += n_seq;
+    W.o_best = o; o += n_seq;
+    W.o_ncig = o; o += n_seq;
+    W.o_nrun = o; o += n_seq + 1;            // runs per read, then of the consensus path
+    W.o_runs = o; o += (run_tot * 2 * ew + 3) >> 2;  // (first node id, position) per run
+    W.o_cig = o; o += 2 * cig_tot;
+    W.o_msa = o; o += (msa_bytes + 3) >> 2;
+    W.words = o;
+}
 // phase cycle counters
 enum { PH_ROWS = 0, PH_FILL, PH_BT, PH_FUSE, PH_TOPO, PH_FINAL, PH_TOTAL, PH_SPARE, PH_N };
 
@@ -141,7 +188,7 @@ struct WsLayout {
     long long o_base, o_aln_n, o_aln, o_in_off, o_in_n, o_out_off, o_out_n, o_pool_id, o_pool_w, o_pool_row;
     long long o_idx2id, o_id2idx, o_remain, o_tmp0, o_tmp1, o_tmp2, o_tmp3;
     long long o_rowinfo, o_rowmeta, o_rbase, o_rr, o_mplr, o_mprr;
-    long long o_cig, o_path, o_best, o_ncig, o_plen, o_qp, o_slab;
+    long long o_cig, o_path, o_best, o_ncig, o_plen, o_nrun, o_qp, o_slab;
     long long slab_bytes;
     int nmax;      // node capacity
     int pool_cap;  // edge pool capacity (entries)
@@ -165,6 +212,7 @@ struct Ws {
     int *rr, *mplr, *mprr;
     unsigned long long *cig;
     int *path, *best, *ncig, *plen;
+    int *nrun;   // [2 * (max_seq + 2)]: runs per read path / their exclusive prefix (output stage)
     char *qp;    // query profile of the alignment in flight, chunked layout (poa_fill16.cuh)
     char *slab;
 };
@@ -189,8 +237,10 @@ struct Shared {
 
 #ifdef POA_HOST_EMU
 static inline int p_ctz32(unsigned x) { return __builtin_ctz(x); }
+static inline int poa_popc(unsigned x) { return __builtin_popcount(x); }
 #else
 POA_D int p_ctz32(unsigned x) { return __ffs((int)x) - 1; }
+POA_D int poa_popc(unsigned x) { return __popc(x); }
 #endif
 POA_D int imax(int a, int b) { return a > b ? a : b; }
 POA_D int imin(int a, int b) { return a < b ? a : b; }
@@ -538,7 +588,9 @@ POA_DN void build_rows(Shared &sh, int qlen, int banded) {
             w.rbase[i] = (uint8_t)bs[u];
             w.tmp0[i] = fpid[u] >= 0 ? fpid[u] : 0;  // backtrack(), fill_p16(): row of the first predecessor
             if (in[u] > 0) w.pool_row[ioff[u]] = fpid[u];
-            for (int k = 1; k < in[u]; ++k) w.pool_row[ioff[u] + k] = w.id2idx[w.pool_id[ioff[u] + k]];
+            int sp_row = -1;
+            for (int k = 1; k < in[u]; ++k) { const int pr = w.id2idx[w.pool_id[ioff[u] + k]]; w.pool_row[ioff[u] + k] = pr; if (k == 1) sp_row = pr; }
+            w.tmp1[i] = sp_row;  // fill_p16(): row of the second predecessor (prefetched with the row's metadata), -1 if none
             for (int k = 0; k < on[u]; ++k) w.pool_row[ooff[u] + k] = w.id2idx[w.pool_id[ooff[u] + k]];
             if (banded) {
                 w.rr[i] = qlen - rm[u];       // qlen - (remain[v] - remain[sink] - 1), remain[sink] = -1
@@ -1365,7 +1417,7 @@ POA_D void ws_bind(Ws &w, char *b, const WsLayout &L) {
     w.tmp0 = (int *)(b + L.o_tmp0); w.tmp1 = (int *)(b + L.o_tmp1); w.tmp2 = (int *)(b + L.o_tmp2); w.tmp3 = (int *)(b + L.o_tmp3);
     w.rowinfo = (int4 *)(b + L.o_rowinfo); w.rowmeta = (int4 *)(b + L.o_rowmeta); w.rbase = (uint8_t *)(b + L.o_rbase);
     w.rr = (int *)(b + L.o_rr); w.mplr = (int *)(b + L.o_mplr); w.mprr = (int *)(b + L.o_mprr);
-    w.cig = (unsigned long long *)(b + L.o_cig); w.path = (int *)(b + L.o_path); w.best = (int *)(b + L.o_best); w.ncig = (int *)(b + L.o_ncig); w.plen = (int *)(b + L.o_plen);
+    w.cig = (unsigned long long *)(b + L.o_cig); w.path = (int *)(b + L.o_path); w.best = (int *)(b + L.o_best); w.ncig = (int *)(b + L.o_ncig); w.plen = (int *)(b + L.o_plen); w.nrun = (int *)(b + L.o_nrun);
     w.qp = b + L.o_qp; w.slab = b + L.o_slab;
 }
 
@@ -1533,11 +1585,39 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
         for (int v = tid; v < n; v += NT) aln_pre[v] = w.aln_n[v];
         sync_block<NW>();
         const int aln_tot = block_excl_scan<NW>(sh, aln_pre, aln_pre, n, scr);
-        long long path_tot = 0;
-        for (int k = 0; k < n_seq; ++k) path_tot += plen_arr[k];
+        long long path_tot = 0, wsum = 0;
+        int maxlen = 0;
+        for (int k = 0; k < n_seq; ++k) { path_tot += plen_arr[k]; wsum += B.weight[s0 + k]; maxlen = imax(maxlen, B.seq_len[s0 + k]); }
+        const int format = (n < 65536 && wsum < 65536 && maxlen < 65536) ? WIRE_NARROW : WIRE_WIDE;
+        const bool wide = format == WIRE_WIDE;
+        // runs of consecutive node ids per read path (and of the consensus path): a warp walks a path 32 steps at a time
+        int *nrun = w.nrun, *run_off = w.nrun + (n_seq + 2);
+        const int wid_ = tid / POA_WARP, lane_ = tid % POA_WARP;
+        auto path_of = [&](int k, int &len) -> const int * {
+            if (k < n_seq) { len = plen_arr[k]; return w.path + (B.seq_off[s0 + k] - base0); }
+            len = cons_len > 0 ? cons_len : 0; return cons;
+        };
+        for (int k = wid_; k <= n_seq; k += NW) {
+            int len; const int *src = path_of(k, len);
+            int cnt = 0, carry = 0;
+            for (int t0 = 0; t0 < len; t0 += POA_WARP) {
+                const int t = t0 + lane_;
+                const int v = t < len ? src[t] : 0;
+                int pv = poa_shfl_up(v, 1);
+                if (lane_ == 0) pv = carry;
+                cnt += poa_popc(poa_ballot(t < len && (t == 0 || v != pv + 1)));
+                carry = poa_shfl(v, POA_WARP - 1);
+            }
+            if (lane_ == 0) nrun[k] = cnt;
+        }
+        sync_block<NW>();
+        if (tid == 0) { int a = 0; for (int k = 0; k <= n_seq; ++k) { run_off[k] = a; a += nrun[k]; } run_off[n_seq + 1] = a; }
+        sync_block<NW>();
+        const long long run_tot = run_off[n_seq + 1];
         const long long msa_bytes = (long long)msa_rows * (msa_len > 0 ? msa_len : 0);
-        const long long words = 4LL * n + 2LL * in_tot + 2LL * out_tot + aln_tot + n_seq + path_tot + (cons_len > 0 ? cons_len : 0)
-                              + 2LL * n_seq + 2LL * cig_tot + (msa_bytes + 3) / 4;
+        WireLayout WL;
+        wire_layout(WL, n, n_seq, in_tot, out_tot, aln_tot, run_tot, cig_tot, msa_bytes, format);
+        const long long words = WL.words;
         if (tid == 0) {
             unsigned long long off = poa_atomic_add(O.arena_used, (unsigned long long)words);
             if (off + (unsigned long long)words > O.arena_cap) {
@@ -1551,39 +1631,62 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
         if (status == ST_OK) {
             const unsigned long long off = (unsigned long long)(unsigned)sh.bcast[0] | ((unsigned long long)(unsigned)sh.bcast[1] << 32);
             int *o = O.arena + off;
-            int *o_base = o, *o_in_n = o_base + n, *o_in_id = o_in_n + n, *o_in_w = o_in_id + in_tot;
-            int *o_out_n = o_in_w + in_tot, *o_out_id = o_out_n + n, *o_out_w = o_out_id + out_tot;
-            int *o_aln_n = o_out_w + out_tot, *o_aln_id = o_aln_n + n;
-            int *o_plen = o_aln_id + aln_tot, *o_path = o_plen + n_seq, *o_cons = o_path + path_tot;
-            int *o_best = o_cons + (cons_len > 0 ? cons_len : 0), *o_ncig = o_best + n_seq, *o_cig = o_ncig + n_seq;
-            uint8_t *o_msa = (uint8_t *)(o_cig + 2LL * cig_tot);
+            uint8_t *o_base = (uint8_t *)(o + WL.o_base), *o_aln_n = (uint8_t *)(o + WL.o_aln_n);
+            int *o_in_n = o + WL.o_in_n, *o_out_n = o + WL.o_out_n, *o_in_id = o + WL.o_in_id, *o_in_w = o + WL.o_in_w;
+            int *o_out_id = o + WL.o_out_id, *o_out_w = o + WL.o_out_w, *o_aln_id = o + WL.o_aln_id;
+            int *o_plen = o + WL.o_plen, *o_best = o + WL.o_best, *o_ncig = o + WL.o_ncig, *o_nrun = o + WL.o_nrun, *o_runs = o + WL.o_runs, *o_cig = o + WL.o_cig;
+            uint8_t *o_msa = (uint8_t *)(o + WL.o_msa);
+            // narrow or wide store of element idx of a section
+            auto put = [&](int *sec, long long idx, int val) {
+                if (wide) sec[idx] = val; else reinterpret_cast<unsigned short *>(sec)[idx] = (unsigned short)val;
+            };
+            // sections are padded to whole words: clear the pad bytes so that equal results are equal byte strings
+            if (tid == 0) {
+                if (n & 3) { o[WL.o_base + (n >> 2)] = 0; o[WL.o_aln_n + (n >> 2)] = 0; }
+                if (!wide) {
+                    if (n & 1) { o_in_n[n >> 1] = 0; o_out_n[n >> 1] = 0; }
+                    if (in_tot & 1) { o_in_id[in_tot >> 1] = 0; o_in_w[in_tot >> 1] = 0; }
+                    if (out_tot & 1) { o_out_id[out_tot >> 1] = 0; o_out_w[out_tot >> 1] = 0; }
+                    if (aln_tot & 1) o_aln_id[aln_tot >> 1] = 0;
+                }
+            }
+            sync_block<NW>();
             for (int v = tid; v < n; v += NT) {
                 o_base[v] = w.base[v];
                 int cn = w.in_n[v], off2 = w.in_off[v], dst = in_pre[v];
-                o_in_n[v] = cn;
-                for (int k = 0; k < cn; ++k) { o_in_id[dst + k] = w.pool_id[off2 + k]; o_in_w[dst + k] = w.pool_w[off2 + k]; }
+                put(o_in_n, v, cn);
+                for (int k = 0; k < cn; ++k) { put(o_in_id, dst + k, w.pool_id[off2 + k]); put(o_in_w, dst + k, w.pool_w[off2 + k]); }
                 cn = w.out_n[v]; off2 = w.out_off[v]; dst = out_pre[v];
-                o_out_n[v] = cn;
-                for (int k = 0; k < cn; ++k) { o_out_id[dst + k] = w.pool_id[off2 + k]; o_out_w[dst + k] = w.pool_w[off2 + k]; }
+                put(o_out_n, v, cn);
+                for (int k = 0; k < cn; ++k) { put(o_out_id, dst + k, w.pool_id[off2 + k]); put(o_out_w, dst + k, w.pool_w[off2 + k]); }
                 cn = w.aln_n[v]; dst = aln_pre[v];
-                o_aln_n[v] = cn;
-                for (int k = 0; k < cn; ++k) o_aln_id[dst + k] = w.aln[4 * v + k];
+                o_aln_n[v] = (uint8_t)cn;
+                for (int k = 0; k < cn; ++k) put(o_aln_id, dst + k, w.aln[4 * v + k]);
             }
-            // per-read paths (only reads that were added have a path)
-            {
-                long long dst = 0;
-                for (int k = 0; k < n_seq; ++k) {
-                    const int pl = plen_arr[k];
-                    const int *src = w.path + (B.seq_off[s0 + k] - base0);
-                    for (int t = tid; t < pl; t += NT) o_path[dst + t] = src[t];
-                    dst += pl;
+            // per-read paths and the consensus path as runs (only reads that were added have a path)
+            for (int k = wid_; k <= n_seq; k += NW) {
+                int len; const int *src = path_of(k, len);
+                int at = run_off[k], carry = 0;
+                for (int t0 = 0; t0 < len; t0 += POA_WARP) {
+                    const int t = t0 + lane_;
+                    const int v = t < len ? src[t] : 0;
+                    int pv = poa_shfl_up(v, 1);
+                    if (lane_ == 0) pv = carry;
+                    const bool head = t < len && (t == 0 || v != pv + 1);
+                    const unsigned hm = poa_ballot(head);
+                    if (head) {
+                        const long long r = at + poa_popc(hm & ((1u << lane_) - 1u));
+                        put(o_runs, 2 * r, v); put(o_runs, 2 * r + 1, t);
+                    }
+                    at += poa_popc(hm);
+                    carry = poa_shfl(v, POA_WARP - 1);
                 }
-                for (int k = tid; k < n_seq; k += NT) { o_plen[k] = plen_arr[k]; o_best[k] = w.best[k]; o_ncig[k] = P.emit_cigar ? w.ncig[k] : 0; }
+                if (lane_ == 0) o_nrun[k] = nrun[k];
             }
-            for (int t = tid; t < cons_len; t += NT) o_cons[t] = cons[t];
+            for (int k = tid; k < n_seq; k += NT) { o_plen[k] = plen_arr[k]; o_best[k] = w.best[k]; o_ncig[k] = P.emit_cigar ? w.ncig[k] : 0; }
             for (int t = tid; t < cig_tot; t += NT) { unsigned long long c = w.cig[t]; o_cig[2 * t] = (int)(unsigned)(c & 0xffffffffull); o_cig[2 * t + 1] = (int)(unsigned)(c >> 32); }
             if (msa_bytes > 0) {  // abpoa_output.c:149-192
-                for (long long t = tid; t < msa_bytes; t += NT) o_msa[t] = 5;
+                for (long long t = tid; t < ((msa_bytes + 3) & ~3LL); t += NT) o_msa[t] = t < msa_bytes ? 5 : 0;
                 sync_block<NW>();
                 for (int k = 0; k < n_seq; ++k) {
                     const int pl = plen_arr[k];
@@ -1598,6 +1701,7 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
                 hdr[H_OFF_LO] = sh.bcast[0]; hdr[H_OFF_HI] = sh.bcast[1];
                 hdr[H_INBAND_LO] = (int)(unsigned)(sh.inband & 0xffffffffll); hdr[H_INBAND_HI] = (int)(unsigned)((unsigned long long)sh.inband >> 32);
                 hdr[H_EDGE_LO] = (int)(unsigned)(sh.edge_rows & 0xffffffffll); hdr[H_EDGE_HI] = (int)(unsigned)((unsigned long long)sh.edge_rows >> 32);
+                hdr[H_BODY_WORDS] = (int)words; hdr[H_FORMAT] = format; hdr[H_RUN_TOT] = (int)run_tot;
             }
         }
     }

@@ -153,6 +153,24 @@ POA_D bool p16_eligible(const DevParams &P, int qlen) {
     return P.p16_ok && (long long)qlen * P.match + (long long)emax * (P16_CW + 8) + 64 <= 32767;
 }
 
+// Compile-time chunk count of one pass of the row loop (fill_p16): generic lambdas take it as a value of this type.
+template <int N> struct p16_n { static constexpr int value = N; };
+#ifndef POA_P16_ILP
+#define POA_P16_ILP 2  // chunks of a row evaluated side by side by one warp (1 = the round-1 loop shape)
+#endif
+
+// fill_p16: one warp, rows in index order, the chunks of a row taken POA_P16_ILP at a time.
+//
+// Why several chunks at once: a row is one dependent chain per chunk -- predecessor loads, the shifted match operand, a
+// 4-cell recurrence per lane, a five-round shuffle scan, the fix-up -- and consecutive rows depend on each other through
+// the adaptive band (a row's band needs the arg-max columns of the whole previous row), so a warp that walks one chunk at
+// a time has nothing independent to issue while a shuffle or a load is in flight (round 1: 52 % of issue slots used with
+// every resident warp stalled on its own chain).  The chunks of ONE row, however, are independent up to the scalar F carry
+// that enters a chunk from its left neighbour, and that carry is applied AFTER the lane scan.  So the row loop evaluates
+// N chunks per pass as straight-line code: N sets of predecessor loads, N x 8 lane chains, N x 2 shuffle scans in flight
+// together, then the carry chain through the N scan totals (two instructions per chunk), then N fix-ups and stores.
+// Everything per chunk is branch-free (out-of-range predecessor chunks read as inf_min through predicated loads) so the
+// compiler can interleave the N instruction streams.
 template <int NW, bool LOCAL>
 POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, long long slab_bytes) {
     Ws &w = sh.ws;
@@ -176,11 +194,13 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
     const int *const pool_row = w.pool_row, *const rr = w.rr;
     int *const mplr = w.mplr, *const mprr = w.mprr;
     const uint8_t *const rbase = w.rbase;
+    const int *const fp = w.tmp0;  // build_rows(): row of the first predecessor
+    const int *const sp = w.tmp1;  // build_rows(): row of the second predecessor, -1 if there is none
 #ifndef POA_HOST_EMU
     __builtin_assume(__isGlobal(slab)); __builtin_assume(__isGlobal(qp)); __builtin_assume(__isGlobal(rowinfo));
     __builtin_assume(__isGlobal(rowmeta)); __builtin_assume(__isGlobal(pool_row)); __builtin_assume(__isGlobal(rr));
     __builtin_assume(__isGlobal(mplr)); __builtin_assume(__isGlobal(mprr)); __builtin_assume(__isGlobal(rbase));
-    __builtin_assume(__isGlobal(q));
+    __builtin_assume(__isGlobal(q)); __builtin_assume(__isGlobal(fp)); __builtin_assume(__isGlobal(sp));
 #endif
     const long long slab_units = slab_bytes / P16_CPB;
     long long used = 0, inband = 0, edge_rows = 0;
@@ -256,16 +276,13 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
     // % P16_SMCH), so the common "predecessor = row just evaluated" read never leaves the SM.
     const ring_ptr_t ring = ring_base(sh.ring, lane);
     bool prev_res = false;  // is the previous row in the ring? (row 0 is not; rows wider than the ring are not)
-    const int *const fp = w.tmp0;  // build_rows(): row of the first predecessor
-#ifndef POA_HOST_EMU
-    __builtin_assume(__isGlobal(fp));
-#endif
-    // Metadata of the next row is gathered into shared memory one row ahead by cp.async, one item per lane
-    // (its first predecessor's number two ahead, so that predecessor's row descriptor can be fetched one ahead too).
+    // Metadata of the next row is gathered into shared memory one row ahead by cp.async, one item per lane (the numbers
+    // of its first and second predecessor two ahead, so that those rows' descriptors can be fetched one ahead too).
     // Layout of a 128-byte slot: +0 rowinfo, +16 rowmeta[first pred], +32 base word, +36 fp two ahead, +40 rr,
-    // +48 mplr window, +64 mprr window (16-byte windows read at L2: they are updated by reductions).
+    // +48 mplr window, +64 mprr window (16-byte windows read at L2: they are updated by reductions),
+    // +80 rowmeta[second pred], +96 sp two ahead.
     const ring_ptr_t sm = ring_base(sh.ring, 0);
-    // each of lanes 0..6 owns one item: its array, element size and slot offset are fixed for the whole alignment
+    // each of lanes 0..8 owns one item: its array, element size and slot offset are fixed for the whole alignment
     const char *gsrc = nullptr; unsigned gdst = 0; int gkind = 0;  // kind: 1 = 16 bytes, 2 = 16 bytes at L2, 3 = 4 bytes
     if (lane == 0) { gsrc = (const char *)rowinfo; gdst = 0; gkind = 1; }
     else if (lane == 1) { gsrc = (const char *)rowmeta; gdst = 16; gkind = 1; }
@@ -274,94 +291,62 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
     else if (lane == 4 && wb >= 0) { gsrc = (const char *)rr; gdst = 40; gkind = 3; }
     else if (lane == 5 && wb >= 0) { gsrc = (const char *)mplr; gdst = 48; gkind = 2; }
     else if (lane == 6 && wb >= 0) { gsrc = (const char *)mprr; gdst = 64; gkind = 2; }
-    auto gather = [&](const int n1, const int np0_n1, const int cur) {  // row n1 into its slot; `cur`: row being evaluated
+    else if (lane == 7) { gsrc = (const char *)rowmeta; gdst = 80; gkind = 1; }
+    else if (lane == 8) { gsrc = (const char *)sp; gdst = 96; gkind = 3; }
+    auto gather = [&](const int n1, const int np0_n1, const int nsp_n1, const int cur) {  // row n1 into its slot; `cur`: row being evaluated
         if (n1 >= rows) return;
         const unsigned slot = P16_META_OFF + (unsigned)(n1 & 1) * 128 + gdst;
-        // element index of this lane's item: the row itself, its first predecessor (lane 1), the row after (lane 3),
-        // or the 4-element window holding it (byte / reduction-updated arrays)
+        // element index of this lane's item: the row itself, one of its first two predecessors (lanes 1, 7), the row after
+        // (lanes 3, 8), or the 4-element window holding it (byte / reduction-updated arrays)
         int idx = n1;
-        if (lane == 1) idx = np0_n1; else if (lane == 3) idx = n1 + 1;
-#ifdef POA_Q_AHEAD
-        if (lane == 2) idx = n1 + 1;  // base of the row after n1: its profile chunks are staged while n1 is still being evaluated
-        const bool live = lane == 1 ? np0_n1 < cur : ((lane == 3 || lane == 2) ? n1 + 1 < rows : true);
-#else
-        const bool live = lane == 1 ? np0_n1 < cur : (lane == 3 ? n1 + 1 < rows : true);
-#endif
+        bool live = true;
+        if (lane == 1) { idx = np0_n1; live = np0_n1 < cur; }
+        else if (lane == 7) { idx = nsp_n1; live = nsp_n1 >= 0 && nsp_n1 < cur; }
+        else if (lane == 3 || lane == 8) { idx = n1 + 1; live = n1 + 1 < rows; }
         if (gkind == 1 && live) cpa16(sm, slot, gsrc + (size_t)(unsigned)idx * 16, false);
         else if (gkind == 2) cpa16(sm, slot, gsrc + (size_t)(unsigned)(idx & ~3) * 4, true);
         else if (gkind == 3 && live) cpa4(sm, slot, gsrc + (lane == 2 ? (size_t)(unsigned)(idx & ~3) : (size_t)(unsigned)idx * 4));
     };
-    int np0 = fp[rows > 1 ? 1 : 0];  // first predecessor of the row about to be evaluated
-    gather(1, np0, 1);
+    int np0 = fp[rows > 1 ? 1 : 0];   // first predecessor of the row about to be evaluated
+    int nsp = rows > 1 ? sp[1] : -1;  // its second predecessor, or -1
+    gather(1, np0, nsp, 1);
     cpa_commit();
-#ifdef POA_Q_AHEAD
-    // Profile chunks are staged ONE ROW AHEAD: row i+1's copies are issued when row i's chunk loop ends (its base arrives with
-    // row i's metadata, the chunk range is guessed from row i's band), so they have the whole row boundary to land.  cp.async
-    // groups alternate G (metadata of the next row, committed at the top of a row) and Q (profile of the next row, committed
-    // after the chunk loop; empty after the last row): every wait below leaves exactly the youngest group in flight.
-    int rb_next = rows > 1 ? (int)rbase[1] : 0, scb_next = 0, sce_next = -1;
-    auto stage_profile = [&](int rbx, const int4 &pmeta) {
-        scb_next = pmeta.y >> 8; sce_next = imin(imin((pmeta.z >> 8) + 1, scb_next + P16_QCH - 1), nchq - 1);
-        const char *qg = qp + (size_t)(unsigned)(rbx * nchq + scb_next) * P16_CPB + lane * 16;
-        for (int k = 0; k <= sce_next - scb_next; ++k) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qg + (size_t)k * P16_CPB, false);
-    };
-    if (rows > 1) stage_profile(rb_next, prev_meta);
-    cpa_commit();
-#endif
 
     // ---- rows in index order (abpoa_align_simd.c:1205-1221)
     for (int i = 1; i < rows; ++i) {
-#ifdef POA_Q_AHEAD
-        cpa_wait_pending(1);  // this row's metadata (G) has landed; its profile (Q, younger) may still be in flight
-#else
         cpa_wait_pending(0);
-#endif
         sync_block<NW>();  // the slot was filled by other lanes' copies
         const unsigned slot = P16_META_OFF + (unsigned)(i & 1) * 128;
-        const uint4 ri_u = ring_ld(sm, slot), npm_u = ring_ld(sm, slot + 16);
+        const uint4 ri_u = ring_ld(sm, slot), npm_u = ring_ld(sm, slot + 16), spm_u = ring_ld(sm, slot + 80);
         const int4 ri = poa_make_int4((int)ri_u.x, (int)ri_u.y, (int)ri_u.z, (int)ri_u.w);  // {in_off, in_n, out_off, out_n}
-        const int4 npm = poa_make_int4((int)npm_u.x, (int)npm_u.y, (int)npm_u.z, (int)npm_u.w);
-#ifdef POA_Q_AHEAD
-        const int rb = rb_next, p0 = np0;
-        rb_next = (ring_ld32(sm, slot + 32) >> (8 * ((i + 1) & 3))) & 0xff;  // base of row i + 1 (garbage after the last row: unused)
-#else
-        const int rb = (ring_ld32(sm, slot + 32) >> (8 * (i & 3))) & 0xff, p0 = np0;
-#endif
+        const int rb = (ring_ld32(sm, slot + 32) >> (8 * (i & 3))) & 0xff, p0 = np0, s0 = nsp;
         const int nnp0 = i + 1 < rows ? ring_ld32(sm, slot + 36) : 0;
+        const int nnsp = i + 1 < rows ? ring_ld32(sm, slot + 96) : -1;
         const int r = ring_ld32(sm, slot + 40);
         int ml = ring_ld32(sm, slot + 48 + 4 * (i & 3)), mr = ring_ld32(sm, slot + 64 + 4 * (i & 3));
-        // first predecessor's row descriptor: from registers when it is the row just evaluated (the common case)
-        const int4 pm0 = p0 == i - 1 ? prev_meta : npm;
+        // the first two predecessors' row descriptors: from registers when it is the row just evaluated (the common case)
+        const int4 pm0 = p0 == i - 1 ? prev_meta : poa_make_int4((int)npm_u.x, (int)npm_u.y, (int)npm_u.z, (int)npm_u.w);
+        const int4 pm1 = s0 == i - 1 ? prev_meta : poa_make_int4((int)spm_u.x, (int)spm_u.y, (int)spm_u.z, (int)spm_u.w);
         // next row's metadata; its band inputs miss only this row's contribution, forwarded below
-        gather(i + 1, nnp0, i);
+        gather(i + 1, nnp0, nnsp, i);
         // rows this row hands its arg-max columns to (one per lane; staged now, used after the last chunk)
         if (lane < ri.w) cpa4(sm, P16_META_OFF + 256 + lane * 4, &pool_row[ri.z + lane]);
         cpa_commit();
-        np0 = nnp0;
+        np0 = nnp0; nsp = nnsp;
         // profile chunks of this row: staged now for the chunk range the previous row covered plus one (bands move
         // slowly), so the copies overlap the band computation below; corrected after it if the guess was wrong
-#ifdef POA_Q_AHEAD
-        int scb = scb_next, sce = sce_next;  // staged when the previous row's chunk loop ended
-        int qpend = 1;                       // groups that may stay in flight when the first chunk reads the profile: this row's G
-#else
         int scb = prev_meta.y >> 8, sce = imin(imin((prev_meta.z >> 8) + 1, scb + P16_QCH - 1), nchq - 1);
         {
             const char *qg = qp + (size_t)(unsigned)(rb * nchq + scb) * P16_CPB + lane * 16;
             for (int k = 0; k <= sce - scb; ++k) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qg + (size_t)k * P16_CPB, false);
             cpa_commit();
         }
-        const int qpend = 0;
-#endif
-        // second predecessor's row descriptor, once per row (every chunk needs it; a third one is rare)
-        int pk1 = -1;
-        int4 pm1 = pm0;
-        if (ri.y > 1) { pk1 = pool_row[ri.x + 1]; pm1 = rowmeta[pk1]; }
         int beg, end;
         if (wb < 0) { beg = 0; end = qlen; }
         else {  // abpoa_align.h:34-35, abpoa_align_simd.c:946-960
             int min_pre_beg = pm0.y;
             bool from_prev = p0 == i - 1;
-            if (ri.y > 1) { from_prev |= pk1 == i - 1; min_pre_beg = imin(min_pre_beg, pm1.y); }
+            if (ri.y > 1) { from_prev |= s0 == i - 1; min_pre_beg = imin(min_pre_beg, pm1.y); }
             for (int k = 2; k < ri.y; ++k) {
                 const int pk = pool_row[ri.x + k];
                 from_prev |= pk == i - 1;
@@ -385,20 +370,15 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
         unsigned carry2 = p_pack(f0_2 + e2 * (beg - cb * P16_CW), f0_2 + e2 * (beg - cb * P16_CW));
         int rmx = INT_MIN, fc = cb, lc = cb;  // row maximum, first / last chunk attaining it
         const char *qrow = qp + (size_t)(unsigned)(rb * nchq) * P16_CPB + lane * 16;
-        int ring_last = inf_min;
         const bool cur_res = nch <= P16_SMCH;
 
-        // running pointers (one 64-bit add per chunk instead of one multiply per access)
-        // the row's profile chunks are staged in shared memory, one cp.async group per chunk
+        // the row's profile chunks are staged in shared memory
         bool qst = cb >= scb && ce <= sce;
         if (!qst && nch <= P16_QCH) {  // wrong guess (rare): let the speculative copies land, then stage the exact range over them
             cpa_wait_pending(0);
             for (int k = 0; k < nch; ++k) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qrow + (size_t)(unsigned)(cb + k) * P16_CPB, false);
             cpa_commit();
             scb = cb; qst = true;
-#ifdef POA_Q_AHEAD
-            qpend = 0;  // the corrected copies are now the youngest group
-#endif
         }
         char *dst = slab_lane + (size_t)roff * P16_CPB;
         const size_t pstride = (size_t)(unsigned)nch * P16_CPB;
@@ -407,156 +387,206 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
         const unsigned pn0 = (unsigned)(pce0 - pcb0 + 1);
         const bool ring0 = prev_res && p0 == i - 1;
         unsigned rslot = (unsigned)(cb % P16_SMCH) * (3 * P16_CPB);  // ring slot of chunk c: (c % P16_SMCH) chunk-plane triples in
-#pragma unroll 1
-        for (int c = cb; c <= ce; ++c) {
-            const int c0 = c * P16_CW;
-            // first predecessor: its chunk c (H shifted one column right for M, E1, E2 as they are), or nothing
-            unsigned M0, M1, M2, M3, A0, A1, A2, A3, B0, B1, B2, B3;
-            {
+        // H of the first predecessor at the column just left of the chunk about to be evaluated (lane 0's match operand);
+        // after a chunk it is simply the last cell of the predecessor chunk just read (inf_min if that was out of range)
+        int plast = inf_min;
+        if (cb > pcb0 && cb <= pce0 + 1) plast = *reinterpret_cast<const short *>(slab + (size_t)((unsigned)pm0.x + (unsigned)(cb - pcb0)) * P16_CPB - 2);
+        bool first_pass = true;
+
+        auto pass = [&](auto nc, const int c) {  // chunks c .. c + N - 1 of row i, side by side
+            constexpr int N = decltype(nc)::value;
+            unsigned M[N][4], A[N][4], B[N][4], H[N][4];
+            // ---- first predecessor: its chunk (H shifted one column right for M, E1, E2 as they are), or inf_min
+#pragma unroll
+            for (int u = 0; u < N; ++u) {
+                const int cu = c + u;
                 uint4 h, a, b;
-                if (c >= pcb0 && c <= pce0) {
+                h.x = h.y = h.z = h.w = INFP; a = h; b = h;
+                if (cu >= pcb0 && cu <= pce0) {
                     if (ring0) {
-                        h = ring_ld(ring, rslot); a = ring_ld(ring, rslot + P16_CPB); b = ring_ld(ring, rslot + 2 * P16_CPB);
+                        const unsigned rs = rslot + (unsigned)u * (3 * P16_CPB), rsw = rs >= P16_SMCH * (3 * P16_CPB) ? rs - P16_SMCH * (3 * P16_CPB) : rs;
+                        h = ring_ld(ring, rsw); a = ring_ld(ring, rsw + P16_CPB); b = ring_ld(ring, rsw + 2 * P16_CPB);
                     } else {
-                        const unsigned idx = (unsigned)pm0.x + (unsigned)(c - pcb0);
+                        const unsigned idx = (unsigned)pm0.x + (unsigned)(cu - pcb0);
                         h = p16_ld(slab_lane + (size_t)idx * P16_CPB);
                         a = p16_ld(slab_lane + (size_t)(idx + pn0) * P16_CPB);
                         b = p16_ld(slab_lane + (size_t)(idx + 2 * pn0) * P16_CPB);
                     }
-                } else {
-                    h.x = h.y = h.z = h.w = INFP; a = h; b = h;
-                }
-                int prevlast = inf_min;  // H_p[c0 - 1]: the last halfword of the previous chunk-plane
-                if (c > pcb0 && c <= pce0 + 1) {
-                    if (ring0 && c > cb) prevlast = ring_last;  // that chunk was read one iteration ago
-                    else prevlast = *reinterpret_cast<const short *>(slab + (size_t)((unsigned)pm0.x + (unsigned)(c - pcb0)) * P16_CPB - 2);
                 }
                 const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
-                if (ring0) ring_last = p_hi(rot);  // lane 0: last cell of this chunk of the previous row (only read back if it was one)
-                M0 = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot; M1 = h.x; M2 = h.y; M3 = h.z;
-                A0 = a.x; A1 = a.y; A2 = a.z; A3 = a.w;
-                B0 = b.x; B1 = b.y; B2 = b.z; B3 = b.w;
+                M[u][0] = lane == 0 ? p_pack(plast, p_lo(rot)) : rot; M[u][1] = h.x; M[u][2] = h.y; M[u][3] = h.z;
+                plast = p_hi(rot);  // lane 0: the predecessor's last cell of this chunk (inf_min when the chunk was out of its range)
+                A[u][0] = a.x; A[u][1] = a.y; A[u][2] = a.z; A[u][3] = a.w;
+                B[u][0] = b.x; B[u][1] = b.y; B[u][2] = b.z; B[u][3] = b.w;
             }
+            // ---- further predecessors in in_id order (abpoa_align_simd.c:966-1029)
 #pragma unroll 1
-            for (int k = 1; k < ri.y; ++k) {  // further predecessors in in_id order (abpoa_align_simd.c:966-1029)
-                int pk = pk1;
+            for (int k = 1; k < ri.y; ++k) {
+                int pk = s0;
                 int4 pm = pm1;
                 if (k > 1) { pk = pool_row[ri.x + k]; pm = rowmeta[pk]; }
                 const int pcb = pm.y >> 8, pce = pm.z >> 8;
-                if (c >= pcb && c <= pce + 1) {
-                    const unsigned pn_ = (unsigned)(pce - pcb + 1), idx = (unsigned)pm.x + (unsigned)(c - pcb);
-                    const bool in_ring = prev_res && pk == i - 1;
-                    int prevlast = inf_min;
-                    if (c > pcb) {
-                        if (in_ring && c > cb) prevlast = ring_last;
-                        else prevlast = *reinterpret_cast<const short *>(slab + (size_t)idx * P16_CPB - 2);
-                    }
-                    if (c <= pce) {
-                        uint4 h, a, b;
+                if (c + N - 1 < pcb || c > pce + 1) continue;
+                const unsigned pn_ = (unsigned)(pce - pcb + 1);
+                const bool in_ring = prev_res && pk == i - 1;
+                int pl = inf_min;  // this predecessor's H at the column left of chunk c
+                if (c > pcb && c <= pce + 1) pl = *reinterpret_cast<const short *>(slab + (size_t)((unsigned)pm.x + (unsigned)(c - pcb)) * P16_CPB - 2);
+#pragma unroll
+                for (int u = 0; u < N; ++u) {
+                    const int cu = c + u;
+                    uint4 h, a, b;
+                    h.x = h.y = h.z = h.w = INFP; a = h; b = h;
+                    if (cu >= pcb && cu <= pce) {
                         if (in_ring) {
-                            h = ring_ld(ring, rslot); a = ring_ld(ring, rslot + P16_CPB); b = ring_ld(ring, rslot + 2 * P16_CPB);
+                            const unsigned rs = rslot + (unsigned)u * (3 * P16_CPB), rsw = rs >= P16_SMCH * (3 * P16_CPB) ? rs - P16_SMCH * (3 * P16_CPB) : rs;
+                            h = ring_ld(ring, rsw); a = ring_ld(ring, rsw + P16_CPB); b = ring_ld(ring, rsw + 2 * P16_CPB);
                         } else {
+                            const unsigned idx = (unsigned)pm.x + (unsigned)(cu - pcb);
                             h = p16_ld(slab_lane + (size_t)idx * P16_CPB);
                             a = p16_ld(slab_lane + (size_t)(idx + pn_) * P16_CPB);
                             b = p16_ld(slab_lane + (size_t)(idx + 2 * pn_) * P16_CPB);
                         }
-                        const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
-                        const unsigned s0 = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot;
-                        if (in_ring) ring_last = p_hi(rot);
-                        M0 = p_max(M0, s0); M1 = p_max(M1, h.x); M2 = p_max(M2, h.y); M3 = p_max(M3, h.z);
-                        A0 = p_max(A0, a.x); A1 = p_max(A1, a.y); A2 = p_max(A2, a.z); A3 = p_max(A3, a.w);
-                        B0 = p_max(B0, b.x); B1 = p_max(B1, b.y); B2 = p_max(B2, b.z); B3 = p_max(B3, b.w);
-                    } else if (lane == 0) {
-                        M0 = p_max(M0, p_pack(prevlast, inf_min));
+                    }
+                    const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
+                    const unsigned s0_ = lane == 0 ? p_pack(pl, p_lo(rot)) : rot;
+                    pl = p_hi(rot);
+                    M[u][0] = p_max(M[u][0], s0_); M[u][1] = p_max(M[u][1], h.x); M[u][2] = p_max(M[u][2], h.y); M[u][3] = p_max(M[u][3], h.z);
+                    A[u][0] = p_max(A[u][0], a.x); A[u][1] = p_max(A[u][1], a.y); A[u][2] = p_max(A[u][2], a.z); A[u][3] = p_max(A[u][3], a.w);
+                    B[u][0] = p_max(B[u][0], b.x); B[u][1] = p_max(B[u][1], b.y); B[u][2] = p_max(B[u][2], b.z); B[u][3] = p_max(B[u][3], b.w);
+                }
+            }
+            if (local && c == 0 && lane == 0) M[0][0] = p_max(M[0][0], p_pack(0, inf_min));  // abpoa_align_simd.c:974 (`first` = 0)
+            // ---- H~ = max(M + profile, E1, E2) (abpoa_align_simd.c:1032-1050); the profile chunks are read as late as possible
+            if (qst && first_pass) cpa_wait_pending(0);
+            first_pass = false;
+#pragma unroll
+            for (int u = 0; u < N; ++u) {
+                uint4 qv;
+                if (qst) qv = ring_ld(sm, P16_QBUF_OFF + (unsigned)(c + u - scb) * P16_CPB + lane * 16);
+                else qv = p16_ld(qrow + (size_t)(unsigned)(c + u) * P16_CPB);
+                H[u][0] = p_max3(p_add(M[u][0], qv.x), A[u][0], B[u][0]); H[u][1] = p_max3(p_add(M[u][1], qv.y), A[u][1], B[u][1]);
+                H[u][2] = p_max3(p_add(M[u][2], qv.z), A[u][2], B[u][2]); H[u][3] = p_max3(p_add(M[u][3], qv.w), A[u][3], B[u][3]);
+            }
+            // ---- cells outside [beg,end]: only the row's first and last chunk can hold any
+            const bool bnd = (c == cb && beg > c * P16_CW) || (c + N - 1 == ce && end < (c + N) * P16_CW - 1);
+            unsigned m[N][4];
+#pragma unroll
+            for (int u = 0; u < N; ++u) { m[u][0] = 0; m[u][1] = 0; m[u][2] = 0; m[u][3] = 0; }
+            if (bnd) {
+#pragma unroll
+                for (int u = 0; u < N; ++u) {
+                    if (u != 0 && u != N - 1) continue;  // an inner chunk of the pass is an inner chunk of the row
+                    const int c0 = (c + u) * P16_CW;
+                    const int brel = imax(beg - c0, 0), erel = imin(end - c0, P16_CW - 1);
+                    const unsigned da = p_pack(lane * 4 - brel, 128 + lane * 4 - brel), db = p_pack(erel - lane * 4, erel - 128 - lane * 4);
+                    m[u][0] = p_signmask(p_min(da, db));
+                    m[u][1] = p_signmask(p_min(p_add(da, 0x00010001u), p_add(db, 0xffffffffu)));
+                    m[u][2] = p_signmask(p_min(p_add(da, 0x00020002u), p_add(db, 0xfffefffeu)));
+                    m[u][3] = p_signmask(p_min(p_add(da, 0x00030003u), p_add(db, 0xfffdfffdu)));
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) H[u][x] = (H[u][x] & ~m[u][x]) | (INFP & m[u][x]);
+                }
+            }
+            // ---- horizontal gaps (abpoa_align_simd.c:1052-1059): per-lane chains and the lane-half scans of all N chunks
+            unsigned l[N][3], k_[N][3], g1[N], g2[N];
+#pragma unroll
+            for (int u = 0; u < N; ++u) {
+                l[u][0] = p_add(H[u][0], NOE1); l[u][1] = p_addmax(l[u][0], NE1, p_add(H[u][1], NOE1)); l[u][2] = p_addmax(l[u][1], NE1, p_add(H[u][2], NOE1));
+                const unsigned lout = p_addmax(l[u][2], NE1, p_add(H[u][3], NOE1));
+                k_[u][0] = p_add(H[u][0], NOE2); k_[u][1] = p_addmax(k_[u][0], NE2, p_add(H[u][1], NOE2)); k_[u][2] = p_addmax(k_[u][1], NE2, p_add(H[u][2], NOE2));
+                const unsigned kout = p_addmax(k_[u][2], NE2, p_add(H[u][3], NOE2));
+                g1[u] = p_add(lout, OFF1); g2[u] = p_add(kout, OFF2);
+            }
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+                for (int u = 0; u < N; ++u) {
+                    const unsigned u1 = (unsigned)poa_shfl_up((int)g1[u], d), u2 = (unsigned)poa_shfl_up((int)g2[u], d);
+                    g1[u] = p_max(g1[u], u1); g2[u] = p_max(g2[u], u2);  // lanes < d get their own value back: a no-op
+                }
+            }
+            unsigned x1[N], x2[N], t1[N], t2[N];
+#pragma unroll
+            for (int u = 0; u < N; ++u) {
+                x1[u] = (unsigned)poa_shfl_up((int)g1[u], 1); x2[u] = (unsigned)poa_shfl_up((int)g2[u], 1);
+                t1[u] = (unsigned)poa_shfl((int)g1[u], 31); t2[u] = (unsigned)poa_shfl((int)g2[u], 31);
+                if (lane == 0) { x1[u] = NEGLP; x2[u] = NEGLP; }
+            }
+            // ---- the scalar carry runs through the N scan totals; then fix-up, H, new E (abpoa_align_simd.c:1060-1071), stores
+#pragma unroll
+            for (int u = 0; u < N; ++u) {
+                const unsigned xx1 = p_max3(x1[u], p_lolo(NEGLP, t1[u]), carry1);  // high halves continue after all low halves
+                const unsigned xx2 = p_max3(x2[u], p_lolo(NEGLP, t2[u]), carry2);
+                const unsigned fin1 = p_add(xx1, NOFF1), fin2 = p_add(xx2, NOFF2);
+                carry1 = p_add(p_max3(t1[u], p_swap(t1[u]), carry1), NCW1);
+                carry2 = p_add(p_max3(t2[u], p_swap(t2[u]), carry2), NCW2);
+                const unsigned F10 = fin1, F11 = p_addmax(fin1, NE1, l[u][0]), F12 = p_addmax(fin1, NE1_2, l[u][1]), F13 = p_addmax(fin1, NE1_3, l[u][2]);
+                const unsigned F20 = fin2, F21 = p_addmax(fin2, NE2, k_[u][0]), F22 = p_addmax(fin2, NE2_2, k_[u][1]), F23 = p_addmax(fin2, NE2_3, k_[u][2]);
+                H[u][0] = p_max3(H[u][0], F10, F20); H[u][1] = p_max3(H[u][1], F11, F21); H[u][2] = p_max3(H[u][2], F12, F22); H[u][3] = p_max3(H[u][3], F13, F23);
+                if (local) { H[u][0] = p_max(H[u][0], ZERO); H[u][1] = p_max(H[u][1], ZERO); H[u][2] = p_max(H[u][2], ZERO); H[u][3] = p_max(H[u][3], ZERO); }
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    A[u][x] = p_addmax(A[u][x], NE1, p_add(H[u][x], NOE1));
+                    B[u][x] = p_addmax(B[u][x], NE2, p_add(H[u][x], NOE2));
+                    if (local) { A[u][x] = p_max(A[u][x], ZERO); B[u][x] = p_max(B[u][x], ZERO); }
+                }
+            }
+            if (bnd) {
+#pragma unroll
+                for (int u = 0; u < N; ++u) {
+                    if (u != 0 && u != N - 1) continue;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        H[u][x] = (H[u][x] & ~m[u][x]) | (INFP & m[u][x]);
+                        A[u][x] = (A[u][x] & ~m[u][x]) | (INFP & m[u][x]);
+                        B[u][x] = (B[u][x] & ~m[u][x]) | (INFP & m[u][x]);
                     }
                 }
             }
-            if (local && c == 0 && lane == 0) M0 = p_max(M0, p_pack(0, inf_min));  // abpoa_align_simd.c:974 (`first` = 0)
-            // H~ = max(M + profile, E1, E2) (abpoa_align_simd.c:1032-1050); the profile chunk is read as late as possible
-            uint4 qv;
-            if (qst) { if (c == cb) cpa_wait_pending(qpend); qv = ring_ld(sm, P16_QBUF_OFF + (unsigned)(c - scb) * P16_CPB + lane * 16); }
-            else qv = p16_ld(qrow + (size_t)(unsigned)c * P16_CPB);
-            unsigned H0 = p_max3(p_add(M0, qv.x), A0, B0), H1 = p_max3(p_add(M1, qv.y), A1, B1);
-            unsigned H2 = p_max3(p_add(M2, qv.z), A2, B2), H3 = p_max3(p_add(M3, qv.w), A3, B3);
-            // cells of this chunk outside [beg,end]
-            const bool bnd = (c == cb && beg > c0) || (c == ce && end < c0 + P16_CW - 1);
-            unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-            if (bnd) {
-                const int brel = imax(beg - c0, 0), erel = imin(end - c0, P16_CW - 1);
-                const unsigned da = p_pack(lane * 4 - brel, 128 + lane * 4 - brel), db = p_pack(erel - lane * 4, erel - 128 - lane * 4);
-                m0 = p_signmask(p_min(da, db));
-                m1 = p_signmask(p_min(p_add(da, 0x00010001u), p_add(db, 0xffffffffu)));
-                m2 = p_signmask(p_min(p_add(da, 0x00020002u), p_add(db, 0xfffefffeu)));
-                m3 = p_signmask(p_min(p_add(da, 0x00030003u), p_add(db, 0xfffdfffdu)));
-                H0 = (H0 & ~m0) | (INFP & m0); H1 = (H1 & ~m1) | (INFP & m1);
-                H2 = (H2 & ~m2) | (INFP & m2); H3 = (H3 & ~m3) | (INFP & m3);
-            }
-            // horizontal gaps (abpoa_align_simd.c:1052-1059): per-lane chains, lane-half scan, fix-up
-            unsigned F10, F11, F12, F13, F20, F21, F22, F23;
-            {
-                const unsigned l1 = p_add(H0, NOE1), l2 = p_addmax(l1, NE1, p_add(H1, NOE1)), l3 = p_addmax(l2, NE1, p_add(H2, NOE1));
-                const unsigned lout = p_addmax(l3, NE1, p_add(H3, NOE1));
-                const unsigned k1 = p_add(H0, NOE2), k2 = p_addmax(k1, NE2, p_add(H1, NOE2)), k3 = p_addmax(k2, NE2, p_add(H2, NOE2));
-                const unsigned kout = p_addmax(k3, NE2, p_add(H3, NOE2));
-                unsigned g1 = p_add(lout, OFF1), g2 = p_add(kout, OFF2);
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const unsigned u1 = (unsigned)poa_shfl_up((int)g1, d), u2 = (unsigned)poa_shfl_up((int)g2, d);
-                    g1 = p_max(g1, u1); g2 = p_max(g2, u2);  // lanes < d get their own value back: a no-op
+            for (int u = 0; u < N; ++u) {
+                p16_st(dst, H[u][0], H[u][1], H[u][2], H[u][3]);
+                p16_st(dst + pstride, A[u][0], A[u][1], A[u][2], A[u][3]);
+                p16_st(dst + 2 * pstride, B[u][0], B[u][1], B[u][2], B[u][3]);
+                dst += P16_CPB;
+                if (cur_res) {  // after every predecessor read of this pass: a lane only ever touches its own slices
+                    ring_st(ring, rslot, H[u][0], H[u][1], H[u][2], H[u][3]); ring_st(ring, rslot + P16_CPB, A[u][0], A[u][1], A[u][2], A[u][3]);
+                    ring_st(ring, rslot + 2 * P16_CPB, B[u][0], B[u][1], B[u][2], B[u][3]);
                 }
-                unsigned x1 = (unsigned)poa_shfl_up((int)g1, 1), x2 = (unsigned)poa_shfl_up((int)g2, 1);
-                const unsigned t1 = (unsigned)poa_shfl((int)g1, 31), t2 = (unsigned)poa_shfl((int)g2, 31);
-                if (lane == 0) { x1 = NEGLP; x2 = NEGLP; }
-                x1 = p_max3(x1, p_lolo(NEGLP, t1), carry1);  // high halves continue after all low halves
-                x2 = p_max3(x2, p_lolo(NEGLP, t2), carry2);
-                const unsigned fin1 = p_add(x1, NOFF1), fin2 = p_add(x2, NOFF2);
-                carry1 = p_add(p_max3(t1, p_swap(t1), carry1), NCW1);
-                carry2 = p_add(p_max3(t2, p_swap(t2), carry2), NCW2);
-                F10 = fin1; F11 = p_addmax(fin1, NE1, l1); F12 = p_addmax(fin1, NE1_2, l2); F13 = p_addmax(fin1, NE1_3, l3);
-                F20 = fin2; F21 = p_addmax(fin2, NE2, k1); F22 = p_addmax(fin2, NE2_2, k2); F23 = p_addmax(fin2, NE2_3, k3);
+                rslot = rslot == (P16_SMCH - 1) * (3 * P16_CPB) ? 0u : rslot + 3 * P16_CPB;
             }
-            // H, new E (abpoa_align_simd.c:1060-1071)
-            H0 = p_max3(H0, F10, F20); H1 = p_max3(H1, F11, F21); H2 = p_max3(H2, F12, F22); H3 = p_max3(H3, F13, F23);
-            if (local) { H0 = p_max(H0, ZERO); H1 = p_max(H1, ZERO); H2 = p_max(H2, ZERO); H3 = p_max(H3, ZERO); }
-            A0 = p_addmax(A0, NE1, p_add(H0, NOE1)); A1 = p_addmax(A1, NE1, p_add(H1, NOE1));
-            A2 = p_addmax(A2, NE1, p_add(H2, NOE1)); A3 = p_addmax(A3, NE1, p_add(H3, NOE1));
-            B0 = p_addmax(B0, NE2, p_add(H0, NOE2)); B1 = p_addmax(B1, NE2, p_add(H1, NOE2));
-            B2 = p_addmax(B2, NE2, p_add(H2, NOE2)); B3 = p_addmax(B3, NE2, p_add(H3, NOE2));
-            if (local) {
-                A0 = p_max(A0, ZERO); A1 = p_max(A1, ZERO); A2 = p_max(A2, ZERO); A3 = p_max(A3, ZERO);
-                B0 = p_max(B0, ZERO); B1 = p_max(B1, ZERO); B2 = p_max(B2, ZERO); B3 = p_max(B3, ZERO);
-            }
-            if (bnd) {
-                H0 = (H0 & ~m0) | (INFP & m0); H1 = (H1 & ~m1) | (INFP & m1); H2 = (H2 & ~m2) | (INFP & m2); H3 = (H3 & ~m3) | (INFP & m3);
-                A0 = (A0 & ~m0) | (INFP & m0); A1 = (A1 & ~m1) | (INFP & m1); A2 = (A2 & ~m2) | (INFP & m2); A3 = (A3 & ~m3) | (INFP & m3);
-                B0 = (B0 & ~m0) | (INFP & m0); B1 = (B1 & ~m1) | (INFP & m1); B2 = (B2 & ~m2) | (INFP & m2); B3 = (B3 & ~m3) | (INFP & m3);
-            }
-            p16_st(dst, H0, H1, H2, H3);
-            p16_st(dst + pstride, A0, A1, A2, A3);
-            p16_st(dst + 2 * pstride, B0, B1, B2, B3);
-#ifdef POA_EXTRA_PLANE
-            p16_st(dst + 3 * pstride, F20, F21, F22, F23);
-#endif
-            dst += P16_CPB;
-            if (cur_res) {  // after every predecessor read of this chunk: a lane only ever touches its own slices
-                ring_st(ring, rslot, H0, H1, H2, H3); ring_st(ring, rslot + P16_CPB, A0, A1, A2, A3); ring_st(ring, rslot + 2 * P16_CPB, B0, B1, B2, B3);
-            }
-            rslot = rslot == (P16_SMCH - 1) * (3 * P16_CPB) ? 0u : rslot + 3 * P16_CPB;
-            // row maximum (abpoa_align_simd.c:1107-1119): remember the first and the last chunk attaining it
+            // ---- row maximum (abpoa_align_simd.c:1107-1119): remember the first and the last chunk attaining it
             if (track) {
-                const unsigned cm = p_max(p_max3(H0, H1, H2), H3);
-                const int cmx = poa_redux_max(imax(p_lo(cm), p_hi(cm)));
-                if (cmx > rmx) { rmx = cmx; fc = c; }
-                if (cmx >= rmx) lc = c;
+                int cmx[N];
+#pragma unroll
+                for (int u = 0; u < N; ++u) {
+                    const unsigned cm = p_max(p_max3(H[u][0], H[u][1], H[u][2]), H[u][3]);
+                    cmx[u] = poa_redux_max(imax(p_lo(cm), p_hi(cm)));
+                }
+#pragma unroll
+                for (int u = 0; u < N; ++u) {
+                    if (cmx[u] > rmx) { rmx = cmx[u]; fc = c + u; }
+                    if (cmx[u] >= rmx) lc = c + u;
+                }
             }
+        };
+        {
+            int c = cb;
+#pragma unroll 1
+            for (; c + (POA_P16_ILP - 1) <= ce; c += POA_P16_ILP) pass(p16_n<POA_P16_ILP>(), c);
+#if POA_P16_ILP >= 4
+            if (c + 2 <= ce) { pass(p16_n<3>(), c); c += 3; }
+#endif
+#if POA_P16_ILP >= 3
+            if (c + 1 <= ce) { pass(p16_n<2>(), c); c += 2; }
+#endif
+#if POA_P16_ILP >= 2
+            if (c <= ce) pass(p16_n<1>(), c);
+#endif
         }
         prev_meta = poa_make_int4((int)roff, beg, end, 0);
         prev_res = cur_res;
         if (lane == 0) rowmeta[i] = prev_meta;
-#ifdef POA_Q_AHEAD
-        if (i + 1 < rows) stage_profile(rb_next, prev_meta);  // the profile stage is free: this row's last chunk has read it
-        cpa_commit();                                         // Q of row i + 1 (an empty group after the last row)
-#endif
         if (track) {
             // first / last column holding the row maximum: bit r of a lane's mask = low-half cell r equals it, bit 4+r = high half
             const unsigned pat = p_pack(rmx, rmx);
@@ -581,11 +611,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
             prev_left = left; prev_right = right;
             if (local && rmx > best_score) { best_score = rmx; best_i = i; best_j = left; }  // abpoa_align_simd.c:1208-1210
             if (wb >= 0) {  // abpoa_align_simd.c:1121-1130; reductions without a return value: nothing to wait for
-#ifdef POA_Q_AHEAD
-                cpa_wait_pending(1);  // the staged successor rows (G); the next row's profile (Q) stays in flight
-#else
                 cpa_wait_pending(0);
-#endif
                 if (lane < ri.w) { const int out_row = ring_ld32(sm, P16_META_OFF + 256 + lane * 4); poa_red_max(&mprr[out_row], right + 1); poa_red_min(&mplr[out_row], left + 1); }
                 for (int k = lane + POA_WARP; k < ri.w; k += POA_WARP) {
                     const int o = pool_row[ri.z + k];

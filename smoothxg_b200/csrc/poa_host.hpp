@@ -83,6 +83,7 @@ inline void make_layout(WsLayout &L, long long nmax, long long max_bases, long l
     L.o_cig = take(8LL * L.cig_cap);
     L.o_path = take(4 * std::max<long long>(max_bases, 1));
     L.o_best = take(4 * std::max<long long>(max_seq, 1)); L.o_ncig = take(4 * std::max<long long>(max_seq, 1)); L.o_plen = take(4 * std::max<long long>(max_seq, 1));
+    L.o_nrun = take(8 * (std::max<long long>(max_seq, 1) + 2));
     L.o_qp = take(5 * ((max_len >> 8) + 2) * 512);
     L.slab_bytes = align_up(slab_bytes, 512);
     L.o_slab = take(L.slab_bytes);

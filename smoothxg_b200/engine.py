@@ -31,8 +31,8 @@ ABI_SYMBOLS = [
     "poa_b200_run_batch", "poa_b200_poa_block",
     "poa_b200_batch_upload", "poa_b200_batch_launch", "poa_b200_batch_download", "poa_b200_batch_finish",
     "poa_b200_batch_free", "poa_b200_batch_stats", "poa_b200_batch_device_result", "poa_b200_result_from_parts", "poa_b200_result_from_device_parts",
-    "poa_b200_result_n_blocks", "poa_b200_result_block", "poa_b200_result_block_hash", "poa_b200_result_stats", "poa_b200_result_free",
-    "poa_b200_block_graph", "poa_b200_graph_view", "poa_b200_graph_free",
+    "poa_b200_result_n_blocks", "poa_b200_result_block", "poa_b200_result_release_block", "poa_b200_result_block_hash", "poa_b200_result_stats", "poa_b200_result_free",
+    "poa_b200_block_graph", "poa_b200_graph_view", "poa_b200_graph_free", "poa_b200_block_final_graph", "poa_b200_final_graph_view",
 ]
 
 
@@ -80,6 +80,25 @@ class BlockGraph:
     """poa_b200_graph_view_t: what build_odgi_abPOA leaves in the odgi graph (reference src/smooth.cpp:2442-2574)."""
     node_id: np.ndarray
     node_base: bytes
+    edge_from: np.ndarray
+    edge_to: np.ndarray
+    path_off: np.ndarray
+    path_node: np.ndarray
+
+    def path(self, i: int) -> np.ndarray:
+        return self.path_node[self.path_off[i]:self.path_off[i + 1]]
+
+
+class _FinalGraphView(C.Structure):
+    _fields_ = [("n_node", C.c_int32), ("seq_off", C.POINTER(C.c_int64)), ("seq", C.POINTER(C.c_char)),
+                ("n_edge", C.c_int32), ("edge_from", C.POINTER(C.c_int32)), ("edge_to", C.POINTER(C.c_int32)),
+                ("n_path", C.c_int32), ("path_off", C.POINTER(C.c_int64)), ("path_node", C.POINTER(C.c_int32))]
+
+
+@dataclass
+class FinalGraph:
+    """poa_b200_final_graph_view_t: the block graph smooth_abpoa returns (reference src/smooth.cpp:545-620), ids 1..n."""
+    node_seq: list
     edge_from: np.ndarray
     edge_to: np.ndarray
     path_off: np.ndarray
@@ -149,8 +168,12 @@ def load_library() -> C.CDLL:
     lib.poa_b200_result_n_blocks.restype = i64
     lib.poa_b200_result_block.argtypes = [vp, i64, C.POINTER(_BlockView)]
     lib.poa_b200_result_block_hash.argtypes = [vp, i64, C.POINTER(C.c_uint64)]
+    lib.poa_b200_result_release_block.argtypes = [vp, i64]
+    lib.poa_b200_result_release_block.restype = None
     lib.poa_b200_block_graph.argtypes = [C.POINTER(_BlockView), i32, i32, C.POINTER(vp)]
     lib.poa_b200_graph_view.argtypes = [vp, C.POINTER(_GraphView)]
+    lib.poa_b200_block_final_graph.argtypes = [C.POINTER(_BlockView), i32, i32, C.POINTER(vp)]
+    lib.poa_b200_final_graph_view.argtypes = [vp, C.POINTER(_FinalGraphView)]
     lib.poa_b200_graph_free.argtypes = [vp]
     lib.poa_b200_graph_free.restype = None
     lib.poa_b200_result_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -227,6 +250,13 @@ class PoaResult:
             return BlockView(v.status, 0, v.n_seq, -1, -1, 0, z, z, z, z, z, z, z, z, z, z, z, z,
                              np.zeros(0, np.uint8), z, z, np.zeros(0, np.uint64), 0)
         n, s = v.n_node, v.n_seq
+        try:
+            return self._copy_view(v, n, s)
+        finally:
+            self._lib.poa_b200_result_release_block(self._h, i)  # everything was copied: drop the library's flat expansion
+
+    @staticmethod
+    def _copy_view(v, n, s) -> BlockView:
         msa = _arr(v.msa, v.msa_rows * max(v.msa_len, 0), np.uint8)
         cig = np.zeros(0, dtype=np.uint64)
         if v.cigar_total > 0:
@@ -243,6 +273,7 @@ class PoaResult:
         """FNV-1a of block i's graph (poa_b200_result_block_hash): comparable with oracle/ref_shim.c's per-block hash."""
         h = C.c_uint64()
         _check(self._lib, self._lib.poa_b200_result_block_hash(self._h, i, C.byref(h)))
+        self._lib.poa_b200_result_release_block(self._h, i)
         return int(h.value)
 
     def block_graph(self, i: int, padding_len: int = 0, include_consensus: bool = True) -> BlockGraph:
@@ -258,6 +289,24 @@ class PoaResult:
                          _arr(gv.edge_from, gv.n_edge), _arr(gv.edge_to, gv.n_edge), off,
                          _arr(gv.path_node, int(off[-1]) if off.size else 0))
         self._lib.poa_b200_graph_free(g)
+        self._lib.poa_b200_result_release_block(self._h, i)
+        return out
+
+    def final_graph(self, i: int, padding_len: int = 0, include_consensus: bool = True) -> FinalGraph:
+        """The graph smooth_abpoa returns for block i: unchopped, topologically ordered, compact ids (poa_b200_block_final_graph)."""
+        v = _BlockView()
+        _check(self._lib, self._lib.poa_b200_result_block(self._h, i, C.byref(v)))
+        g = C.c_void_p()
+        _check(self._lib, self._lib.poa_b200_block_final_graph(C.byref(v), padding_len, int(include_consensus), C.byref(g)))
+        gv = _FinalGraphView()
+        _check(self._lib, self._lib.poa_b200_final_graph_view(g, C.byref(gv)))
+        so = _arr(gv.seq_off, gv.n_node + 1, np.int64)
+        seq = bytes(gv.seq[:int(so[-1])]) if gv.n_node else b""
+        off = _arr(gv.path_off, gv.n_path + 1, np.int64)
+        out = FinalGraph([seq[int(so[k]):int(so[k + 1])].decode() for k in range(gv.n_node)],
+                         _arr(gv.edge_from, gv.n_edge), _arr(gv.edge_to, gv.n_edge), off, _arr(gv.path_node, int(off[-1]) if off.size else 0))
+        self._lib.poa_b200_graph_free(g)
+        self._lib.poa_b200_result_release_block(self._h, i)
         return out
 
     def stats(self) -> dict:

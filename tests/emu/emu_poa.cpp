@@ -14,6 +14,7 @@
 #include <cstring>
 #include <vector>
 #include "../../smoothxg_b200/csrc/poa_host.hpp"
+#include "../../smoothxg_b200/csrc/poa_wire.hpp"
 #include "../../oracle/poa_dump.h"
 
 namespace poa {
@@ -144,19 +145,20 @@ extern "C" int32_t *emu_poa_block(const pd_params_t *pp, int n_seq, const int32_
         *n_out = (int64_t)(HDR_WORDS + used);
         return out;
     }
-    // wire format -> canonical dump
+    // wire format -> flat arrays (the decoder the C ABI uses) -> canonical dump
     const int n = hdr[H_N_NODE], ns = hdr[H_N_SEQ];
     const long long in_tot = hdr[H_IN_TOT], out_tot = hdr[H_OUT_TOT], aln_tot = hdr[H_ALN_TOT], path_tot = hdr[H_PATH_TOT], cig_tot = hdr[H_CIG_TOT];
     const int cons_len = hdr[H_CONS_LEN], msa_len = hdr[H_MSA_LEN], msa_rows = hdr[H_MSA_ROWS];
     const int *o = arena.data() + ((unsigned long long)(unsigned)hdr[H_OFF_LO] | ((unsigned long long)(unsigned)hdr[H_OFF_HI] << 32));
-    long long body = 4LL * n + 2 * in_tot + 2 * out_tot + aln_tot + ns + path_tot + (cons_len > 0 ? cons_len : 0);
-    const int *tail = o + body;  // best, ncig, cig
-    const uint8_t *msa = (const uint8_t *)(tail + 2LL * ns + 2 * cig_tot);
+    DecodedBlock dec;
+    if (!wire_header_ok(hdr.data()) || !wire_decode(hdr.data(), o, dec)) { fprintf(stderr, "[emu] corrupt wire body\n"); return nullptr; }
+    const long long body = 4LL * n + 2 * in_tot + 2 * out_tot + aln_tot + ns + path_tot + (cons_len > 0 ? cons_len : 0);  // base .. cons_node
     pd_buf_t b = {0, 0, 0};
     for (int i = 0; i < PD_HEADER_LEN; ++i) pd_push(&b, 0);
-    for (long long i = 0; i < body; ++i) pd_push(&b, o[i]);
-    for (long long i = 0; i < (long long)msa_rows * (msa_len > 0 ? msa_len : 0); ++i) pd_push(&b, msa[i]);
-    for (long long i = 0; i < 2LL * ns + 2 * cig_tot; ++i) pd_push(&b, tail[i]);
+    for (long long i = 0; i < body; ++i) pd_push(&b, dec.buf[(size_t)i]);
+    for (long long i = 0; i < (long long)msa_rows * (msa_len > 0 ? msa_len : 0); ++i) pd_push(&b, dec.msa[i]);
+    for (long long i = 0; i < 2LL * ns; ++i) pd_push(&b, dec.buf[(size_t)(dec.best + i)]);
+    for (long long i = 0; i < 2 * cig_tot; ++i) pd_push(&b, dec.cig[i]);
     b.d[PD_MAGIC] = POA_DUMP_MAGIC; b.d[PD_N_NODE] = n; b.d[PD_N_SEQ] = ns;
     b.d[PD_CONS_LEN] = cons_len; b.d[PD_MSA_LEN] = msa_len; b.d[PD_MSA_ROWS] = msa_rows;
     b.d[PD_N_IN_TOT] = (int)in_tot; b.d[PD_N_OUT_TOT] = (int)out_tot; b.d[PD_N_ALN_TOT] = (int)aln_tot;

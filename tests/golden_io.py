@@ -51,3 +51,31 @@ def pd_params(p):
 def engine_params(p):
     from smoothxg_b200.engine import PoaParams
     return PoaParams(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], 0.03, p[8], p[9])
+
+
+# ---- full-size single blocks stored as per-section digests (tests/golden/make_deep_golden.py)
+DEEP_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deep_golden.npz")
+DEEP_CASES = {
+    "deep_256x8kb": (dict(n_blocks=1, n_seqs=256, length=8000, divergence=0.02, seed=3001), dict()),
+    "local_32x2kb": (dict(n_blocks=1, n_seqs=32, length=2000, divergence=0.02, seed=3002), dict(local=True)),
+}
+_SMALL = ("best_score", "n_cigar", "path_len", "cons_node")
+
+
+def digest_dump(name, d):
+    """{name/hdr, name/<small section>, name/sha/<section>} of a canonical dump (oracle.Dump)."""
+    import hashlib
+    from oracle.oracle import PD_FULL_LO
+    out = {f"{name}/hdr": d.raw[:PD_FULL_LO].copy()}
+    for k, v in d.sections().items():
+        out[f"{name}/sha/{k}"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(v, dtype=np.int32).tobytes()).digest(), dtype=np.uint8)
+        if k in _SMALL:
+            out[f"{name}/{k}"] = np.asarray(v, dtype=np.int32)
+    return out
+
+
+def deep_mismatches(name, d):
+    """Sections of dump `d` whose digest differs from the unmodified abPOA's for DEEP_CASES[name] ([] = bit-exact)."""
+    want = np.load(DEEP_PATH)
+    got = digest_dump(name, d)
+    return [k for k in got if k not in want.files or not np.array_equal(got[k], want[k])] + [k for k in want.files if k.startswith(name + "/") and k not in got]

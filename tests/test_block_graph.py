@@ -1,5 +1,7 @@
 """CPU: poa_b200_block_graph() -- the per-block graph smoothxg's build_odgi_abPOA leaves behind (reference
 src/smooth.cpp:2442-2574) -- against a literal restatement of that function on a dict graph.
+(The restatement is ours; what pins this stage to the reference itself is tests/test_final_graph.py, which compares the graph
+after the next stage with the block graphs the reference binary returned for real blocks.)
 The POA results come from the emulated device code (wire format -> poa_b200_result_from_parts), so the test needs
 no GPU; the -m gpu suite repeats it on results produced by the CUDA path."""
 import ctypes as C
@@ -56,10 +58,9 @@ def build_odgi_restated(v, padding_len, include_consensus):
         for x in p:
             steps[x] = steps.get(x, 0) + 1
         paths.append(p)
-    walked = set()
-    for p in paths:
-        walked.update(zip(p[:-1], p[1:]))
-    edges = [e for e in edges if e in walked]   # :2559-2565 (an edge is walked in either direction by the same pair)
+    # :2559-2565 removes nothing: odgi's find_edges_exceeding_depth_limits(min_depth=1) only inspects edges some path walks
+    # (deps/odgi/src/algorithms/depth.cpp:17-51); edges go away only with an uncovered node (:2567-2573, destroy_handle)
+    edges = [e for e in edges if steps.get(e[0], 0) > 0 and steps.get(e[1], 0) > 0]
     nodes = [x for x in nodes if steps.get(x, 0) > 0]  # :2567-2573
     return nodes, edges, paths
 
@@ -68,7 +69,7 @@ def build_odgi_restated(v, padding_len, include_consensus):
 def wire():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     csrc = os.path.join(HERE, "..", "smoothxg_b200", "csrc")
-    deps = [SRC] + [os.path.join(csrc, f) for f in ("poa_core.cuh", "poa_fill16.cuh", "poa_host.hpp")]
+    deps = [SRC] + [os.path.join(csrc, f) for f in ("poa_core.cuh", "poa_fill16.cuh", "poa_host.hpp", "poa_wire.hpp")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-O1", "-fPIC", "-shared", "-std=c++17", "-I/usr/local/cuda/include", "-o", OUT, SRC])
     return _Checker(C.CDLL(OUT), "emu_poa_block_wire", "emu_free")

@@ -24,7 +24,7 @@ CASES = load_cases()
 @pytest.fixture(scope="module")
 def emu():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    deps = [SRC] + [os.path.join(HERE, "..", "smoothxg_b200", "csrc", f) for f in ("poa_core.cuh", "poa_fill16.cuh", "poa_host.hpp")]
+    deps = [SRC] + [os.path.join(HERE, "..", "smoothxg_b200", "csrc", f) for f in ("poa_core.cuh", "poa_fill16.cuh", "poa_host.hpp", "poa_wire.hpp")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         inc = "/usr/local/cuda/include"
         subprocess.check_call(["/usr/bin/g++", "-O1", "-fPIC", "-shared", "-std=c++17", f"-I{inc}", "-o", OUT, SRC])
@@ -47,7 +47,7 @@ def emu32():
     warp-level logic -- shuffle scans, reductions, the lane-striped packed 16-bit fill of poa_fill16.cuh."""
     os.makedirs(os.path.dirname(OUT32), exist_ok=True)
     csrc = os.path.join(HERE, "..", "smoothxg_b200", "csrc")
-    deps = [SRC] + [os.path.join(csrc, f) for f in ("poa_core.cuh", "poa_fill16.cuh", "poa_host.hpp")]
+    deps = [SRC] + [os.path.join(csrc, f) for f in ("poa_core.cuh", "poa_fill16.cuh", "poa_host.hpp", "poa_wire.hpp")]
     if not os.path.exists(OUT32) or any(os.path.getmtime(d) > os.path.getmtime(OUT32) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-O1", "-fPIC", "-shared", "-std=c++17", "-DPOA_EMU_LANES=32",
                                "-I/usr/local/cuda/include", "-o", OUT32, SRC])
@@ -64,7 +64,7 @@ def emu32x4():
     warps, carry chain through shared memory) and the generic multi-warp fill, cross-warp barriers included."""
     os.makedirs(os.path.dirname(OUT32X4), exist_ok=True)
     csrc = os.path.join(HERE, "..", "smoothxg_b200", "csrc")
-    deps = [SRC] + [os.path.join(csrc, f) for f in ("poa_core.cuh", "poa_fill16.cuh", "poa_host.hpp")]
+    deps = [SRC] + [os.path.join(csrc, f) for f in ("poa_core.cuh", "poa_fill16.cuh", "poa_host.hpp", "poa_wire.hpp")]
     if not os.path.exists(OUT32X4) or any(os.path.getmtime(d) > os.path.getmtime(OUT32X4) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-O1", "-fPIC", "-shared", "-std=c++17", "-DPOA_EMU_LANES=32", "-DPOA_EMU_NW=4",
                                "-I/usr/local/cuda/include", "-o", OUT32X4, SRC])

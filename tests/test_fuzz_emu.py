@@ -12,7 +12,7 @@ def test_fuzz_emulated_device_logic(tmp_path):
     # the emulation libraries are built by tests/test_emu_parity.py's fixtures; build them here too if this file runs alone
     from tests import test_emu_parity as T
     for out, flags in ((T.OUT, []), (T.OUT32, ["-DPOA_EMU_LANES=32"])):
-        deps = [T.SRC] + [os.path.join(ROOT, "smoothxg_b200", "csrc", f) for f in ("poa_core.cuh", "poa_fill16.cuh", "poa_host.hpp")]
+        deps = [T.SRC] + [os.path.join(ROOT, "smoothxg_b200", "csrc", f) for f in ("poa_core.cuh", "poa_fill16.cuh", "poa_host.hpp", "poa_wire.hpp")]
         if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
             os.makedirs(os.path.dirname(out), exist_ok=True)
             subprocess.check_call(["/usr/bin/g++", "-O1", "-fPIC", "-shared", "-std=c++17", *flags, "-I/usr/local/cuda/include", "-o", out, T.SRC])

@@ -44,6 +44,19 @@ def test_real_drb1_blocks(warps):
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["local_32x2kb", "deep_256x8kb"])
+def test_full_size_single_blocks(name):
+    """One full-size configs[3] block (256 x 8 kb: int16 -> int32 switch mid-block, 28 592 rows) and one 32 x 2 kb block in
+    local mode, against the unmodified abPOA's per-section digests (graph, edge order, weights, paths, scores, cigars)."""
+    from tests.golden_io import DEEP_CASES, deep_mismatches
+    kw, pk = DEEP_CASES[name]
+    batch = synth.make_batch(**kw)
+    eng = E.PoaEngine(device=0, emit_cigar=True)
+    res = eng.run_batch(batch, E.make_params(**pk))
+    assert deep_mismatches(name, view_to_dump(res.block(0))) == []
+    res.close(); eng.close()
+
+
 @pytest.mark.parametrize("kw,pk", [
     (dict(n_blocks=24, n_seqs=16, length=1000, seed=201), dict()),
     (dict(n_blocks=8, n_seqs=12, length=1500, seed=202, indel_prob=0.6, indel_len=(100, 700), dup_weights=True, n_frac=0.01), dict(out_msa=True)),

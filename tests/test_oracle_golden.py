@@ -27,6 +27,17 @@ def test_oracle_matches_golden(oracle, name, batch, p, dumps):
         assert np.array_equal(got.raw, dumps[b].raw), f"{name} block {b}"
 
 
+def test_oracle_matches_full_size_local_block(oracle):
+    """One configs[2]-shaped block (32 x 2 kb) in LOCAL mode -- what plain -A gives (src/main.cpp:487) -- against the
+    unmodified abPOA's per-section digests (tests/golden/make_deep_golden.py)."""
+    from oracle.oracle import make_params
+    from smoothxg_b200.synth import make_batch
+    from tests.golden_io import DEEP_CASES, deep_mismatches
+    kw, pk = DEEP_CASES["local_32x2kb"]
+    got = oracle.poa_block(make_params(**pk), *make_batch(**kw).block(0))
+    assert deep_mismatches("local_32x2kb", got) == []
+
+
 def test_oracle_lane_count_only_moves_junk(oracle):
     """The reference's SIMD lane count only shifts the band start over -inf cells: results equal."""
     name, batch, p, dumps = next(c for c in CASES if c[0] == "syn_indel")
