@@ -150,8 +150,21 @@ int  poa_b200_run_batch(poa_b200_engine_t *eng, const poa_b200_params_t *params,
                         const int64_t *block_seq_off, const int32_t *seq_len, const int64_t *seq_off,
                         const uint8_t *bases, const int32_t *weight, poa_b200_result_t **result);
 
-/* Per-block convenience with abpoa_poa's own argument shapes (deps/abPOA/src/abpoa_align.c:304):
- * seqs[i] = codes of sequence i, weights[i] = its dedup multiplicity. */
+/* Per-block entry points with abpoa_poa's own argument shapes (deps/abPOA/src/abpoa_align.c:304): seqs[i] = codes of sequence
+ * i, weights[i] = its dedup multiplicity.  They are what the UNMODIFIED OpenMP loop over blocks (src/smooth.cpp:1931) would call
+ * from its worker threads, and they coalesce: blocks submitted by any number of host threads accumulate in one pending batch
+ * that the engine's dispatcher thread launches when it holds 8 192 blocks, when a block with other parameters arrives, or as
+ * soon as some thread waits for one of its blocks while the GPU is idle; submissions arriving while a batch runs form the next
+ * one.  So N concurrent callers share launches instead of taking turns on the GPU.
+ *   poa_b200_submit_block  copies the block and returns a ticket at once;
+ *   poa_b200_wait_block    blocks until that block is done and returns a one-block result (block index 0; it keeps the shared
+ *                          batch result alive until poa_b200_result_free).  A ticket can be collected once, from any thread.
+ *   poa_b200_poa_block     = submit + wait.  With T synchronous callers a launch carries at most T blocks -- enough to keep
+ *                          the reference's loop body unchanged, not enough to fill a B200: throughput needs either
+ *                          poa_b200_run_batch or a window of outstanding tickets per thread. */
+int  poa_b200_submit_block(poa_b200_engine_t *eng, const poa_b200_params_t *params, int32_t n_seq,
+                           const uint8_t *const *seqs, const int32_t *seq_lens, const int32_t *weights, uint64_t *ticket);
+int  poa_b200_wait_block(poa_b200_engine_t *eng, uint64_t ticket, poa_b200_result_t **result);
 int  poa_b200_poa_block(poa_b200_engine_t *eng, const poa_b200_params_t *params, int32_t n_seq,
                         const uint8_t *const *seqs, const int32_t *seq_lens, const int32_t *weights,
                         poa_b200_result_t **result);

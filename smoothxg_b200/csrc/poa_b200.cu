@@ -20,6 +20,11 @@
 #include "poa_host.hpp"
 #include "poa_wire.hpp"
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <thread>
+#include <unordered_map>
 
 using namespace poa;
 
@@ -51,7 +56,7 @@ __global__ void POA_KERNEL_BOUNDS poa_b200_block_kernel(const __grid_constant__ 
         const int t = sh.blk;
         __syncthreads();
         if (t >= B.n_order) break;
-        poa_block<NW>(sh, P, B, L, O, B.order[t]);
+        poa_block<NW>(sh, P, B, L, O, B.order[t], ws_base + (long long)blockIdx.x * L.stride);
     }
 }
 
@@ -170,7 +175,36 @@ struct Arena {
 
 }  // namespace
 
+// Coalescing front end of the per-block entry points (poa_b200_submit_block / poa_b200_wait_block / poa_b200_poa_block):
+// blocks submitted by any number of host threads accumulate in one pending batch; a dispatcher thread owned by the engine
+// closes the batch and runs it through poa_b200_run_batch when it is large enough, or as soon as some thread waits for one of
+// its blocks while the GPU is idle.  While a batch runs, further submissions accumulate for the next one, so concurrent
+// callers share launches instead of serialising on the engine (the reference's counterpart is the OpenMP loop over blocks,
+// src/smooth.cpp:1931, whose workers each own a private abpoa_t).
+struct Coalescer {
+    struct Batch {
+        poa_b200_params_t params{};
+        std::vector<int64_t> bso{0}, so{0};
+        std::vector<int32_t> lens, wts;
+        std::vector<uint8_t> bases;
+        std::vector<uint64_t> tickets;
+    };
+    struct Done { std::shared_ptr<poa_b200_result> res; int64_t block = 0; int rc = 0; std::string err; };
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::unique_ptr<Batch> open;            // accumulating
+    std::deque<std::unique_ptr<Batch>> ready;  // closed, waiting for the GPU
+    std::unordered_map<uint64_t, Done> done;
+    std::unordered_map<uint64_t, int> where;   // ticket -> 0 open / 1 ready or running (absent once done and collected)
+    uint64_t next_ticket = 1;
+    int64_t max_blocks = 8192;              // close the open batch at this many blocks
+    int waiting_on_open = 0;                // threads blocked in wait() on a ticket of the open batch
+    bool running = false, stop = false, started = false;
+    std::thread worker;
+};
+
 struct poa_b200_engine {
+    Coalescer co;
     int device = 0;
     int n_sm = 0;
     cudaStream_t stream = nullptr;
@@ -192,6 +226,10 @@ struct poa_b200_result {
     std::vector<unsigned long long> arena_words;
     poa_b200_stats_t stats{};
     int emit_cigar = 0;
+    // A result handed out by poa_b200_wait_block() is a window of ONE block onto the (shared) result of the batch its block
+    // was coalesced into: `parent` owns the memory, block 0 of this object is block `parent_block` of the parent.
+    std::shared_ptr<poa_b200_result> parent;
+    int64_t parent_block = 0;
     // Block bodies are stored narrow and run-length coded (WireLayout, poa_core.cuh); a block is decoded into the view's flat
     // int32 arrays the first time it is looked at, lock-free (threads racing on one block both decode, one copy is kept).
     mutable std::unique_ptr<std::atomic<poa::DecodedBlock *>[]> decoded;
@@ -581,6 +619,13 @@ int poa_b200_engine_trim(poa_b200_engine_t *eng) {
 
 void poa_b200_engine_destroy(poa_b200_engine_t *eng) {
     if (!eng) return;
+    {
+        std::unique_lock<std::mutex> lk(eng->co.mu);
+        eng->co.stop = true;
+        eng->co.cv_work.notify_all();
+    }
+    if (eng->co.worker.joinable()) eng->co.worker.join();
+    eng->co.done.clear();
     cudaSetDevice(eng->device);
     if (eng->stream) cudaStreamDestroy(eng->stream);
     delete eng;
@@ -859,15 +904,121 @@ int poa_b200_run_batch(poa_b200_engine_t *eng, const poa_b200_params_t *params, 
     return rc;
 }
 
+namespace {
+void coalescer_main(poa_b200_engine *eng) {
+    Coalescer &co = eng->co;
+    std::unique_lock<std::mutex> lk(co.mu);
+    for (;;) {
+        // close the open batch when it is full, or when somebody is waiting for one of its blocks and the GPU would idle
+        co.cv_work.wait(lk, [&] { return co.stop || !co.ready.empty() || (co.open && !co.open->tickets.empty() && co.waiting_on_open > 0); });
+        if (co.stop && co.ready.empty() && !(co.open && !co.open->tickets.empty())) break;
+        if (co.ready.empty() && co.open && !co.open->tickets.empty()) {
+            for (uint64_t t : co.open->tickets) co.where[t] = 1;
+            co.ready.push_back(std::move(co.open));
+            co.waiting_on_open = 0;
+        }
+        if (co.ready.empty()) continue;
+        std::unique_ptr<Coalescer::Batch> b = std::move(co.ready.front());
+        co.ready.pop_front();
+        co.running = true;
+        lk.unlock();
+        poa_b200_result_t *res = nullptr;
+        const int64_t nb = (int64_t)b->tickets.size();
+        const int rc = poa_b200_run_batch(eng, &b->params, nb, b->bso.data(), b->lens.data(), b->so.data(),
+                                          b->bases.empty() ? nullptr : b->bases.data(), b->wts.data(), &res);
+        const std::string err = poa::g_last_error;
+        std::shared_ptr<poa_b200_result> holder;
+        if (res) holder.reset(res, [](poa_b200_result *r) { poa_b200_result_free(r); });
+        lk.lock();
+        for (int64_t i = 0; i < nb; ++i) {
+            Coalescer::Done d;
+            d.res = holder; d.block = i;
+            if (!res) { d.rc = rc ? rc : POA_B200_EINTERNAL; d.err = err; }
+            else { const int st = res->hdr[(size_t)i * HDR_WORDS + H_STATUS]; d.rc = st == ST_OK ? POA_B200_OK : POA_B200_EBLOCK; if (st != ST_OK) d.err = err; }
+            co.done.emplace(b->tickets[(size_t)i], std::move(d));
+            co.where.erase(b->tickets[(size_t)i]);
+        }
+        co.running = false;
+        co.cv_done.notify_all();
+    }
+}
+}  // namespace
+
+int poa_b200_submit_block(poa_b200_engine_t *eng, const poa_b200_params_t *params, int32_t n_seq,
+                          const uint8_t *const *seqs, const int32_t *seq_lens, const int32_t *weights, uint64_t *ticket) {
+    if (!eng || !params || !ticket || n_seq < 0 || (n_seq > 0 && (!seqs || !seq_lens || !weights))) return set_err(POA_B200_EARG, "bad block");
+    int rc = check_params(*params);
+    if (rc) return rc;
+    for (int i = 0; i < n_seq; ++i) if (seq_lens[i] < 0 || (seq_lens[i] > 0 && !seqs[i])) return set_err(POA_B200_EARG, "bad sequence");
+    Coalescer &co = eng->co;
+    std::unique_lock<std::mutex> lk(co.mu);
+    if (co.stop) return set_err(POA_B200_EARG, "engine is shutting down");
+    if (!co.started) { co.worker = std::thread(coalescer_main, eng); co.started = true; }
+    // one batch = one parameter set: a block with other parameters closes the open batch first
+    if (co.open && !co.open->tickets.empty() && memcmp(&co.open->params, params, sizeof(*params)) != 0) {
+        for (uint64_t t : co.open->tickets) co.where[t] = 1;
+        co.ready.push_back(std::move(co.open));
+        co.waiting_on_open = 0;
+        co.cv_work.notify_all();
+    }
+    if (!co.open) { co.open.reset(new Coalescer::Batch()); }
+    Coalescer::Batch &b = *co.open;
+    if (b.tickets.empty()) b.params = *params;
+    for (int i = 0; i < n_seq; ++i) {
+        b.lens.push_back(seq_lens[i]); b.wts.push_back(weights[i]);
+        if (seq_lens[i]) b.bases.insert(b.bases.end(), seqs[i], seqs[i] + seq_lens[i]);
+        b.so.push_back((int64_t)b.bases.size());
+    }
+    b.bso.push_back((int64_t)b.lens.size());
+    const uint64_t t = co.next_ticket++;
+    b.tickets.push_back(t);
+    co.where[t] = 0;
+    *ticket = t;
+    if ((int64_t)b.tickets.size() >= co.max_blocks) {
+        for (uint64_t x : b.tickets) co.where[x] = 1;
+        co.ready.push_back(std::move(co.open));
+        co.waiting_on_open = 0;
+        co.cv_work.notify_all();
+    }
+    return POA_B200_OK;
+}
+
+int poa_b200_wait_block(poa_b200_engine_t *eng, uint64_t ticket, poa_b200_result_t **result) {
+    if (!eng || !result) return set_err(POA_B200_EARG, "NULL argument");
+    *result = nullptr;
+    Coalescer &co = eng->co;
+    std::unique_lock<std::mutex> lk(co.mu);
+    auto it = co.done.find(ticket);
+    if (it == co.done.end()) {
+        auto w = co.where.find(ticket);
+        if (w == co.where.end()) return set_err(POA_B200_EARG, "unknown or already collected ticket");
+        bool counted = false;
+        while ((it = co.done.find(ticket)) == co.done.end()) {
+            w = co.where.find(ticket);
+            if (w != co.where.end() && w->second == 0 && !counted) { ++co.waiting_on_open; counted = true; co.cv_work.notify_all(); }
+            co.cv_done.wait(lk);
+        }
+    }
+    Coalescer::Done d = std::move(it->second);
+    co.done.erase(it);
+    lk.unlock();
+    if (!d.res) return set_err(d.rc ? d.rc : POA_B200_EINTERNAL, d.err);
+    poa_b200_result *r = new (std::nothrow) poa_b200_result();
+    if (!r) return set_err(POA_B200_ENOMEM, "result alloc");
+    r->n_blocks = 1; r->parent = d.res; r->parent_block = d.block; r->emit_cigar = d.res->emit_cigar;
+    *result = r;
+    return d.rc == POA_B200_OK ? POA_B200_OK : set_err(d.rc, d.err.empty() ? "block failed; see its status" : d.err);
+}
+
 int poa_b200_poa_block(poa_b200_engine_t *eng, const poa_b200_params_t *params, int32_t n_seq,
                        const uint8_t *const *seqs, const int32_t *seq_lens, const int32_t *weights,
                        poa_b200_result_t **result) {
-    if (n_seq < 0 || (n_seq > 0 && (!seqs || !seq_lens || !weights))) return set_err(POA_B200_EARG, "bad block");
-    std::vector<int64_t> bso{0, n_seq}, so((size_t)n_seq + 1, 0);
-    for (int i = 0; i < n_seq; ++i) so[(size_t)i + 1] = so[(size_t)i] + seq_lens[i];
-    std::vector<uint8_t> cat((size_t)so[(size_t)n_seq]);
-    for (int i = 0; i < n_seq; ++i) if (seq_lens[i]) memcpy(cat.data() + so[(size_t)i], seqs[i], (size_t)seq_lens[i]);
-    return poa_b200_run_batch(eng, params, 1, bso.data(), seq_lens, so.data(), cat.data(), weights, result);
+    if (!result) return set_err(POA_B200_EARG, "NULL result");
+    *result = nullptr;
+    uint64_t t = 0;
+    int rc = poa_b200_submit_block(eng, params, n_seq, seqs, seq_lens, weights, &t);
+    if (rc) return rc;
+    return poa_b200_wait_block(eng, t, result);
 }
 
 int poa_b200_block_graph(const poa_b200_block_view_t *v, int32_t padding_len, int32_t include_consensus, poa_b200_graph_t **out) {
@@ -1062,6 +1213,7 @@ int64_t poa_b200_result_n_blocks(const poa_b200_result_t *res) { return res ? re
 
 int poa_b200_result_block(const poa_b200_result_t *res, int64_t blk, poa_b200_block_view_t *v) {
     if (!res || !v || blk < 0 || blk >= res->n_blocks) return set_err(POA_B200_EARG, "bad block index");
+    if (res->parent) return poa_b200_result_block(res->parent.get(), res->parent_block + blk, v);
     memset(v, 0, sizeof(*v));
     const int *h = &res->hdr[(size_t)blk * HDR_WORDS];
     v->status = h[H_STATUS];
@@ -1097,6 +1249,7 @@ int poa_b200_result_block(const poa_b200_result_t *res, int64_t blk, poa_b200_bl
 }
 
 void poa_b200_result_release_block(const poa_b200_result_t *res, int64_t blk) {
+    if (res && res->parent && blk >= 0 && blk < res->n_blocks) { poa_b200_result_release_block(res->parent.get(), res->parent_block + blk); return; }
     if (!res || blk < 0 || blk >= res->n_blocks || !res->decoded) return;
     delete res->decoded[(size_t)blk].exchange(nullptr, std::memory_order_acq_rel);
 }
@@ -1127,12 +1280,13 @@ int poa_b200_result_block_hash(const poa_b200_result_t *res, int64_t blk, uint64
 
 int poa_b200_result_stats(const poa_b200_result_t *res, poa_b200_stats_t *s) {
     if (!res || !s) return set_err(POA_B200_EARG, "NULL argument");
-    *s = res->stats;
+    *s = res->parent ? res->parent->stats : res->stats;
     return POA_B200_OK;
 }
 
 void poa_b200_result_free(poa_b200_result_t *res) {
     if (!res) return;
+    if (res->parent) { poa_b200_result_release_block(res->parent.get(), res->parent_block); delete res; return; }  // the last window frees the batch result
     for (size_t i = 0; i < res->arenas.size(); ++i) if (res->arena_caps[i]) res->pinned->give(res->arenas[i], res->arena_caps[i]);
     delete res;
 }

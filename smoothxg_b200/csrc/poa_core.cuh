@@ -169,6 +169,10 @@ struct DevParams {
     int emit_cigar;
     int p16_ok;  // scoring parameters allow the packed 16-bit fill (poa_fill16.cuh)
     int gap_mode;  // 0 convex, 1 affine, 2 linear (abpoa_set_gap_mode, abpoa_align.c:87-91)
+    // Packed (two int16 per word) constants of the 16-bit fill, prepared on the host (build_params): as fields of a
+    // __grid_constant__ parameter they are constant-bank operands of the packed-integer instructions instead of a dozen
+    // loop-invariant vector registers (the fill runs at 128 registers per thread with nothing to spare).
+    unsigned pk_inf, pk_negl, pk_noe1, pk_noe2, pk_ne1, pk_ne2, pk_ne1_2, pk_ne1_3, pk_ne2_2, pk_ne2_3, pk_ncw1, pk_ncw2;
 };
 
 // Device-resident batch input (flat, same arrays as the C ABI takes).
@@ -1458,7 +1462,7 @@ POA_D int block_excl_scan(Shared &sh, const int *src, int *dst, int n, int *scra
 }
 
 template <int NW>
-POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const WsLayout &L, const DevOut &O, int b) {
+POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const WsLayout &L, const DevOut &O, int b, char *const wsb /* this CTA's workspace */) {
     constexpr int NT = NW * POA_WARP;
     Ws &w = sh.ws;
     const int tid = poa_tid();
@@ -1513,7 +1517,7 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
             if (p16) {
                 t_ph[PH_SPARE] += 1;  // alignments that took the packed 16-bit fill
 #if POA_WARP == 32
-                if (NW == 1) { if (P.local) fill_p16<NW, true>(sh, P, q, qlen, L.slab_bytes); else fill_p16<NW, false>(sh, P, q, qlen, L.slab_bytes); }
+                if (NW == 1) { if (P.local) fill_p16<NW, true>(sh, P, L, wsb, q, qlen); else fill_p16<NW, false>(sh, P, L, wsb, q, qlen); }
                 else { if (P.local) fill_p16_mw<NW, true>(sh, P, q, qlen, L.slab_bytes); else fill_p16_mw<NW, false>(sh, P, q, qlen, L.slab_bytes); }
 #endif
             } else if (P.gap_mode == 0) {

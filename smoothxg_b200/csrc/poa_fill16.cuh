@@ -156,24 +156,25 @@ POA_D bool p16_eligible(const DevParams &P, int qlen) {
 // Compile-time chunk count of one pass of the row loop (fill_p16): generic lambdas take it as a value of this type.
 template <int N> struct p16_n { static constexpr int value = N; };
 #ifndef POA_P16_ILP
-#define POA_P16_ILP 2  // chunks of a row evaluated side by side by one warp (1 = the round-1 loop shape)
+#define POA_P16_ILP 1  // chunks of a row evaluated side by side by one warp; 1 is what ships (see below), 2..4 are experiments
 #endif
 
 // fill_p16: one warp, rows in index order, the chunks of a row taken POA_P16_ILP at a time.
 //
-// Why several chunks at once: a row is one dependent chain per chunk -- predecessor loads, the shifted match operand, a
-// 4-cell recurrence per lane, a five-round shuffle scan, the fix-up -- and consecutive rows depend on each other through
-// the adaptive band (a row's band needs the arg-max columns of the whole previous row), so a warp that walks one chunk at
-// a time has nothing independent to issue while a shuffle or a load is in flight (round 1: 52 % of issue slots used with
-// every resident warp stalled on its own chain).  The chunks of ONE row, however, are independent up to the scalar F carry
-// that enters a chunk from its left neighbour, and that carry is applied AFTER the lane scan.  So the row loop evaluates
-// N chunks per pass as straight-line code: N sets of predecessor loads, N x 8 lane chains, N x 2 shuffle scans in flight
-// together, then the carry chain through the N scan totals (two instructions per chunk), then N fix-ups and stores.
-// Everything per chunk is branch-free (out-of-range predecessor chunks read as inf_min through predicated loads) so the
-// compiler can interleave the N instruction streams.
+// The row loop is written for N chunks per pass (`pass`, a generic lambda over a compile-time N): a row is one dependent chain
+// per chunk -- predecessor loads, the shifted match operand, a 4-cell recurrence per lane, a five-round shuffle scan, the
+// fix-up -- and consecutive rows depend on each other through the adaptive band (a row's band needs the arg-max columns of
+// the whole previous row), so a warp that walks one chunk at a time has little independent work to issue while a shuffle or
+// a load is in flight (52 % of issue slots used).  The chunks of ONE row are independent up to the scalar F carry that enters
+// a chunk from its left neighbour, and that carry is applied AFTER the lane scan, so N chunks can run as interleaved
+// straight-line code.  MEASURED on configs[2] (profiles/r02_ilp_variants.json): N = 2 cuts long-scoreboard, short-scoreboard
+// and fixed-latency stalls per issued instruction from 2.22 / 0.60 / 1.79 to 1.40 / 0.36 / 1.53, but the pass body no longer
+// fits the SM's instruction caches (726 instead of 373 instructions; `no_instruction` stalls rise from 0.49 to 1.41 per issue)
+// and it needs 168 registers (12 resident warps per SM instead of 16): 188-211 Gcells/s against 250 for N = 1; N = 3 and 4 are
+// slower still (150 / 122).  So N = 1 ships; the switch stays for the next machine with a larger L0/L1.5 I-cache.
 template <int NW, bool LOCAL>
-POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, long long slab_bytes) {
-    Ws &w = sh.ws;
+POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *const wsb, const uint8_t *q, int qlen) {
+    const long long slab_bytes = L.slab_bytes;
     const int lane = poa_tid();
     const int n_node = sh.n_node;
     const int rows = n_node - 1;  // the sink row is never filled
@@ -187,15 +188,19 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
     const int bw = wb < 0 ? qlen : wb + (int)__fmul_rn(P.wf, (float)qlen);
 #endif
     const int e1 = P.e1, e2 = P.e2, oe1 = P.oe1, oe2 = P.oe2;
-    // workspace pointers: read once from shared memory and told to be global so the hot loop uses LDG/STG
-    char *const slab = w.slab, *const qp = w.qp;
-    const int4 *const rowinfo = w.rowinfo;
-    int4 *const rowmeta = w.rowmeta;
-    const int *const pool_row = w.pool_row, *const rr = w.rr;
-    int *const mplr = w.mplr, *const mprr = w.mprr;
-    const uint8_t *const rbase = w.rbase;
-    const int *const fp = w.tmp0;  // build_rows(): row of the first predecessor
-    const int *const sp = w.tmp1;  // build_rows(): row of the second predecessor, -1 if there is none
+    // Workspace pointers are formed from the CTA's workspace base (a kernel parameter plus blockIdx.x * stride: warp-uniform) and
+    // the layout's offsets (constant bank), NOT read back from the Ws struct in shared memory: values loaded from memory are
+    // not provably uniform, so a dozen 64-bit pointers would each pin two vector registers for the whole alignment -- with
+    // 128 registers per thread that was what pushed loop invariants onto the stack (two local-memory reloads per row, 9 % of
+    // all stall samples in the ncu source view).  Uniform values live in uniform registers or are rematerialised for free.
+    char *const slab = wsb + L.o_slab, *const qp = wsb + L.o_qp;
+    const int4 *const rowinfo = reinterpret_cast<const int4 *>(wsb + L.o_rowinfo);
+    int4 *const rowmeta = reinterpret_cast<int4 *>(wsb + L.o_rowmeta);
+    const int *const pool_row = reinterpret_cast<const int *>(wsb + L.o_pool_row), *const rr = reinterpret_cast<const int *>(wsb + L.o_rr);
+    int *const mplr = reinterpret_cast<int *>(wsb + L.o_mplr), *const mprr = reinterpret_cast<int *>(wsb + L.o_mprr);
+    const uint8_t *const rbase = reinterpret_cast<const uint8_t *>(wsb + L.o_rbase);
+    const int *const fp = reinterpret_cast<const int *>(wsb + L.o_tmp0);  // build_rows(): row of the first predecessor
+    const int *const sp = reinterpret_cast<const int *>(wsb + L.o_tmp1);  // build_rows(): row of the second predecessor, -1 if there is none
 #ifndef POA_HOST_EMU
     __builtin_assume(__isGlobal(slab)); __builtin_assume(__isGlobal(qp)); __builtin_assume(__isGlobal(rowinfo));
     __builtin_assume(__isGlobal(rowmeta)); __builtin_assume(__isGlobal(pool_row)); __builtin_assume(__isGlobal(rr));
@@ -208,13 +213,23 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
     // packed constants
     const int emax = imax(e1, e2);
     const int negl = -32768 + 8 * emax + 8;  // below every value a band cell can take, never wraps when used
-    const unsigned INFP = p_pack(inf_min, inf_min), NEGLP = p_pack(negl, negl), ZERO = 0u;
-    const unsigned NOE1 = p_pack(-oe1, -oe1), NOE2 = p_pack(-oe2, -oe2), NE1 = p_pack(-e1, -e1), NE2 = p_pack(-e2, -e2);
-    const unsigned NE1_2 = p_add(NE1, NE1), NE1_3 = p_add(NE1_2, NE1);
-    const unsigned NE2_2 = p_add(NE2, NE2), NE2_3 = p_add(NE2_2, NE2);
+    (void)negl;
+    // uniform ones come from the constant bank (DevParams::pk_*, build_params()); the lane-dependent four stay in registers
+#define INFP (P.pk_inf)
+#define NEGLP (P.pk_negl)
+#define NOE1 (P.pk_noe1)
+#define NOE2 (P.pk_noe2)
+#define NE1 (P.pk_ne1)
+#define NE2 (P.pk_ne2)
+#define NE1_2 (P.pk_ne1_2)
+#define NE1_3 (P.pk_ne1_3)
+#define NE2_2 (P.pk_ne2_2)
+#define NE2_3 (P.pk_ne2_3)
+#define NCW1 (P.pk_ncw1)
+#define NCW2 (P.pk_ncw2)
+    const unsigned ZERO = 0u;
     const unsigned OFF1 = p_pack(e1 * 4 * (lane + 1), e1 * 4 * (lane + 33)), NOFF1 = p_pack(-e1 * 4 * lane, -e1 * 4 * (lane + 32));
     const unsigned OFF2 = p_pack(e2 * 4 * (lane + 1), e2 * 4 * (lane + 33)), NOFF2 = p_pack(-e2 * 4 * lane, -e2 * 4 * (lane + 32));
-    const unsigned NCW1 = p_pack(-e1 * P16_CW, -e1 * P16_CW), NCW2 = p_pack(-e2 * P16_CW, -e2 * P16_CW);
     const int f0_1 = imax(inf_min - oe1, inf_min - e1), f0_2 = imax(inf_min - oe2, inf_min - e2);
 
     // ---- query profile in the chunked layout: qp[base][chunk][lane] (abpoa_align_simd.c:531-546)
@@ -631,7 +646,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
                 const int pi = pool_row[ri.x + k];
                 const int4 pm = rowmeta[pi];
                 const int e = qlen > pm.z ? pm.z : qlen;
-                const int sc = *cell_ptr16(w, pm, 0, e);
+                const int sc = *cell_ptr16(sh.ws, pm, 0, e);
                 if (sc > best_score) { best_score = sc; best_i = pi; best_j = e; }
             }
         }
@@ -640,6 +655,18 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, 
     }
     sync_block<NW>();
 }
+#undef INFP
+#undef NEGLP
+#undef NOE1
+#undef NOE2
+#undef NE1
+#undef NE2
+#undef NE1_2
+#undef NE1_3
+#undef NE2_2
+#undef NE2_3
+#undef NCW1
+#undef NCW2
 
 // ------------------------------------------------------------------------------------------------
 // F1 / F2 of row i at columns j and j - 1, for the traceback's insertion steps (abpoa_align_simd.c:420-445 reads

@@ -40,6 +40,15 @@ inline void build_params(const poa_b200_params_t &p, const poa_b200_engine_opts_
     // and the scan's position offsets
     const long long emax = std::max(d.e1, d.e2);
     d.gap_mode = p.gap_open1 == 0 ? 2 : (p.gap_open2 == 0 ? 1 : 0);  // abpoa_align.c:87-91
+    {   // packed constants of the 16-bit fill (poa_fill16.cuh); same expressions as the kernel used to evaluate per alignment
+        auto pk = [](long long v) { const unsigned h = (unsigned)(v & 0xffff); return h | (h << 16); };
+        const long long bm = INT16_MIN;
+        const long long inf16 = std::max(bm + d.min_mis, std::max(bm + d.oe1, bm + d.oe2)) + 512 * emax;  // inf_min_of<short>()
+        d.pk_inf = pk(inf16); d.pk_negl = pk(-32768 + 8 * emax + 8);
+        d.pk_noe1 = pk(-d.oe1); d.pk_noe2 = pk(-d.oe2); d.pk_ne1 = pk(-d.e1); d.pk_ne2 = pk(-d.e2);
+        d.pk_ne1_2 = pk(-2LL * d.e1); d.pk_ne1_3 = pk(-3LL * d.e1); d.pk_ne2_2 = pk(-2LL * d.e2); d.pk_ne2_3 = pk(-3LL * d.e2);
+        d.pk_ncw1 = pk(-256LL * d.e1); d.pk_ncw2 = pk(-256LL * d.e2);
+    }
     d.p16_ok = d.gap_mode == 0 && (o.flags & 1) == 0 && emax >= 1 && emax <= 100 && 240 * emax >= (long long)d.min_mis + std::max(d.oe1, d.oe2) + 64
                && d.oe1 > d.e1 && d.oe2 > d.e2;
 }

@@ -28,7 +28,7 @@ H_OFF_LO, H_OFF_HI = 11, 12  # header slots holding a block body's word offset i
 ABI_SYMBOLS = [
     "poa_b200_abi_version", "poa_b200_strerror", "poa_b200_last_error",
     "poa_b200_encode_bases", "poa_b200_engine_create", "poa_b200_engine_destroy", "poa_b200_engine_trim",
-    "poa_b200_run_batch", "poa_b200_poa_block",
+    "poa_b200_run_batch", "poa_b200_poa_block", "poa_b200_submit_block", "poa_b200_wait_block",
     "poa_b200_batch_upload", "poa_b200_batch_launch", "poa_b200_batch_download", "poa_b200_batch_finish",
     "poa_b200_batch_free", "poa_b200_batch_stats", "poa_b200_batch_device_result", "poa_b200_result_from_parts", "poa_b200_result_from_device_parts",
     "poa_b200_result_n_blocks", "poa_b200_result_block", "poa_b200_result_release_block", "poa_b200_result_block_hash", "poa_b200_result_stats", "poa_b200_result_free",
@@ -155,6 +155,8 @@ def load_library() -> C.CDLL:
     lib.poa_b200_run_batch.argtypes = batch_args
     lib.poa_b200_batch_upload.argtypes = batch_args
     lib.poa_b200_poa_block.argtypes = [vp, C.POINTER(PoaParams), i32, C.POINTER(C.c_void_p), vp, vp, C.POINTER(vp)]
+    lib.poa_b200_submit_block.argtypes = [vp, C.POINTER(PoaParams), i32, C.POINTER(C.c_void_p), vp, vp, C.POINTER(C.c_uint64)]
+    lib.poa_b200_wait_block.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
     lib.poa_b200_batch_launch.argtypes = [vp, vp]
     lib.poa_b200_batch_download.argtypes = [vp, vp, C.POINTER(vp)]
     lib.poa_b200_batch_finish.argtypes = [vp, vp]
@@ -435,6 +437,21 @@ class PoaEngine:
     def trim(self):
         """Return pooled device / pinned buffers to the driver (poa_b200_engine_trim)."""
         _check(self._lib, self._lib.poa_b200_engine_trim(self._h))
+
+    def submit_block(self, seqs, weights, params: PoaParams) -> int:
+        """Queue one block for the engine's coalescing dispatcher; returns a ticket (poa_b200_submit_block)."""
+        seqs = [_c(s, np.uint8) for s in seqs]
+        n = len(seqs)
+        ptrs = (C.c_void_p * max(n, 1))(*[s.ctypes.data for s in seqs])
+        lens = _c([s.shape[0] for s in seqs], np.int32); wts = _c(weights, np.int32)
+        t = C.c_uint64()
+        _check(self._lib, self._lib.poa_b200_submit_block(self._h, C.byref(params), n, ptrs, lens.ctypes.data, wts.ctypes.data, C.byref(t)))
+        return int(t.value)
+
+    def wait_block(self, ticket: int) -> PoaResult:
+        r = C.c_void_p()
+        _check(self._lib, self._lib.poa_b200_wait_block(self._h, C.c_uint64(ticket), C.byref(r)))
+        return PoaResult(self._lib, r)
 
     def close(self):
         if self._h:

@@ -132,9 +132,9 @@ extern "C" int32_t *emu_poa_block(const pd_params_t *pp, int n_seq, const int32_
     sh.ring_bytes = POA_EMU_NW == 1 ? P16_SMEM_BYTES : p16_mw_smem_bytes<POA_EMU_NW>();
 #endif
 #if POA_EMU_LANES > 1
-    poa_emu::run_warp([&]() { poa_block<POA_EMU_NW>(sh, dp, B, L, O, 0); });
+    poa_emu::run_warp([&]() { poa_block<POA_EMU_NW>(sh, dp, B, L, O, 0, wsp); });
 #else
-    poa_block<1>(sh, dp, B, L, O, 0);
+    poa_block<1>(sh, dp, B, L, O, 0, wsp);
 #endif
     if (getenv("POA_EMU_VERBOSE")) fprintf(stderr, "[emu] packed-16 alignments: %llu of %d\n", phase[PH_SPARE], n_seq > 0 ? n_seq - 1 : 0);
     if (hdr[H_STATUS] != ST_OK) { fprintf(stderr, "[emu] block status %d\n", hdr[H_STATUS]); *n_out = -hdr[H_STATUS]; return nullptr; }
