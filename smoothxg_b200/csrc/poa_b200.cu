@@ -210,6 +210,7 @@ struct poa_b200_engine {
     cudaStream_t stream = nullptr;
     poa_b200_engine_opts_t opts{};
     std::mutex mu;
+    int occ[4] = {16, 6, 3, 1};  // resident CTAs per SM of poa_b200_block_kernel<1 / 2 / 4 / 8> (occupancy calculator, engine_create)
     size_t total_mem = 0;
     std::shared_ptr<PinnedPool> pinned = std::make_shared<PinnedPool>();
     DevicePool dev_pool;
@@ -356,7 +357,10 @@ Sizing size_for(const poa_b200_batch *b, const std::vector<int> &blocks, int lev
     const long long vecs_per_row = width / 8 + 2;
     // int16 rows unless the block can reach the int32 regime (abpoa_align_simd.c:1293-1302)
     const long long len = std::max(max_len, nmax);
-    const bool may32 = std::max<long long>(max_len * b->dp.match, len * b->dp.e1 + b->dp.o1) > (long long)INT16_MAX - b->dp.min_mis - b->dp.oe1 - b->dp.oe2;
+    // ... unless 16-bit cells provably hold every real value however long the graph gets (p16_safe_for_long_graph, poa_core.cuh:
+    // monotone in the query length, so the block's longest sequence decides for all of its alignments)
+    const bool may32 = std::max<long long>(max_len * b->dp.match, len * b->dp.e1 + b->dp.o1) > (long long)INT16_MAX - b->dp.min_mis - b->dp.oe1 - b->dp.oe2
+                       && !(b->dp.p16_ok && p16_safe_for_long_graph(b->dp, max_len, max_len));
     Sizing s;
     s.nmax = nmax; s.max_bases = max_bases; s.max_len = max_len; s.max_seq = max_seq;
     const long long edges = std::min<long long>(max_bases + max_seq, level >= LEVEL_WORST ? (1LL << 60) : 3 * nmax);
@@ -387,16 +391,26 @@ int run_launch(poa_b200_batch *b, const std::vector<int> &blocks, int level, cud
     Sizing sz = size_for(b, blocks, level, rows_factor);
     WsLayout L;
     make_layout(L, sz.nmax, sz.max_bases, sz.max_len, sz.max_seq, sz.pool_growth, sz.slab_bytes, b->dp.emit_cigar);
-    // how many CTAs
+    // How many warps per POA block, how many resident blocks per SM.  One warp per block (fill_p16) is by far the most efficient
+    // use of the machine -- the per-row part of the work is serial and every further warp repeats it -- so several warps per
+    // block only pay when the batch cannot fill the resident single-warp slots anyway: measured per-block time on 16 x 1 kb
+    // blocks 62.7 ms with one warp, 66.6 with two, 47 with four (profiles/bench_r02_mw_*).  So: one warp while the blocks fill
+    // the four-warp slots, else four, else eight (deep blocks: one block per SM, only row latency matters).  Resident CTAs per
+    // SM come from the occupancy calculator of the instantiation actually launched (registers differ: 128 / 168 / 168 / 183).
     int nw = eng->opts.warps_per_block;
     if (nw != 1 && nw != 2 && nw != 4 && nw != 8) {
-        // one warp per POA block whenever the packed 16-bit fill applies and every SM gets a couple of blocks: that
-        // path is several times leaner than the generic multi-warp fill (1 000 x 16 x 1 kb: 136 vs 56 Gcells/s)
-        long long target_warps = (b->dp.p16_ok ? 2LL : 16LL) * eng->n_sm;
+        const long long nb_ = (long long)blocks.size();
         nw = 1;
-        while (nw < 8 && (long long)nw * (long long)blocks.size() < target_warps) nw *= 2;
+        if (b->dp.p16_ok) {
+            if (nb_ <= (long long)eng->n_sm * eng->occ[3]) nw = 8;
+            else if (nb_ <= (long long)eng->n_sm * eng->occ[2]) nw = 4;
+        } else {
+            // generic fill (int32 / affine / linear): its vectors are dealt to all threads of the block
+            while (nw < 8 && (long long)nw * nb_ < 16LL * eng->n_sm) nw *= 2;
+        }
     }
-    int per_sm = eng->opts.ctas_per_sm > 0 ? eng->opts.ctas_per_sm : std::max(1, 16 / nw);
+    const int occ = eng->occ[nw == 1 ? 0 : (nw == 2 ? 1 : (nw == 4 ? 2 : 3))];
+    int per_sm = eng->opts.ctas_per_sm > 0 ? eng->opts.ctas_per_sm : std::max(1, occ);
     per_sm = std::min(per_sm, 32);
     long long n_ctas = std::min<long long>((long long)blocks.size(), (long long)eng->n_sm * per_sm);
     size_t free_b = 0, total_b = 0;
@@ -604,6 +618,18 @@ int poa_b200_engine_create(int device, const poa_b200_engine_opts_t *opts, poa_b
     e->device = device; e->n_sm = prop.multiProcessorCount; e->total_mem = prop.totalGlobalMem;
     if (opts) e->opts = *opts;
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    {
+        cudaFuncSetAttribute(poa_b200_block_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(poa_b200_block_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(poa_b200_block_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(poa_b200_block_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, poa_b200_block_kernel<1>, 32, P16_SMEM_BYTES) == cudaSuccess && o > 0) e->occ[0] = o;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, poa_b200_block_kernel<2>, 64, p16_mw_smem_bytes<2>()) == cudaSuccess && o > 0) e->occ[1] = o;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, poa_b200_block_kernel<4>, 128, p16_mw_smem_bytes<4>()) == cudaSuccess && o > 0) e->occ[2] = o;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, poa_b200_block_kernel<8>, 256, p16_mw_smem_bytes<8>()) == cudaSuccess && o > 0) e->occ[3] = o;
+        cudaGetLastError();
+    }
     *out = e;
     return POA_B200_OK;
 }

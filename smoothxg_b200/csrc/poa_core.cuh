@@ -91,6 +91,12 @@ POA_D void poa_red_max(int *p, int v) { atomicMax(p, v); }
 POA_D void poa_red_min(int *p, int v) { atomicMin(p, v); }
 #endif
 
+#ifdef POA_HOST_EMU
+#define POA_HD static inline
+#else
+#define POA_HD __host__ __device__ __forceinline__
+#endif
+
 namespace poa {
 
 constexpr int SRC_ID = 0, SINK_ID = 1;
@@ -123,11 +129,6 @@ struct WireLayout {
     long long o_base, o_aln_n, o_in_n, o_out_n, o_in_id, o_in_w, o_out_id, o_out_w, o_aln_id;  // word offsets from the body start
     long long o_plen, o_best, o_ncig, o_nrun, o_runs, o_cig, o_msa, words;
 };
-#ifdef POA_HOST_EMU
-#define POA_HD static inline
-#else
-#define POA_HD __host__ __device__ __forceinline__
-#endif
 POA_HD void wire_layout(WireLayout &W, long long n, long long n_seq, long long in_tot, long long out_tot, long long aln_tot, long long run_tot,
                        long long cig_tot, long long msa_bytes, int format) {
     const long long ew = format == WIRE_WIDE ? 4 : 2;
@@ -175,6 +176,33 @@ struct DevParams {
     unsigned pk_inf, pk_negl, pk_noe1, pk_noe2, pk_ne1, pk_ne2, pk_ne1_2, pk_ne1_3, pk_ne2_2, pk_ne2_3, pk_ncw1, pk_ncw2;
 };
 
+// ------------------------------------------------------------------------------------------------
+// When 16-bit cells are enough although abPOA itself would switch to 32 bits.
+// abPOA picks int32 as soon as max(qlen * match, max(qlen, graph rows) * e1 + o1) could leave the int16 range
+// (abpoa_align_simd.c:1293-1302) -- a bound on a gap as long as the GRAPH HAS ROWS, which a deep block passes quickly
+// (256 x 8 kb: 28 592 rows) although no cell of a global alignment can be that far down: every node lies on the path of some
+// sequence of the block, so it is at most Lmax = max sequence length steps from the source, and cell (row, j) is reachable by
+// j inserted bases plus at most Lmax deleted nodes.  Hence every REAL cell (H, and E/F which are >= H - oe) is at least
+//   real_min = -(gap(qlen) + gap(Lmax)) - max(oe1, oe2),     gap(k) = min(o1 + e1 k, o2 + e2 k)   (o2 = 0: o1 + e1 k),
+// and at most qlen * match.  Cells no real path reaches hold inf_min16-derived junk, at most inf_min16 + qlen * match (a junk
+// value grows by at most `match` per row).  If junk_max stays below real_min, junk never wins a max against a real value, so the
+// 16-bit fill computes every real cell exactly as abPOA's 32-bit kernel does and the traceback, which only ever follows
+// equalities between real cells, takes the same steps.  (What does differ between the two kernels, the vector width of the
+// band-start rounding rule, is passed in: pn32 instead of pn16.)  Global mode only; local alignments keep the generic path.
+// ------------------------------------------------------------------------------------------------
+POA_HD bool p16_safe_for_long_graph(const DevParams &P, long long qlen, long long lmax) {
+    if (P.local || P.gap_mode != 0) return false;
+    const long long g1q = P.o1 + (long long)P.e1 * qlen, g2q = P.o2 + (long long)P.e2 * qlen;
+    const long long g1l = P.o1 + (long long)P.e1 * lmax, g2l = P.o2 + (long long)P.e2 * lmax;
+    const long long gq = g1q < g2q ? g1q : g2q, gl = g1l < g2l ? g1l : g2l;
+    const long long oe = P.oe1 > P.oe2 ? P.oe1 : P.oe2, emax = P.e1 > P.e2 ? P.e1 : P.e2;
+    const long long real_min = -(gq + gl) - oe - P.min_mis;
+    long long a = -32768LL + P.min_mis, b = -32768LL + P.oe1, c = -32768LL + P.oe2;
+    const long long inf16 = (a > b ? (a > c ? a : c) : (b > c ? b : c)) + 512 * emax;  // inf_min_of<short>()
+    const long long junk_max = inf16 + qlen * P.match + 2 * oe;
+    return junk_max + 1024 < real_min;
+}
+
 // Device-resident batch input (flat, same arrays as the C ABI takes).
 struct DevBatch {
     const long long *block_seq_off;
@@ -191,7 +219,7 @@ struct WsLayout {
     long long stride;  // bytes per CTA
     long long o_base, o_aln_n, o_aln, o_in_off, o_in_n, o_out_off, o_out_n, o_pool_id, o_pool_w, o_pool_row;
     long long o_idx2id, o_id2idx, o_remain, o_tmp0, o_tmp1, o_tmp2, o_tmp3;
-    long long o_rowinfo, o_rowmeta, o_rbase, o_rr, o_mplr, o_mprr;
+    long long o_rowinfo, o_rowmeta, o_rbase, o_rr, o_mplr, o_mprr, o_pred4;
     long long o_cig, o_path, o_best, o_ncig, o_plen, o_nrun, o_qp, o_slab;
     long long slab_bytes;
     int nmax;      // node capacity
@@ -213,6 +241,7 @@ struct Ws {
     int *aln, *in_off, *in_n, *out_off, *out_n, *pool_id, *pool_w, *pool_row;
     int *idx2id, *id2idx, *remain, *tmp0, *tmp1, *tmp2, *tmp3;
     int4 *rowinfo, *rowmeta;
+    int4 *pred4;  // build_rows(): rows of a row's first four predecessors in in_id order, -1 where there is none
     int *rr, *mplr, *mprr;
     unsigned long long *cig;
     int *path, *best, *ncig, *plen;
@@ -592,9 +621,14 @@ POA_DN void build_rows(Shared &sh, int qlen, int banded) {
             w.rbase[i] = (uint8_t)bs[u];
             w.tmp0[i] = fpid[u] >= 0 ? fpid[u] : 0;  // backtrack(), fill_p16(): row of the first predecessor
             if (in[u] > 0) w.pool_row[ioff[u]] = fpid[u];
-            int sp_row = -1;
-            for (int k = 1; k < in[u]; ++k) { const int pr = w.id2idx[w.pool_id[ioff[u] + k]]; w.pool_row[ioff[u] + k] = pr; if (k == 1) sp_row = pr; }
-            w.tmp1[i] = sp_row;  // fill_p16(): row of the second predecessor (prefetched with the row's metadata), -1 if none
+            int4 p4 = poa_make_int4(in[u] > 0 ? fpid[u] : -1, -1, -1, -1);
+            for (int k = 1; k < in[u]; ++k) {
+                const int pr = w.id2idx[w.pool_id[ioff[u] + k]];
+                w.pool_row[ioff[u] + k] = pr;
+                if (k == 1) p4.y = pr; else if (k == 2) p4.z = pr; else if (k == 3) p4.w = pr;
+            }
+            w.pred4[i] = p4;  // multi-warp packed fill: the first four predecessors' rows, prefetched with the row's metadata
+            w.tmp1[i] = p4.y;  // fill_p16(): row of the second predecessor, -1 if none
             for (int k = 0; k < on[u]; ++k) w.pool_row[ooff[u] + k] = w.id2idx[w.pool_id[ooff[u] + k]];
             if (banded) {
                 w.rr[i] = qlen - rm[u];       // qlen - (remain[v] - remain[sink] - 1), remain[sink] = -1
@@ -1420,7 +1454,7 @@ POA_D void ws_bind(Ws &w, char *b, const WsLayout &L) {
     w.idx2id = (int *)(b + L.o_idx2id); w.id2idx = (int *)(b + L.o_id2idx); w.remain = (int *)(b + L.o_remain);
     w.tmp0 = (int *)(b + L.o_tmp0); w.tmp1 = (int *)(b + L.o_tmp1); w.tmp2 = (int *)(b + L.o_tmp2); w.tmp3 = (int *)(b + L.o_tmp3);
     w.rowinfo = (int4 *)(b + L.o_rowinfo); w.rowmeta = (int4 *)(b + L.o_rowmeta); w.rbase = (uint8_t *)(b + L.o_rbase);
-    w.rr = (int *)(b + L.o_rr); w.mplr = (int *)(b + L.o_mplr); w.mprr = (int *)(b + L.o_mprr);
+    w.rr = (int *)(b + L.o_rr); w.mplr = (int *)(b + L.o_mplr); w.mprr = (int *)(b + L.o_mprr); w.pred4 = (int4 *)(b + L.o_pred4);
     w.cig = (unsigned long long *)(b + L.o_cig); w.path = (int *)(b + L.o_path); w.best = (int *)(b + L.o_best); w.ncig = (int *)(b + L.o_ncig); w.plen = (int *)(b + L.o_plen); w.nrun = (int *)(b + L.o_nrun);
     w.qp = b + L.o_qp; w.slab = b + L.o_slab;
 }
@@ -1483,6 +1517,8 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
     }
     sync_block<NW>();
 
+    int block_lmax = 0;  // longest sequence of the block (p16_safe_for_long_graph)
+    for (int k = 0; k < n_seq; ++k) block_lmax = imax(block_lmax, B.seq_len[s0 + k]);
     int cig_tot = 0;
     for (int k = 0; k < n_seq && sh.err == ST_OK; ++k) {
         const int qlen = B.seq_len[s0 + k];
@@ -1510,15 +1546,18 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
             long long max_score = ms1 > ms2 ? ms1 : ms2;
             const bool bits16 = max_score <= (long long)INT16_MAX - P.min_mis - P.oe1 - P.oe2;
 #if POA_WARP == 32
-            const bool p16 = bits16 && p16_eligible(P, qlen);
+            // packed 16-bit fill: whenever abPOA itself computes in int16, and beyond that while 16-bit cells provably hold every
+            // real value (p16_safe_for_long_graph: deep blocks, whose graphs outgrow abPOA's int16 rule long before their scores do)
+            const bool p16 = p16_eligible(P, qlen) && (bits16 || p16_safe_for_long_graph(P, qlen, block_lmax));
+            const int p16_pn = bits16 ? P.pn16 : P.pn32;  // vector width of the reference kernel whose band-start rounding is reproduced
 #else
             const bool p16 = false;
 #endif
             if (p16) {
                 t_ph[PH_SPARE] += 1;  // alignments that took the packed 16-bit fill
 #if POA_WARP == 32
-                if (NW == 1) { if (P.local) fill_p16<NW, true>(sh, P, L, wsb, q, qlen); else fill_p16<NW, false>(sh, P, L, wsb, q, qlen); }
-                else { if (P.local) fill_p16_mw<NW, true>(sh, P, q, qlen, L.slab_bytes); else fill_p16_mw<NW, false>(sh, P, q, qlen, L.slab_bytes); }
+                if (NW == 1) { if (P.local) fill_p16<NW, true>(sh, P, L, wsb, q, qlen, p16_pn); else fill_p16<NW, false>(sh, P, L, wsb, q, qlen, p16_pn); }
+                else { if (P.local) fill_p16_mw<NW, true>(sh, P, q, qlen, L.slab_bytes, p16_pn); else fill_p16_mw<NW, false>(sh, P, q, qlen, L.slab_bytes, p16_pn); }
 #endif
             } else if (P.gap_mode == 0) {
                 if (bits16) fill<NW, short, 0>(sh, P, q, qlen, L.slab_bytes / 16); else fill<NW, int, 0>(sh, P, q, qlen, L.slab_bytes / 32);

@@ -70,8 +70,10 @@ constexpr int P16_PLANES = 3;
 constexpr int P16_SMCH = POA_P16_SMCH;  // chunks of the previous row kept in shared memory (H, E1, E2)
 constexpr int P16_RING_BYTES = P16_SMCH * 3 * P16_CPB;
 constexpr int P16_QCH = POA_P16_QCH;   // profile chunks of the row in flight staged in shared memory
-constexpr int P16_QBUF_OFF = P16_RING_BYTES, P16_META_OFF = P16_QBUF_OFF + P16_QCH * P16_CPB;  // meta: 2 x 128 B + 128 B
-constexpr int P16_SMEM_BYTES = P16_META_OFF + 3 * 128;
+constexpr int P16_QBUF_OFF = P16_RING_BYTES, P16_META_OFF = P16_QBUF_OFF + P16_QCH * P16_CPB;
+constexpr int P16_SLOT = 160;                                  // one row's prefetched metadata (layout: fill_p16)
+constexpr int P16_OUTS_OFF = P16_META_OFF + 2 * P16_SLOT;     // + 128 B: the row's successor rows
+constexpr int P16_SMEM_BYTES = P16_OUTS_OFF + 128;
 
 // address of cell (plane, j) of a row stored in the chunked layout; pm = {first chunk-plane of the row, beg, end, _}
 POA_D const short *cell_ptr16(const Ws &w, const int4 &pm, int plane, int j) {
@@ -173,13 +175,12 @@ template <int N> struct p16_n { static constexpr int value = N; };
 // and it needs 168 registers (12 resident warps per SM instead of 16): 188-211 Gcells/s against 250 for N = 1; N = 3 and 4 are
 // slower still (150 / 122).  So N = 1 ships; the switch stays for the next machine with a larger L0/L1.5 I-cache.
 template <int NW, bool LOCAL>
-POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *const wsb, const uint8_t *q, int qlen) {
+POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *const wsb, const uint8_t *q, int qlen, const int pn) {
     const long long slab_bytes = L.slab_bytes;
     const int lane = poa_tid();
     const int n_node = sh.n_node;
     const int rows = n_node - 1;  // the sink row is never filled
     const int inf_min = inf_min_of<short>(P);
-    const int pn = P.pn16;
     constexpr bool local = LOCAL;
     const int wb = local ? -1 : P.wb;  // abpoa_align.c:158
 #ifdef POA_HOST_EMU
@@ -310,7 +311,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
     else if (lane == 8) { gsrc = (const char *)sp; gdst = 96; gkind = 3; }
     auto gather = [&](const int n1, const int np0_n1, const int nsp_n1, const int cur) {  // row n1 into its slot; `cur`: row being evaluated
         if (n1 >= rows) return;
-        const unsigned slot = P16_META_OFF + (unsigned)(n1 & 1) * 128 + gdst;
+        const unsigned slot = P16_META_OFF + (unsigned)(n1 & 1) * P16_SLOT + gdst;
         // element index of this lane's item: the row itself, one of its first two predecessors (lanes 1, 7), the row after
         // (lanes 3, 8), or the 4-element window holding it (byte / reduction-updated arrays)
         int idx = n1;
@@ -331,7 +332,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
     for (int i = 1; i < rows; ++i) {
         cpa_wait_pending(0);
         sync_block<NW>();  // the slot was filled by other lanes' copies
-        const unsigned slot = P16_META_OFF + (unsigned)(i & 1) * 128;
+        const unsigned slot = P16_META_OFF + (unsigned)(i & 1) * P16_SLOT;
         const uint4 ri_u = ring_ld(sm, slot), npm_u = ring_ld(sm, slot + 16), spm_u = ring_ld(sm, slot + 80);
         const int4 ri = poa_make_int4((int)ri_u.x, (int)ri_u.y, (int)ri_u.z, (int)ri_u.w);  // {in_off, in_n, out_off, out_n}
         const int rb = (ring_ld32(sm, slot + 32) >> (8 * (i & 3))) & 0xff, p0 = np0, s0 = nsp;
@@ -345,7 +346,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
         // next row's metadata; its band inputs miss only this row's contribution, forwarded below
         gather(i + 1, nnp0, nnsp, i);
         // rows this row hands its arg-max columns to (one per lane; staged now, used after the last chunk)
-        if (lane < ri.w) cpa4(sm, P16_META_OFF + 256 + lane * 4, &pool_row[ri.z + lane]);
+        if (lane < ri.w) cpa4(sm, P16_OUTS_OFF + lane * 4, &pool_row[ri.z + lane]);
         cpa_commit();
         np0 = nnp0; nsp = nnsp;
         // profile chunks of this row: staged now for the chunk range the previous row covered plus one (bands move
@@ -627,7 +628,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
             if (local && rmx > best_score) { best_score = rmx; best_i = i; best_j = left; }  // abpoa_align_simd.c:1208-1210
             if (wb >= 0) {  // abpoa_align_simd.c:1121-1130; reductions without a return value: nothing to wait for
                 cpa_wait_pending(0);
-                if (lane < ri.w) { const int out_row = ring_ld32(sm, P16_META_OFF + 256 + lane * 4); poa_red_max(&mprr[out_row], right + 1); poa_red_min(&mplr[out_row], left + 1); }
+                if (lane < ri.w) { const int out_row = ring_ld32(sm, P16_OUTS_OFF + lane * 4); poa_red_max(&mprr[out_row], right + 1); poa_red_min(&mplr[out_row], left + 1); }
                 for (int k = lane + POA_WARP; k < ri.w; k += POA_WARP) {
                     const int o = pool_row[ri.z + k];
                     poa_red_max(&mprr[o], right + 1); poa_red_min(&mplr[o], left + 1);
@@ -775,28 +776,39 @@ POA_DN void p16_row_f(Shared &sh, const DevParams &P, int qlen, int i, int j, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// Packed 16-bit fill for NW > 1 warps per POA block (small or deep batches: few blocks, long rows).
-// Same arithmetic and row layout as fill_p16(); the 256-column chunks of a row are dealt to the warps
-// (chunk c belongs to warp c % NW), NW chunks per round:
-//   phase A  each warp gathers its chunk's predecessors, runs the per-lane chains and the lane-half scan;
-//            lane 0 publishes the chunk's scan total (per gap piece) in shared memory        -- barrier --
-//   phase B  every warp replays the cheap scalar carry chain over the round's totals up to its own chunk,
-//            fixes up F, finishes H / E, stores.
-// A warp only ever reads ring slots it wrote itself (chunk ownership is by absolute chunk number); the one
-// cross-warp operand, the predecessor's last cell of the previous chunk, goes through a small shared array.
+// Packed 16-bit fill for NW > 1 warps per POA block (small or deep batches: few blocks, long rows -- with one block per SM the
+// only thing that matters is the latency of one row, and the chunks of a row are the only parallelism a row has).
+// Same arithmetic and row layout as fill_p16(); the 256-column chunks of a row are dealt to the warps (chunk c belongs to warp
+// c % NW), NW chunks per round:
+//   row start  -- barrier --  every warp reads the row's metadata from shared memory (gathered one row ahead by warp 0 with
+//              cp.async, exactly as in fill_p16: rowinfo, the first two predecessors' descriptors, base, band inputs) and the
+//              previous row's arg-max candidates, and computes the band redundantly (a few dozen ALU instructions);
+//   phase A    each warp gathers its chunk's predecessors, runs the per-lane chains and the lane-half scan; lane 0 publishes
+//              the chunk's scan total (per gap piece) in shared memory                                   -- barrier --
+//   phase B    every warp replays the cheap scalar carry chain over the round's totals up to its own chunk, fixes up F,
+//              finishes H / E, stores; after its last chunk it publishes its own row maximum with the first / last column
+//              attaining it (from its ring slots: no global re-read), which the next row start combines.
+// One barrier per row plus one per round, no global-memory round trip on the row-to-row critical path.  A warp only ever
+// reads ring slots it wrote itself (chunk ownership is by absolute chunk number); the one cross-warp operand, the
+// predecessor's last cell of the previous chunk, goes through a small shared array.
 // ------------------------------------------------------------------------------------------------
 constexpr int P16_MW_SMCH = 3;  // ring chunks per warp (rows up to 3 * NW chunks stay resident)
-template <int NW> struct p16_mw_smem { static constexpr int bytes = NW * P16_MW_SMCH * 3 * P16_CPB + 2 * NW * 8 + NW * 16 + 2 * 64 * 4 + 64; };
+template <int NW> struct p16_mw_smem {
+    static constexpr int o_xch = NW * P16_MW_SMCH * 3 * P16_CPB;  // [2 round parities][NW][2] scan totals
+    static constexpr int o_rowx = o_xch + 2 * NW * 2 * 4;         // [2 row parities][NW][4] row maximum, first / last column
+    static constexpr int o_lastH = o_rowx + 2 * NW * 4 * 4;       // [2 row parities][64] last H cell of a chunk
+    static constexpr int o_meta = (o_lastH + 2 * 64 * 4 + 15) & ~15;  // 2 row metadata slots (P16_SLOT), 2 x 128 B successor rows
+    static constexpr int bytes = o_meta + 2 * P16_SLOT + 2 * 128;
+};
 template <int NW> constexpr int p16_mw_smem_bytes() { return p16_mw_smem<NW>::bytes; }
 
 template <int NW, bool LOCAL>
-POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, long long slab_bytes) {
+POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int qlen, long long slab_bytes, const int pn) {
     Ws &w = sh.ws;
     const int tid = poa_tid(), lane = tid & 31, wid = tid >> 5;
     const int n_node = sh.n_node;
     const int rows = n_node - 1;
     const int inf_min = inf_min_of<short>(P);
-    const int pn = P.pn16;
     constexpr bool local = LOCAL;
     const int wb = local ? -1 : P.wb;
 #ifdef POA_HOST_EMU
@@ -808,14 +820,15 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
     char *const slab = w.slab, *const qp = w.qp;
     const int4 *const rowinfo = w.rowinfo;
     int4 *const rowmeta = w.rowmeta;
-    const int *const pool_row = w.pool_row, *const rr = w.rr, *const fp = w.tmp0;
+    const int *const pool_row = w.pool_row, *const rr = w.rr;
+    const int4 *const pred4 = w.pred4;
     int *const mplr = w.mplr, *const mprr = w.mprr;
     const uint8_t *const rbase = w.rbase;
 #ifndef POA_HOST_EMU
     __builtin_assume(__isGlobal(slab)); __builtin_assume(__isGlobal(qp)); __builtin_assume(__isGlobal(rowinfo));
     __builtin_assume(__isGlobal(rowmeta)); __builtin_assume(__isGlobal(pool_row)); __builtin_assume(__isGlobal(rr));
     __builtin_assume(__isGlobal(mplr)); __builtin_assume(__isGlobal(mprr)); __builtin_assume(__isGlobal(rbase));
-    __builtin_assume(__isGlobal(q)); __builtin_assume(__isGlobal(fp));
+    __builtin_assume(__isGlobal(q)); __builtin_assume(__isGlobal(pred4));
 #endif
     const long long slab_units = slab_bytes / P16_CPB;
     long long used = 0, inband = 0, edge_rows = 0;
@@ -827,11 +840,15 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
     const unsigned OFF1 = p_pack(e1 * 4 * (lane + 1), e1 * 4 * (lane + 33)), NOFF1 = p_pack(-e1 * 4 * lane, -e1 * 4 * (lane + 32));
     const unsigned OFF2 = p_pack(e2 * 4 * (lane + 1), e2 * 4 * (lane + 33)), NOFF2 = p_pack(-e2 * 4 * lane, -e2 * 4 * (lane + 32));
     const int f0_1 = imax(inf_min - oe1, inf_min - e1), f0_2 = imax(inf_min - oe2, inf_min - e2);
-    // shared memory: per-warp rings, round totals (two parities), per-warp row maxima, last H cell per chunk (two row parities)
+    // shared memory: per-warp rings, round totals (two parities), per-warp row maxima (two row parities), last H cell per chunk
+    // (two row parities), metadata slots
+    typedef p16_mw_smem<NW> SM;
     const ring_ptr_t ring = ring_base(sh.ring + wid * (P16_MW_SMCH * 3 * P16_CPB), lane);
-    int *const xch = reinterpret_cast<int *>(sh.ring + NW * P16_MW_SMCH * 3 * P16_CPB);  // [2][NW][2]
-    int *const rowx = xch + 2 * NW * 2;                                                   // [NW][4]
-    int *const lastH = rowx + NW * 4;                                                     // [2][64]
+    int *const xch = reinterpret_cast<int *>(sh.ring + SM::o_xch);
+    int *const rowx = reinterpret_cast<int *>(sh.ring + SM::o_rowx);
+    int *const lastH = reinterpret_cast<int *>(sh.ring + SM::o_lastH);
+    const ring_ptr_t sm = ring_base(sh.ring, 0);
+    constexpr unsigned META = (unsigned)SM::o_meta, OUTS = META + 2 * P16_SLOT;
 
     const int nchq = (qlen >> 8) + 1;
     for (int bc = wid; bc < 5 * nchq; bc += NW) {  // query profile, chunked layout
@@ -877,37 +894,108 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
         }
         used = (long long)P16_PLANES * nch;
         inband += end0 + 1;
-        sync_block<NW>();
+        sync_block<NW>();  // also orders row 0's band inputs (thread 0) before the first gather reads them
     }
     int best_score = inf_min, best_i = 0, best_j = 0;
     const int pshift = 31 - p_clz((unsigned)pn);
     char *const slab_lane = slab + lane * 16;
     const bool track = local || wb >= 0;
     int4 prev_meta = rowmeta[0];
-    int prev_left = 0, prev_right = 0;
+    int prev_left = 0, prev_right = 0;  // arg-max columns of row i - 1 ...
+    int pp_left = INT_MAX - 1, pp_right = -1;  // ... and of row i - 2 (see the band computation)
     bool prev_res = false;
+    int prev_out_z = 0, prev_out_n = 0;  // successor list of the previous row (band propagation, warp 0)
+    // metadata gather (warp 0): same slot layout as fill_p16
+    const char *gsrc = nullptr; unsigned gdst = 0; int gkind = 0;
+    if (wid == 0) {
+        if (lane == 0) { gsrc = (const char *)rowinfo; gdst = 0; gkind = 1; }
+        else if (lane == 1) { gsrc = (const char *)rowmeta; gdst = 16; gkind = 1; }
+        else if (lane == 2) { gsrc = (const char *)rbase; gdst = 32; gkind = 3; }
+        else if (lane == 3) { gsrc = (const char *)pred4; gdst = 96; gkind = 1; }
+        else if (lane == 4 && wb >= 0) { gsrc = (const char *)rr; gdst = 40; gkind = 3; }
+        else if (lane == 5 && wb >= 0) { gsrc = (const char *)mplr; gdst = 48; gkind = 2; }
+        else if (lane == 6 && wb >= 0) { gsrc = (const char *)mprr; gdst = 64; gkind = 2; }
+        else if (lane == 7) { gsrc = (const char *)rowmeta; gdst = 80; gkind = 1; }
+        else if (lane == 8) { gsrc = (const char *)rowmeta; gdst = 112; gkind = 1; }
+        else if (lane == 9) { gsrc = (const char *)rowmeta; gdst = 128; gkind = 1; }
+    }
+    auto gather = [&](const int n1, const int4 &p4_n1, const int cur) {  // warp 0: row n1 into its slot
+        if (n1 >= rows) return;
+        const unsigned slot = META + (unsigned)(n1 & 1) * P16_SLOT + gdst;
+        int idx = n1;
+        bool live = true;
+        if (lane == 1) { idx = p4_n1.x; live = idx >= 0 && idx < cur; }
+        else if (lane == 7) { idx = p4_n1.y; live = idx >= 0 && idx < cur; }
+        else if (lane == 8) { idx = p4_n1.z; live = idx >= 0 && idx < cur; }
+        else if (lane == 9) { idx = p4_n1.w; live = idx >= 0 && idx < cur; }
+        else if (lane == 3) { idx = n1 + 1; live = n1 + 1 < rows; }
+        if (gkind == 1 && live) cpa16(sm, slot, gsrc + (size_t)(unsigned)idx * 16, false);
+        else if (gkind == 2) cpa16(sm, slot, gsrc + (size_t)(unsigned)(idx & ~3) * 4, true);
+        else if (gkind == 3 && live) cpa4(sm, slot, gsrc + (lane == 2 ? (size_t)(unsigned)(idx & ~3) : (size_t)(unsigned)idx * 4));
+    };
+    int4 np4 = rows > 1 ? pred4[1] : poa_make_int4(0, -1, -1, -1);
+    if (wid == 0) { gather(1, np4, 1); cpa_commit(); }
+    int par = 0;
+    // previous row's arg-max columns from the candidates every warp published (rowx, parity of that row)
+    auto combine = [&](const int row) {
+        const int *rx = rowx + (row & 1) * NW * 4;
+        int gmx = INT_MIN, left = INT_MAX, right = -1;
+        for (int k = 0; k < NW; ++k) gmx = imax(gmx, rx[k * 4]);
+        for (int k = 0; k < NW; ++k) if (rx[k * 4] == gmx) { left = imin(left, rx[k * 4 + 1]); right = imax(right, rx[k * 4 + 2]); }
+        prev_left = left; prev_right = right;
+        if (local && gmx > best_score) { best_score = gmx; best_i = row; best_j = left; }  // abpoa_align_simd.c:1208-1210
+    };
 
     for (int i = 1; i < rows; ++i) {
-        const int4 ri = rowinfo[i];
-        const int rb = rbase[i], p0 = fp[i];
-        const int4 pm0 = p0 == i - 1 ? prev_meta : rowmeta[p0];
-        int pk1 = -1;
-        int4 pm1 = pm0;
-        if (ri.y > 1) { pk1 = pool_row[ri.x + 1]; pm1 = rowmeta[pk1]; }
+        if (wid == 0) cpa_wait_pending(0);
+        sync_block<NW>();  // row start: metadata slot filled, previous row finished by every warp
+        if (track && i > 1) {
+            pp_left = prev_left; pp_right = prev_right;
+            combine(i - 1);
+            if (wb >= 0 && wid == 0) {  // abpoa_align_simd.c:1121-1130 for the previous row, before the next gather reads the band inputs
+                if (lane < prev_out_n) { const int o = ring_ld32(sm, OUTS + (unsigned)((i - 1) & 1) * 128 + lane * 4); poa_red_max(&mprr[o], prev_right + 1); poa_red_min(&mplr[o], prev_left + 1); }
+                for (int k = lane + POA_WARP; k < prev_out_n; k += POA_WARP) { const int o = pool_row[prev_out_z + k]; poa_red_max(&mprr[o], prev_right + 1); poa_red_min(&mplr[o], prev_left + 1); }
+            }
+        }
+        const unsigned slot = META + (unsigned)(i & 1) * P16_SLOT;
+        const uint4 ri_u = ring_ld(sm, slot), m0_u = ring_ld(sm, slot + 16), m1_u = ring_ld(sm, slot + 80), m2_u = ring_ld(sm, slot + 112), m3_u = ring_ld(sm, slot + 128);
+        const uint4 nn_u = ring_ld(sm, slot + 96);
+        const int4 ri = poa_make_int4((int)ri_u.x, (int)ri_u.y, (int)ri_u.z, (int)ri_u.w);
+        const int rb = (ring_ld32(sm, slot + 32) >> (8 * (i & 3))) & 0xff;
+        const int p0 = np4.x, s0 = np4.y, s2 = np4.z, s3 = np4.w;
+        const int4 nnp4 = i + 1 < rows ? poa_make_int4((int)nn_u.x, (int)nn_u.y, (int)nn_u.z, (int)nn_u.w) : poa_make_int4(0, -1, -1, -1);
+        const int r = ring_ld32(sm, slot + 40);
+        int ml = ring_ld32(sm, slot + 48 + 4 * (i & 3)), mr = ring_ld32(sm, slot + 64 + 4 * (i & 3));
+        const int4 pm0 = p0 == i - 1 ? prev_meta : poa_make_int4((int)m0_u.x, (int)m0_u.y, (int)m0_u.z, (int)m0_u.w);
+        const int4 pm1 = s0 == i - 1 ? prev_meta : poa_make_int4((int)m1_u.x, (int)m1_u.y, (int)m1_u.z, (int)m1_u.w);
+        const int4 pm2 = s2 == i - 1 ? prev_meta : poa_make_int4((int)m2_u.x, (int)m2_u.y, (int)m2_u.z, (int)m2_u.w);
+        const int4 pm3 = s3 == i - 1 ? prev_meta : poa_make_int4((int)m3_u.x, (int)m3_u.y, (int)m3_u.z, (int)m3_u.w);
+        if (wid == 0) {
+            gather(i + 1, nnp4, i);
+            if (lane < ri.w) cpa4(sm, OUTS + (unsigned)(i & 1) * 128 + lane * 4, &pool_row[ri.z + lane]);
+            cpa_commit();
+        }
+        np4 = nnp4;
+        prev_out_z = ri.z; prev_out_n = ri.w;
         int beg, end;
         if (wb < 0) { beg = 0; end = qlen; }
         else {
-            const int r = rr[i];
-            int ml = p16_ldcg(&mplr[i]), mr = p16_ldcg(&mprr[i]);
+            // ml / mr were fetched one row ago, when row i - 1 had not been evaluated and the reductions carrying row i - 2's
+            // columns had only just been issued (by other lanes: nothing orders them before that fetch).  Both rows' contributions
+            // are therefore forwarded in registers; min / max are idempotent, so a contribution that also arrived through memory
+            // does no harm.  Rows further back had a whole row's time for their reductions to land.
             int min_pre_beg = pm0.y;
-            bool from_prev = p0 == i - 1;
-            if (ri.y > 1) { from_prev |= pk1 == i - 1; min_pre_beg = imin(min_pre_beg, pm1.y); }
-            for (int k = 2; k < ri.y; ++k) {
+            bool from_prev = p0 == i - 1, from_pp = p0 == i - 2;
+            if (ri.y > 1) { from_prev |= s0 == i - 1; from_pp |= s0 == i - 2; min_pre_beg = imin(min_pre_beg, pm1.y); }
+            if (ri.y > 2) { from_prev |= s2 == i - 1; from_pp |= s2 == i - 2; min_pre_beg = imin(min_pre_beg, pm2.y); }
+            if (ri.y > 3) { from_prev |= s3 == i - 1; from_pp |= s3 == i - 2; min_pre_beg = imin(min_pre_beg, pm3.y); }
+            for (int k = 4; k < ri.y; ++k) {
                 const int pk = pool_row[ri.x + k];
-                from_prev |= pk == i - 1;
+                from_prev |= pk == i - 1; from_pp |= pk == i - 2;
                 min_pre_beg = imin(min_pre_beg, rowmeta[pk].y);
             }
             if (from_prev) { ml = imin(ml, prev_left + 1); mr = imax(mr, prev_right + 1); }
+            if (from_pp && i > 2) { ml = imin(ml, pp_left + 1); mr = imax(mr, pp_right + 1); }
             beg = imax(0, imin(ml, r) - bw);
             end = imin(qlen, imax(mr, r) + bw);
             if ((beg >> pshift) < (min_pre_beg >> pshift)) beg = min_pre_beg;
@@ -920,11 +1008,10 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
         inband += end - beg + 1;
         edge_rows += (long long)ri.y * (end - beg + 1);
         int cf1 = f0_1 + e1 * (beg - cb * P16_CW), cf2 = f0_2 + e2 * (beg - cb * P16_CW);  // F entering column cb*256
-        int rmx = INT_MIN, fc = cb, lc = cb;  // this warp's chunks only
+        int rmx = INT_MIN, fc = -1, lc = -1;  // this warp's chunks only
         const char *qrow = qp + (size_t)(unsigned)(rb * nchq) * P16_CPB + lane * 16;
         const size_t pstride = (size_t)(unsigned)nch * P16_CPB;
-        const bool cur_res = nch <= P16_MW_SMCH * NW;
-        int par = 0;
+        const bool cur_res = nch <= P16_MW_SMCH * NW && nch <= 64;
 
 #pragma unroll 1
         for (int cbase = cb; cbase <= ce; cbase += NW) {
@@ -941,7 +1028,8 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
                 for (int k = 0; k < ri.y; ++k) {  // predecessors in in_id order (abpoa_align_simd.c:966-1029)
                     int pk = p0;
                     int4 pm = pm0;
-                    if (k == 1) { pk = pk1; pm = pm1; } else if (k > 1) { pk = pool_row[ri.x + k]; pm = rowmeta[pk]; }
+                    if (k == 1) { pk = s0; pm = pm1; } else if (k == 2) { pk = s2; pm = pm2; } else if (k == 3) { pk = s3; pm = pm3; }
+                    else if (k > 3) { pk = pool_row[ri.x + k]; pm = rowmeta[pk]; }
                     const int pcb = pm.y >> 8, pce = pm.z >> 8;
                     if (c < pcb || c > pce + 1) continue;
                     const unsigned pn_ = (unsigned)(pce - pcb + 1), idx = (unsigned)pm.x + (unsigned)(c - pcb);
@@ -957,8 +1045,8 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
                             b = p16_ld(slab_lane + (size_t)(idx + 2 * pn_) * P16_CPB);
                         }
                         const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
-                        const unsigned s0 = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot;
-                        M0 = p_max(M0, s0); M1 = p_max(M1, h.x); M2 = p_max(M2, h.y); M3 = p_max(M3, h.z);
+                        const unsigned s0_ = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot;
+                        M0 = p_max(M0, s0_); M1 = p_max(M1, h.x); M2 = p_max(M2, h.y); M3 = p_max(M3, h.z);
                         A0 = p_max(A0, a.x); A1 = p_max(A1, a.y); A2 = p_max(A2, a.z); A3 = p_max(A3, a.w);
                         B0 = p_max(B0, b.x); B1 = p_max(B1, b.y); B2 = p_max(B2, b.z); B3 = p_max(B3, b.w);
                     } else if (lane == 0) {
@@ -996,16 +1084,16 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
                 x1 = p_max(x1, p_lolo(NEGLP, t1)); x2 = p_max(x2, p_lolo(NEGLP, t2));
             }
             if (lane == 0) {
-                int *slot = xch + (par * NW + (c - cbase)) * 2;
-                slot[0] = imax(p_lo(t1), p_hi(t1)); slot[1] = imax(p_lo(t2), p_hi(t2));
+                int *slot_ = xch + (par * NW + (c - cbase)) * 2;
+                slot_[0] = imax(p_lo(t1), p_hi(t1)); slot_[1] = imax(p_lo(t2), p_hi(t2));
             }
             sync_block<NW>();
             // carry chain over the round's chunks: F entering each chunk's first column (scalar, F domain)
             int mine1 = cf1, mine2 = cf2;
             for (int k = 0; k < NW && cbase + k <= ce; ++k) {
                 if (cbase + k == c) { mine1 = cf1; mine2 = cf2; }
-                const int *slot = xch + (par * NW + k) * 2;
-                cf1 = imax(slot[0], cf1) - e1 * P16_CW; cf2 = imax(slot[1], cf2) - e2 * P16_CW;
+                const int *slot_ = xch + (par * NW + k) * 2;
+                cf1 = imax(slot_[0], cf1) - e1 * P16_CW; cf2 = imax(slot_[1], cf2) - e2 * P16_CW;
             }
             par ^= 1;
             if (act) {
@@ -1043,36 +1131,39 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
             }
         }
         prev_meta = poa_make_int4((int)roff, beg, end, 0);
-        prev_res = cur_res && nch <= 64;
+        prev_res = cur_res;
         if (tid == 0) rowmeta[i] = prev_meta;
         if (track) {
-            if (lane == 0) { rowx[wid * 4] = rmx; rowx[wid * 4 + 1] = fc; rowx[wid * 4 + 2] = lc; }
-            sync_block<NW>();  // also: every warp's plane stores of this row are visible below
-            int gmx = INT_MIN, gfc = INT_MAX, glc = -1;
-            for (int k = 0; k < NW; ++k) gmx = imax(gmx, rowx[k * 4]);
-            for (int k = 0; k < NW; ++k) if (rowx[k * 4] == gmx) { gfc = imin(gfc, rowx[k * 4 + 1]); glc = imax(glc, rowx[k * 4 + 2]); }
-            const unsigned pat = p_pack(gmx, gmx);
-            const uint4 fh = p16_ld(slab_lane + (size_t)(roff + (unsigned)(gfc - cb)) * P16_CPB);
-            const uint4 lh = p16_ld(slab_lane + (size_t)(roff + (unsigned)(glc - cb)) * P16_CPB);
-            const unsigned fz = p_minu(fh.x ^ pat, 0x00010001u) | (p_minu(fh.y ^ pat, 0x00010001u) << 1)
-                              | (p_minu(fh.z ^ pat, 0x00010001u) << 2) | (p_minu(fh.w ^ pat, 0x00010001u) << 3);
-            const unsigned lz = p_minu(lh.x ^ pat, 0x00010001u) | (p_minu(lh.y ^ pat, 0x00010001u) << 1)
-                              | (p_minu(lh.z ^ pat, 0x00010001u) << 2) | (p_minu(lh.w ^ pat, 0x00010001u) << 3);
-            const unsigned fm = (~fz & 0xfu) | ((~fz >> 12) & 0xf0u), lm = (~lz & 0xfu) | ((~lz >> 12) & 0xf0u);
+            // this warp's candidates: first / last column of ITS chunks holding ITS maximum; a lane only reads back what it wrote
+            // itself (its ring slices, or its own 16-byte slices of the slab), so no barrier is needed here
             int first = INT_MAX, last = -1;
-            if (fm) { const int b = p_ctz(fm); first = gfc * P16_CW + lane * 4 + b + (b >= 4 ? 124 : 0); }
-            if (lm) { const int b = 31 - p_clz(lm); last = glc * P16_CW + lane * 4 + b + (b >= 4 ? 124 : 0); }
-            const int left = poa_redux_min(first), right = poa_redux_max(last);
-            prev_left = left; prev_right = right;
-            if (local && gmx > best_score) { best_score = gmx; best_i = i; best_j = left; }
-            if (wb >= 0 && wid == 0) {
-                for (int k = lane; k < ri.w; k += POA_WARP) {
-                    const int o = pool_row[ri.z + k];
-                    poa_red_max(&mprr[o], right + 1); poa_red_min(&mplr[o], left + 1);
+            if (fc >= 0) {
+                const unsigned pat = p_pack(rmx, rmx);
+                uint4 fh, lh;
+                if (cur_res) {
+                    fh = ring_ld(ring, (unsigned)((fc / NW) % P16_MW_SMCH) * (3 * P16_CPB));
+                    lh = ring_ld(ring, (unsigned)((lc / NW) % P16_MW_SMCH) * (3 * P16_CPB));
+                } else {
+                    fh = p16_ld(slab_lane + (size_t)(roff + (unsigned)(fc - cb)) * P16_CPB);
+                    lh = p16_ld(slab_lane + (size_t)(roff + (unsigned)(lc - cb)) * P16_CPB);
                 }
+                const unsigned fz = p_minu(fh.x ^ pat, 0x00010001u) | (p_minu(fh.y ^ pat, 0x00010001u) << 1)
+                                  | (p_minu(fh.z ^ pat, 0x00010001u) << 2) | (p_minu(fh.w ^ pat, 0x00010001u) << 3);
+                const unsigned lz = p_minu(lh.x ^ pat, 0x00010001u) | (p_minu(lh.y ^ pat, 0x00010001u) << 1)
+                                  | (p_minu(lh.z ^ pat, 0x00010001u) << 2) | (p_minu(lh.w ^ pat, 0x00010001u) << 3);
+                const unsigned fm = (~fz & 0xfu) | ((~fz >> 12) & 0xf0u), lm = (~lz & 0xfu) | ((~lz >> 12) & 0xf0u);
+                if (fm) { const int b = p_ctz(fm); first = fc * P16_CW + lane * 4 + b + (b >= 4 ? 124 : 0); }
+                if (lm) { const int b = 31 - p_clz(lm); last = lc * P16_CW + lane * 4 + b + (b >= 4 ? 124 : 0); }
             }
+            first = poa_redux_min(first); last = poa_redux_max(last);
+            if (lane == 0) { int *rx = rowx + ((i & 1) * NW + wid) * 4; rx[0] = rmx; rx[1] = first; rx[2] = last; }
         }
-        sync_block<NW>();
+        // no barrier here: the next row starts with one
+    }
+    if (wid == 0) cpa_wait_pending(0);
+    sync_block<NW>();
+    if (track && rows > 1) {
+        combine(rows - 1);  // the last row's maximum (local mode's best cell); its successors' band inputs are not needed any more
     }
     if (tid == 0) {  // global best (abpoa_align_simd.c:1092-1105)
         if (!local) {

@@ -86,7 +86,7 @@ inline void make_layout(WsLayout &L, long long nmax, long long max_bases, long l
     L.o_idx2id = take(4 * nmax); L.o_id2idx = take(4 * nmax); L.o_remain = take(4 * nmax);
     L.o_tmp0 = take(4 * nmax); L.o_tmp1 = take(4 * nmax + 64); L.o_tmp2 = take(4 * nmax); L.o_tmp3 = take(4 * nmax + 64);
     L.o_rowinfo = take(16 * nmax); L.o_rowmeta = take(16 * nmax); L.o_rbase = take(nmax);
-    L.o_rr = take(4 * nmax); L.o_mplr = take(4 * nmax); L.o_mprr = take(4 * nmax);
+    L.o_rr = take(4 * nmax); L.o_mplr = take(4 * nmax); L.o_mprr = take(4 * nmax); L.o_pred4 = take(16 * nmax);
     long long cig_one = max_len + nmax + 8;
     L.cig_cap = (int)std::min<long long>(emit_cigar ? cig_one * std::max<long long>(max_seq, 1) : cig_one, INT32_MAX);
     L.o_cig = take(8LL * L.cig_cap);

@@ -87,10 +87,12 @@ def test_cpp_caller_compiles_and_links():
 
 @pytest.mark.gpu
 def test_sixteen_threads_with_a_ticket_window_reach_half_of_batched_throughput():
-    """C++ caller (tests/cpp/coalesce_test.cpp): 16 std::threads, 256 outstanding tickets each, 4 096 blocks of 16 x 1 kb;
-    every block's graph hash equals the batched call's, and the coalesced path sustains >= 50 % of batched throughput."""
+    """C++ caller (tests/cpp/coalesce_test.cpp): 16 std::threads, 384 outstanding tickets each, 12 288 blocks of 16 x 1 kb;
+    every block's graph hash equals the batched call's, and the coalesced path sustains >= 50 % of batched throughput.
+    (Every launch costs at least one block's serial chain, ~60 ms here, so the figure depends on how many launches the
+    dispatcher ends up making: the batch must be large against that floor for the comparison to mean anything.)"""
     import subprocess
-    out = subprocess.run([_build_cpp(), "4096", "16", "1000", "16", "256"], capture_output=True, text=True)
+    out = subprocess.run([_build_cpp(), "12288", "16", "1000", "16", "384"], capture_output=True, text=True)
     print(out.stdout, out.stderr)
     assert out.returncode == 0, out.stdout + out.stderr
     f = out.stdout.split()
