@@ -32,6 +32,51 @@ struct block_sequences {
     std::vector<std::vector<bool>> dup_is_revs;             // their orientation flags
 };
 
+// ---- a2: one path range -> the string handed to the POA (src/smooth.cpp:75-126 append_to_sequence, :177-214).
+// Graph is any type with the handle-graph calls the reference makes on xg::XG: get_path_handle_of_step, path_begin, path_end,
+// get_handle_of_step, get_length, get_sequence (oriented), get_is_reverse, get_previous_step, get_next_step; Step is its step handle.
+// The reference's behaviour is the specification here, including what looks accidental: the left flank starts AT the range's first
+// step (so it repeats bases of that node), collects node sequences in walk order (backwards along the path, each node spelled
+// forwards) and never visits the path's first step; both flanks take the LAST `need` bases of a node that is longer than what is
+// still needed; flanks that run off the path are filled with 'N' (left: in front, right: behind).  `rev_comp` is the caller's
+// reverse-complement (the reference uses odgi::reverse_complement_in_place); it is applied when more bases were walked on the
+// reverse strand than on the forward strand (:208-210).  Returns the oriented, padded string; *is_rev tells the orientation.
+template <class Graph, class Step, class RevComp>
+inline std::string extract_range_sequence(const Graph &graph, const Step &range_begin, const Step &range_end, int poa_padding,
+                                          RevComp rev_comp, bool *is_rev = nullptr) {
+    std::string seq;
+    uint64_t fwd_bp = 0, rev_bp = 0;
+    const auto path = graph.get_path_handle_of_step(range_begin);
+    auto flank = [&](const Step &from, bool left) {           // :75-126
+        Step step = from;
+        const Step stop = left ? graph.path_begin(path) : graph.path_end(path);
+        uint64_t need = (uint64_t)poa_padding;
+        std::string got;
+        while (step != stop && need > 0) {
+            const auto h = graph.get_handle_of_step(step);
+            const uint64_t l = graph.get_length(h);
+            const std::string node_seq = graph.get_sequence(h);
+            const uint64_t take = l <= need ? l : need;
+            got.append(l <= need ? node_seq : node_seq.substr(node_seq.size() - need));
+            (graph.get_is_reverse(h) ? rev_bp : fwd_bp) += take;
+            need -= take;
+            step = left ? graph.get_previous_step(step) : graph.get_next_step(step);
+        }
+        if (left) { seq.append(need, 'N'); seq.append(got); } else { seq.append(got); seq.append(need, 'N'); }
+    };
+    flank(range_begin, true);
+    for (Step step = range_begin; step != range_end; step = graph.get_next_step(step)) {   // :191-201
+        const auto h = graph.get_handle_of_step(step);
+        seq.append(graph.get_sequence(h));
+        (graph.get_is_reverse(h) ? rev_bp : fwd_bp) += graph.get_length(h);
+    }
+    flank(range_end, false);
+    const bool rev = rev_bp > fwd_bp;                         // :208-210
+    if (rev) rev_comp(seq);
+    if (is_rev) *is_rev = rev;
+    return seq;
+}
+
 // src/smooth.cpp:217-241.  The reference keys on XXH64(seq) only; identical strings always share a key, so keying
 // on the string itself gives the same grouping except on a 64-bit hash collision between different strings.
 inline block_sequences dedup_sequences(const std::vector<std::string> &seqs, const std::vector<std::string> &names,

@@ -71,7 +71,8 @@ constexpr int P16_SMCH = POA_P16_SMCH;  // chunks of the previous row kept in sh
 constexpr int P16_RING_BYTES = P16_SMCH * 3 * P16_CPB;
 constexpr int P16_QCH = POA_P16_QCH;   // profile chunks of the row in flight staged in shared memory
 constexpr int P16_QBUF_OFF = P16_RING_BYTES, P16_META_OFF = P16_QBUF_OFF + P16_QCH * P16_CPB;
-constexpr int P16_SLOT = 160;                                  // one row's prefetched metadata (layout: fill_p16)
+constexpr int P16_SLOT = 128;                                  // one row's prefetched metadata (layout: fill_p16)
+constexpr int P16_MW_SLOT = 160;                               // the multi-warp fill also prefetches the third / fourth predecessor
 constexpr int P16_OUTS_OFF = P16_META_OFF + 2 * P16_SLOT;     // + 128 B: the row's successor rows
 constexpr int P16_SMEM_BYTES = P16_OUTS_OFF + 128;
 
@@ -797,8 +798,8 @@ template <int NW> struct p16_mw_smem {
     static constexpr int o_xch = NW * P16_MW_SMCH * 3 * P16_CPB;  // [2 round parities][NW][2] scan totals
     static constexpr int o_rowx = o_xch + 2 * NW * 2 * 4;         // [2 row parities][NW][4] row maximum, first / last column
     static constexpr int o_lastH = o_rowx + 2 * NW * 4 * 4;       // [2 row parities][64] last H cell of a chunk
-    static constexpr int o_meta = (o_lastH + 2 * 64 * 4 + 15) & ~15;  // 2 row metadata slots (P16_SLOT), 2 x 128 B successor rows
-    static constexpr int bytes = o_meta + 2 * P16_SLOT + 2 * 128;
+    static constexpr int o_meta = (o_lastH + 2 * 64 * 4 + 15) & ~15;  // 2 row metadata slots (P16_MW_SLOT), 2 x 128 B successor rows
+    static constexpr int bytes = o_meta + 2 * P16_MW_SLOT + 2 * 128;
 };
 template <int NW> constexpr int p16_mw_smem_bytes() { return p16_mw_smem<NW>::bytes; }
 
@@ -848,7 +849,7 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
     int *const rowx = reinterpret_cast<int *>(sh.ring + SM::o_rowx);
     int *const lastH = reinterpret_cast<int *>(sh.ring + SM::o_lastH);
     const ring_ptr_t sm = ring_base(sh.ring, 0);
-    constexpr unsigned META = (unsigned)SM::o_meta, OUTS = META + 2 * P16_SLOT;
+    constexpr unsigned META = (unsigned)SM::o_meta, OUTS = META + 2 * P16_MW_SLOT;
 
     const int nchq = (qlen >> 8) + 1;
     for (int bc = wid; bc < 5 * nchq; bc += NW) {  // query profile, chunked layout
@@ -921,7 +922,7 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
     }
     auto gather = [&](const int n1, const int4 &p4_n1, const int cur) {  // warp 0: row n1 into its slot
         if (n1 >= rows) return;
-        const unsigned slot = META + (unsigned)(n1 & 1) * P16_SLOT + gdst;
+        const unsigned slot = META + (unsigned)(n1 & 1) * P16_MW_SLOT + gdst;
         int idx = n1;
         bool live = true;
         if (lane == 1) { idx = p4_n1.x; live = idx >= 0 && idx < cur; }
@@ -957,7 +958,7 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
                 for (int k = lane + POA_WARP; k < prev_out_n; k += POA_WARP) { const int o = pool_row[prev_out_z + k]; poa_red_max(&mprr[o], prev_right + 1); poa_red_min(&mplr[o], prev_left + 1); }
             }
         }
-        const unsigned slot = META + (unsigned)(i & 1) * P16_SLOT;
+        const unsigned slot = META + (unsigned)(i & 1) * P16_MW_SLOT;
         const uint4 ri_u = ring_ld(sm, slot), m0_u = ring_ld(sm, slot + 16), m1_u = ring_ld(sm, slot + 80), m2_u = ring_ld(sm, slot + 112), m3_u = ring_ld(sm, slot + 128);
         const uint4 nn_u = ring_ld(sm, slot + 96);
         const int4 ri = poa_make_int4((int)ri_u.x, (int)ri_u.y, (int)ri_u.z, (int)ri_u.w);

@@ -43,6 +43,28 @@ def test_dedup_and_encoding_on_cpu():
     assert out == ["1 19 39 3 81 1", "1 19 39 3 81 1", "1 13 31 3 51 1", "1 9 16 2 41 1", "1 4 6 2 26 1", "1 7 11 2 33 1", "-", "1 4 6 2 26 1", "-"]
 
 
+def test_extract_range_sequence_on_a_mock_graph():
+    """poa_b200::extract_range_sequence == src/smooth.cpp:75-126,:177-214, quirks included (worked out by hand from the reference
+    code; the patched smoothxg compares it with the reference's own strings on every real range, integration/)."""
+    exe = os.path.join(os.path.dirname(EXE), "extract_test")
+    src = os.path.join(ROOT, "tests", "cpp", "extract_test.cpp")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L", LIBDIR, "-lpoa_b200", f"-Wl,-rpath,{LIBDIR}"])
+    run = lambda *a: subprocess.run([exe, *map(str, a)], capture_output=True, text=True, check=True).stdout.strip()
+    nodes = ["ACGT+", "GG+", "TTA+", "C+", "AAAA+"]
+    # range = steps 2..3 (TTA C), padding 3: left flank starts AT step 2 (its last 3 bases: TTA), nothing more needed; right
+    # flank from step 4: the LAST 3 bases of AAAA
+    assert run(3, 2, 4, *nodes) == "TTATTACAAA 0"
+    # padding 5: left takes TTA (3) then the last 2 of GG; step 0 is never visited; right runs off the path: AAAA + one N
+    assert run(5, 2, 4, *nodes) == "TTAGGTTACAAAAN 0"
+    # padding 9: left TTA, GG, then stops at the path's first step with 4 still missing -> NNNN in front
+    assert run(9, 2, 4, *nodes) == "NNNNTTAGGTTACAAAANNNNN 0"
+    # padding 0: the bare range
+    assert run(0, 1, 3, *nodes) == "GGTTA 0"
+    # mostly reverse-strand steps: the whole string is reverse-complemented
+    assert run(0, 0, 3, "ACGT-", "GG-", "T+") == "AGGACGT 1"  # walk = ACGT (rc of the palindrome) CC T; 6 reverse bases > 1 forward
+
+
 def _identity_exe():
     exe = os.path.join(os.path.dirname(EXE), "dedup_test")
     src = os.path.join(ROOT, "tests", "cpp", "dedup_test.cpp")
