@@ -1025,37 +1025,61 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
             bool bnd = false;
             if (act) {
                 unsigned M0 = INFP, M1 = INFP, M2 = INFP, M3 = INFP;
-#pragma unroll 1
-                for (int k = 0; k < ri.y; ++k) {  // predecessors in in_id order (abpoa_align_simd.c:966-1029)
-                    int pk = p0;
-                    int4 pm = pm0;
-                    if (k == 1) { pk = s0; pm = pm1; } else if (k == 2) { pk = s2; pm = pm2; } else if (k == 3) { pk = s3; pm = pm3; }
-                    else if (k > 3) { pk = pool_row[ri.x + k]; pm = rowmeta[pk]; }
+                // With one block per SM nothing hides a load but the block's own instruction stream, so everything this chunk
+                // needs from memory is requested before any of it is consumed: the profile chunk and the chunks of the first TWO
+                // predecessors (further ones, rare, take the loop below one at a time).
+                const uint4 qv = p16_ld(qrow + (size_t)(unsigned)c * P16_CPB);
+                auto fetch = [&](const int pk, const int4 &pm, uint4 &h, uint4 &a, uint4 &bb, int &prevlast, bool &inrange, bool &touch) {
                     const int pcb = pm.y >> 8, pce = pm.z >> 8;
-                    if (c < pcb || c > pce + 1) continue;
+                    touch = !(c < pcb || c > pce + 1);
+                    inrange = touch && c <= pce;
+                    prevlast = inf_min;  // H_p[c0 - 1]
+                    if (!touch) return;
                     const unsigned pn_ = (unsigned)(pce - pcb + 1), idx = (unsigned)pm.x + (unsigned)(c - pcb);
                     const bool in_ring = prev_res && pk == i - 1;
-                    int prevlast = inf_min;  // H_p[c0 - 1]
                     if (c > pcb) prevlast = in_ring ? lastH[((i - 1) & 1) * 64 + ((c - 1) & 63)] : (int)*reinterpret_cast<const short *>(slab + (size_t)idx * P16_CPB - 2);
-                    if (c <= pce) {
-                        uint4 h, a, b;
-                        if (in_ring) { h = ring_ld(ring, cslot); a = ring_ld(ring, cslot + P16_CPB); b = ring_ld(ring, cslot + 2 * P16_CPB); }
+                    if (inrange) {
+                        if (in_ring) { h = ring_ld(ring, cslot); a = ring_ld(ring, cslot + P16_CPB); bb = ring_ld(ring, cslot + 2 * P16_CPB); }
                         else {
                             h = p16_ld(slab_lane + (size_t)idx * P16_CPB);
                             a = p16_ld(slab_lane + (size_t)(idx + pn_) * P16_CPB);
-                            b = p16_ld(slab_lane + (size_t)(idx + 2 * pn_) * P16_CPB);
+                            bb = p16_ld(slab_lane + (size_t)(idx + 2 * pn_) * P16_CPB);
                         }
+                    }
+                };
+                auto consume = [&](const uint4 &h, const uint4 &a, const uint4 &bb, const int prevlast, const bool inrange, const bool touch) {
+                    if (!touch) return;
+                    if (inrange) {
                         const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
                         const unsigned s0_ = lane == 0 ? p_pack(prevlast, p_lo(rot)) : rot;
                         M0 = p_max(M0, s0_); M1 = p_max(M1, h.x); M2 = p_max(M2, h.y); M3 = p_max(M3, h.z);
                         A0 = p_max(A0, a.x); A1 = p_max(A1, a.y); A2 = p_max(A2, a.z); A3 = p_max(A3, a.w);
-                        B0 = p_max(B0, b.x); B1 = p_max(B1, b.y); B2 = p_max(B2, b.z); B3 = p_max(B3, b.w);
+                        B0 = p_max(B0, bb.x); B1 = p_max(B1, bb.y); B2 = p_max(B2, bb.z); B3 = p_max(B3, bb.w);
                     } else if (lane == 0) {
                         M0 = p_max(M0, p_pack(prevlast, inf_min));
                     }
+                };
+                {
+                    uint4 h0 = {0, 0, 0, 0}, a0 = h0, b0 = h0, h1 = h0, a1 = h0, b1 = h0;
+                    int pl0 = inf_min, pl1 = inf_min;
+                    bool in0 = false, in1 = false, t0 = false, t1_ = false;
+                    fetch(p0, pm0, h0, a0, b0, pl0, in0, t0);
+                    if (ri.y > 1) fetch(s0, pm1, h1, a1, b1, pl1, in1, t1_);
+                    consume(h0, a0, b0, pl0, in0, t0);   // in in_id order (abpoa_align_simd.c:966-1029)
+                    if (ri.y > 1) consume(h1, a1, b1, pl1, in1, t1_);
+                }
+#pragma unroll 1
+                for (int k = 2; k < ri.y; ++k) {
+                    int pk = s2;
+                    int4 pm = pm2;
+                    if (k == 3) { pk = s3; pm = pm3; } else if (k > 3) { pk = pool_row[ri.x + k]; pm = rowmeta[pk]; }
+                    uint4 h = {0, 0, 0, 0}, a = h, bb = h;
+                    int pl = inf_min;
+                    bool in_ = false, t_ = false;
+                    fetch(pk, pm, h, a, bb, pl, in_, t_);
+                    consume(h, a, bb, pl, in_, t_);
                 }
                 if (local && c == 0 && lane == 0) M0 = p_max(M0, p_pack(0, inf_min));
-                const uint4 qv = p16_ld(qrow + (size_t)(unsigned)c * P16_CPB);
                 H0 = p_max3(p_add(M0, qv.x), A0, B0); H1 = p_max3(p_add(M1, qv.y), A1, B1);
                 H2 = p_max3(p_add(M2, qv.z), A2, B2); H3 = p_max3(p_add(M3, qv.w), A3, B3);
                 bnd = (c == cb && beg > c0) || (c == ce && end < c0 + P16_CW - 1);

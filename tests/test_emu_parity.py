@@ -144,3 +144,22 @@ def test_result_from_parts_rejects_truncated_arena(emu):
     w = wire.poa_block(pd_params(p), *batch.block(0)).raw
     with pytest.raises(engine.PoaError):
         engine.result_from_parts(w[:engine.HDR_WORDS], w[engine.HDR_WORDS:-10])
+
+
+def test_wide_wire_format_roundtrip(emu, oracle):
+    """Total dedup weight >= 65 536 switches the result body to its 32-bit form (WIRE_WIDE, poa_core.cuh): device writer
+    (emulated) -> poa_wire.hpp decoder -> views == oracle."""
+    from oracle.oracle import make_params
+    from smoothxg_b200 import synth
+    from smoothxg_b200.shard import merge_parts
+    _, wire = emu
+    batch = synth.make_batch(n_blocks=2, n_seqs=24, length=120, seed=77, divergence=0.7)
+    batch.weight[:] = 3000 + (np.arange(batch.weight.shape[0]) % 7) * 500
+    p = make_params(out_msa=True)
+    for b in range(batch.n_blocks):
+        w = wire.poa_block(p, *batch.block(b)).raw
+        assert w[18] == 3  # H_FORMAT == WIRE_WIDE
+        hdr, arena = merge_parts(1, [(np.array([0]), w[:engine.HDR_WORDS], w[engine.HDR_WORDS:])])
+        res = engine.result_from_parts(hdr, arena)
+        assert np.array_equal(view_to_dump(res.block(0)).compare_part(), oracle.poa_block(p, *batch.block(b)).compare_part())
+        res.close()

@@ -78,6 +78,18 @@ def test_fresh_inputs_vs_oracle(engine, oracle, kw, pk):
     assert st["edge_row_cells"] == sum(d.edge_rows for d in want)
 
 
+def test_wide_wire_format_and_arena_retry(engine, oracle):
+    """Dedup weights whose sum passes 65 535 force the 32-bit form of the result body (WIRE_WIDE): twice the words of the
+    first-guess arena estimate for unrelated sequences, so some blocks overflow the arena and are re-run with the exact size the
+    kernel reported.  Results must not depend on any of that."""
+    batch = synth.make_batch(n_blocks=12, n_seqs=24, length=260, seed=77, divergence=0.7)
+    batch.weight[:] = 3000 + (np.arange(batch.weight.shape[0]) % 7) * 500
+    pk = dict(out_msa=True)
+    want = oracle.poa_batch(oracle_params(**pk), batch)
+    st = _check_batch(engine, batch, E.make_params(**pk), want, "wide")
+    assert st["inband_cells"] == sum(d.inband_cells for d in want)
+
+
 def test_int32_scores_and_mid_block_switch(engine, oracle):
     """max(qlen, rows) > 16361 switches abPOA to 32-bit scores (abpoa_align_simd.c:1293-1302), also mid-block."""
     for kw in (dict(n_blocks=1, n_seqs=3, length=17000, seed=21), dict(n_blocks=1, n_seqs=6, length=8000, seed=22, divergence=0.3)):

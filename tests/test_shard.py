@@ -85,3 +85,27 @@ def test_gather_to_root_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert got == [list(range(3)), [100 + i for i in range(7)]]
+
+
+@pytest.mark.gpu
+def test_run_shard_world1_nccl_matches_run_batch():
+    """The multi-GPU call path end to end on one GPU (world_size 1 NCCL group): H2D of the shard, kernel, the size-exact gather,
+    poa_b200_result_from_device_parts (one D2H into pinned memory) == poa_b200_run_batch, block by block."""
+    from smoothxg_b200 import engine as E
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(29700 + os.getpid() % 200)
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        batch = make_batch(n_blocks=300, n_seqs=8, length=300, seed=9, indel_prob=0.2, indel_len=(5, 60))
+        eng = E.PoaEngine(device=0)
+        p = E.make_params(out_msa=True)
+        ids = shard.plan(batch, 1)
+        tm = {}
+        got = shard.run_shard(eng, batch.select(ids[0]), ids, batch.n_blocks, p, dist, None, tm)
+        want = eng.run_batch(batch, p)
+        assert all(got.block_hash(b) == want.block_hash(b) for b in range(batch.n_blocks))
+        assert np.array_equal(got.block(7).path_node, want.block(7).path_node) and np.array_equal(got.block(7).msa, want.block(7).msa)
+        assert tm["gathered_bytes"] > 0 and "gather_ms" in tm
+        got.close(); want.close(); eng.close()
+    finally:
+        dist.destroy_process_group()
