@@ -160,6 +160,14 @@ inline poa_b200_params_t make_params(int poa_m, int poa_n, int poa_g, int poa_e,
     return p;
 }
 
+// What smooth_abpoa returns (src/smooth.cpp:545-620): the block graph after odgi unchop, renumbered 1..n in a topological order,
+// one edge per consecutive pair of path steps, paths in the block's original order with the consensus last.
+struct final_block_graph {
+    std::vector<std::string> node_seq;                      // node k (0-based) has id k + 1
+    std::vector<std::pair<int32_t, int32_t>> edges;         // forward-forward, ids
+    std::vector<path_t> paths;
+};
+
 namespace detail {
 inline void check(int rc, const char *what) {
     if (rc != POA_B200_OK) throw std::runtime_error(std::string("poa_b200: ") + what + ": " + poa_b200_strerror(rc) + ": " + poa_b200_last_error());
@@ -199,6 +207,44 @@ inline block_graph graph_of(const poa_b200_result_t *res, int64_t blk, const blo
     return out;
 }
 }  // namespace detail
+
+// The same block as smooth_abpoa finally returns it (poa_b200_block_final_graph): `names_in_original_order` is the block's
+// all_names_in_original_order (:242, one name per path range, duplicates of a sequence included); paths come out in that order.
+inline final_block_graph final_graph_of(const poa_b200_result_t *res, int64_t blk, const block_sequences &b, int padding_len,
+                                        const std::string &consensus_name, const std::vector<std::string> &names_in_original_order) {
+    poa_b200_block_view_t v;
+    detail::check(poa_b200_result_block(res, blk, &v), "result_block");
+    if (v.status != POA_B200_OK) throw std::runtime_error(std::string("poa_b200: block failed: ") + poa_b200_strerror(v.status));
+    const bool add_consensus = !consensus_name.empty();
+    poa_b200_graph_t *g = nullptr;
+    detail::check(poa_b200_block_final_graph(&v, padding_len, add_consensus ? 1 : 0, &g), "block_final_graph");
+    poa_b200_final_graph_view_t gv;
+    detail::check(poa_b200_final_graph_view(g, &gv), "final_graph_view");
+    final_block_graph out;
+    for (int32_t k = 0; k < gv.n_node; ++k) out.node_seq.emplace_back(gv.seq + gv.seq_off[k], gv.seq + gv.seq_off[k + 1]);
+    for (int32_t i = 0; i < gv.n_edge; ++i) out.edges.emplace_back(gv.edge_from[i], gv.edge_to[i]);
+    std::unordered_map<std::string, std::pair<size_t, bool>> owner;  // name -> (deduplicated sequence, reverse strand)
+    for (size_t i = 0; i < b.seqs.size(); ++i)
+        for (size_t z = 0; z < b.dup_seq_names[i].size(); ++z) owner[b.dup_seq_names[i][z]] = {i, b.dup_is_revs[i][z]};
+    for (auto &name : names_in_original_order) {             // :608-620
+        auto it = owner.find(name);
+        if (it == owner.end()) throw std::runtime_error("poa_b200: unknown path name " + name);
+        const size_t i = it->second.first;
+        path_t p; p.name = name;
+        const int32_t *s0 = gv.path_node + gv.path_off[i], *s1 = gv.path_node + gv.path_off[i + 1];
+        if (it->second.second) for (const int32_t *s = s1; s != s0;) p.steps.push_back({*--s, true});
+        else for (const int32_t *s = s0; s != s1; ++s) p.steps.push_back({*s, false});
+        out.paths.push_back(std::move(p));
+    }
+    if (add_consensus) {
+        path_t p; p.name = consensus_name;
+        for (int64_t k = gv.path_off[gv.n_path - 1]; k < gv.path_off[gv.n_path]; ++k) p.steps.push_back({gv.path_node[k], false});
+        out.paths.push_back(std::move(p));
+    }
+    poa_b200_graph_free(g);
+    poa_b200_result_release_block(res, blk);
+    return out;
+}
 
 // Batched form of smooth_abpoa (src/smooth.cpp:133-627) from the de-duplicated sequences on: one GPU launch for all
 // blocks.  `padding_len[b]` is the block's poa_padding (:1946-1970), `consensus_name[b]` empty = no consensus path.

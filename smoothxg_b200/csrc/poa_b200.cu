@@ -1141,48 +1141,70 @@ int poa_b200_block_final_graph(const poa_b200_block_view_t *v, int32_t padding_l
     for (int x : one->node_id) max_id = std::max(max_id, x);
     std::vector<int> dense((size_t)max_id + 1, -1);
     for (int k = 0; k < n1; ++k) dense[(size_t)one->node_id[(size_t)k]] = k;
+    // every path step as a dense node index, once (the three passes below walk plain arrays)
+    const size_t n_steps = one->path_node.size();
+    std::vector<int> dstep(n_steps);
+    { const int32_t *pn = one->path_node.data(); const int *dn = dense.data(); int *ds = dstep.data(); for (size_t k = 0; k < n_steps; ++k) ds[k] = dn[pn[k]]; }
+    const int64_t *poff = one->path_off.data();
+    const int *ds = dstep.data();
     // unchop (deps/odgi/src/algorithms/unchop.cpp, simple_components.cpp:27-60, perfect_neighbors.cpp:10-100): two nodes merge when
     // every path step on the left one continues to the right one and every step on the right one comes from the left one
     // -- no path starts, ends or branches between them.  NONE = no step seen yet, MANY = several targets or a path end.
     const int NONE = -1, MANY = -2;
     std::vector<int> nxt((size_t)n1, NONE), prv((size_t)n1, NONE);
-    auto note = [&](std::vector<int> &arr, int at, int to) { int &x = arr[(size_t)at]; x = (x == NONE || x == to) ? to : MANY; };
     for (size_t p = 0; p < n_path; ++p) {
-        const int64_t a = one->path_off[p], b = one->path_off[p + 1];
+        const int64_t a = poff[p], b = poff[p + 1];
         if (a == b) continue;
-        prv[(size_t)dense[(size_t)one->path_node[(size_t)a]]] = MANY;       // a path starts here
-        nxt[(size_t)dense[(size_t)one->path_node[(size_t)(b - 1)]]] = MANY;  // a path ends here
+        prv[(size_t)ds[a]] = MANY;      // a path starts here
+        nxt[(size_t)ds[b - 1]] = MANY;  // a path ends here
+        int *nx = nxt.data(), *pv = prv.data();
         for (int64_t k = a; k + 1 < b; ++k) {
-            const int u = dense[(size_t)one->path_node[(size_t)k]], w = dense[(size_t)one->path_node[(size_t)k + 1]];
-            note(nxt, u, w); note(prv, w, u);
+            const int u = ds[k], w = ds[k + 1];
+            int &x = nx[u]; x = (x == NONE || x == w) ? w : MANY;
+            int &y = pv[w]; y = (y == NONE || y == u) ? u : MANY;
         }
     }
     // ... and the two are joined by the only edge leaving the left and the only edge entering the right one (simple_components.cpp:
     // get_degree == 1 on both sides), counted over ALL kept edges, walked by a path or not
     std::vector<int> outdeg((size_t)n1, 0), indeg1((size_t)n1, 0);
     for (size_t e = 0; e < one->edge_from.size(); ++e) { ++outdeg[(size_t)dense[(size_t)one->edge_from[e]]]; ++indeg1[(size_t)dense[(size_t)one->edge_to[e]]]; }
-    auto linked = [&](int u) { const int w = nxt[(size_t)u]; return w >= 0 && prv[(size_t)w] == u && outdeg[(size_t)u] == 1 && indeg1[(size_t)w] == 1; };  // u and nxt[u] are one node
+    // link[u] = the node u is merged with on its right, or -1
+    std::vector<int> link((size_t)n1, -1);
+    std::vector<char> is_head((size_t)n1, 1);
+    for (int u = 0; u < n1; ++u) {
+        const int w = nxt[(size_t)u];
+        if (w >= 0 && prv[(size_t)w] == u && outdeg[(size_t)u] == 1 && indeg1[(size_t)w] == 1) { link[(size_t)u] = w; is_head[(size_t)w] = 0; }
+    }
     // merged nodes: chains of linked 1-bp nodes, discovered in creation order of their heads
     std::vector<int> comp((size_t)n1, -1);
     std::vector<int> head;  // first 1-bp node of every merged node
     for (int k = 0; k < n1; ++k) {
-        const int pv = prv[(size_t)k];
-        if (pv >= 0 && nxt[(size_t)pv] == k && linked(pv)) continue;  // not a chain head
+        if (!is_head[(size_t)k]) continue;
         const int c = (int)head.size();
         head.push_back(k);
-        for (int u = k;; u = nxt[(size_t)u]) { comp[(size_t)u] = c; if (!linked(u)) break; }
+        for (int u = k; u >= 0; u = link[(size_t)u]) comp[(size_t)u] = c;
     }
     const int nc = (int)head.size();
     // edges between merged nodes: every consecutive pair of path steps that crosses a chain boundary (src/smooth.cpp:590-606 creates
-    // an edge for every such pair, consensus steps included)
-    std::vector<std::pair<int, int>> edges;
-    for (size_t p = 0; p < n_path; ++p)
-        for (int64_t k = one->path_off[p]; k + 1 < one->path_off[p + 1]; ++k) {
-            const int u = dense[(size_t)one->path_node[(size_t)k]], w = dense[(size_t)one->path_node[(size_t)k + 1]];
-            if (!(linked(u) && nxt[(size_t)u] == w)) edges.emplace_back(comp[(size_t)u], comp[(size_t)w]);
+    // an edge for every such pair, consensus steps included); out-degrees are tiny, so duplicates are found by a short scan
+    std::vector<std::vector<int>> outs((size_t)nc);
+    size_t n_edges = 0;
+    {
+        const int *lk = link.data(), *cp = comp.data();
+        for (size_t p = 0; p < n_path; ++p) {
+            const int64_t a = poff[p], b = poff[p + 1];
+            for (int64_t k = a; k + 1 < b; ++k) {
+                const int u = ds[k], w = ds[k + 1];
+                if (lk[u] == w) continue;
+                std::vector<int> &o = outs[(size_t)cp[u]];
+                const int cw = cp[w];
+                if (std::find(o.begin(), o.end(), cw) == o.end()) { o.push_back(cw); ++n_edges; }
+            }
         }
-    std::sort(edges.begin(), edges.end());
-    edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+    }
+    std::vector<std::pair<int, int>> edges;
+    edges.reserve(n_edges);
+    for (int c = 0; c < nc; ++c) { std::sort(outs[(size_t)c].begin(), outs[(size_t)c].end()); for (int w : outs[(size_t)c]) edges.emplace_back(c, w); }
     // topological order (src/smooth.cpp:557: apply_ordering(topological_order(...), compact ids)): Kahn's algorithm, ready nodes
     // taken in discovery order.  odgi's own tie-breaking keys on handle ranks that come out of a hash map after unchop, so
     // the reference's ids are not a function of the block; any topological order gives an isomorphic graph.
@@ -1201,17 +1223,19 @@ int poa_b200_block_final_graph(const poa_b200_block_view_t *v, int32_t padding_l
     g->node_id.resize((size_t)nc);
     for (int r = 0; r < nc; ++r) {
         g->node_id[(size_t)r] = r + 1;
-        for (int u = head[(size_t)order[(size_t)r]];; u = nxt[(size_t)u]) { g->node_base.push_back(one->node_base[(size_t)u]); if (!linked(u)) break; }
+        for (int u = head[(size_t)order[(size_t)r]]; u >= 0; u = link[(size_t)u]) g->node_base.push_back(one->node_base[(size_t)u]);
         g->seq_off.push_back((int64_t)g->node_base.size());
     }
     for (auto &e : edges) { g->edge_from.push_back(rank[(size_t)e.first] + 1); g->edge_to.push_back(rank[(size_t)e.second] + 1); }
     // paths: one step per merged node (a path that enters a chain walks all of it)
-    for (size_t p = 0; p < n_path; ++p) {
-        for (int64_t k = one->path_off[p]; k < one->path_off[p + 1]; ++k) {
-            const int u = dense[(size_t)one->path_node[(size_t)k]];
-            if (head[(size_t)comp[(size_t)u]] == u) g->path_node.push_back(rank[(size_t)comp[(size_t)u]] + 1);
+    {
+        const char *ih = is_head.data(); const int *cp = comp.data(), *rk = rank.data();
+        g->path_node.reserve(n_steps / 2 + 16);
+        for (size_t p = 0; p < n_path; ++p) {
+            const int64_t a = poff[p], b = poff[p + 1];
+            for (int64_t k = a; k < b; ++k) { const int u = ds[k]; if (ih[u]) g->path_node.push_back(rk[cp[u]] + 1); }
+            g->path_off.push_back((int64_t)g->path_node.size());
         }
-        g->path_off.push_back((int64_t)g->path_node.size());
     }
     *out = g;
     return POA_B200_OK;

@@ -38,6 +38,30 @@ int main(int argc, char **argv) {
             printf("\n");
         }
         printf("msa %d %d\n", g.msa_rows, g.msa_len);
+        // the graph smooth_abpoa finally returns (unchop + topological order): final_graph_of on the same block
+        {
+            std::vector<poa_b200::block_sequences> one{blk};
+            poa_b200_params_t p = poa_b200::make_params(1, 4, 6, 2, 26, 1, local, true, false, !cons.empty());
+            std::vector<int64_t> bso{0}, so{0}; std::vector<int32_t> lens, wts; std::vector<uint8_t> codes;
+            for (size_t i = 0; i < blk.seqs.size(); ++i) {
+                const size_t at = codes.size(); codes.resize(at + blk.seqs[i].size());
+                poa_b200_encode_bases(blk.seqs[i].data(), (int64_t)blk.seqs[i].size(), codes.data() + at);
+                lens.push_back((int32_t)blk.seqs[i].size()); wts.push_back(blk.weights[i]); so.push_back((int64_t)codes.size());
+            }
+            bso.push_back((int64_t)lens.size());
+            poa_b200_result_t *res = nullptr;
+            if (poa_b200_run_batch(eng, &p, 1, bso.data(), lens.data(), so.data(), codes.data(), wts.data(), &res) != POA_B200_OK) { fprintf(stderr, "run_batch: %s\n", poa_b200_last_error()); return 5; }
+            const poa_b200::final_block_graph f = poa_b200::final_graph_of(res, 0, blk, padding, cons, names);
+            printf("final %zu\n", f.node_seq.size());
+            for (size_t k = 0; k < f.node_seq.size(); ++k) printf("FS %zu %s\n", k + 1, f.node_seq[k].c_str());
+            for (auto &e : f.edges) printf("FL %d %d\n", e.first, e.second);
+            for (auto &pp : f.paths) {
+                printf("FP %s", pp.name.c_str());
+                for (auto &st : pp.steps) printf(" %d%c", st.node_id, st.is_rev ? '-' : '+');
+                printf("\n");
+            }
+            poa_b200_result_free(res);
+        }
         poa_b200_engine_destroy(eng);
     } catch (const std::exception &e) { fprintf(stderr, "error: %s\n", e.what()); return 4; }
     return 0;

@@ -141,5 +141,20 @@ def test_adapter_matches_ctypes_path(padding, local, cons):
     if cons != "-":
         want.append(" ".join([f"P {cons}"] + [f"{x}+" for x in g.path(len(uniq)).tolist()]))
     want.append(f"msa {v.msa_rows} {v.msa_len}")
-    assert out.stdout.strip().split("\n") == want
-    res.close(); eng.close()
+    lines = out.stdout.strip().split("\n")
+    cut = next(i for i, ln in enumerate(lines) if ln.startswith("final "))
+    assert lines[:cut] == want
+    # final_graph_of (unchop + topological order), paths in the block's original order with duplicates and reverse strands
+    res2 = eng.run_batch(batch, E.make_params(local=bool(local), out_msa=False, out_cons=cons != "-"))
+    fg = res2.final_graph(0, padding, cons != "-")
+    wantf = [f"final {len(fg.node_seq)}"] + [f"FS {k + 1} {sq}" for k, sq in enumerate(fg.node_seq)]
+    wantf += [f"FL {a_} {b_}" for a_, b_ in zip(fg.edge_from.tolist(), fg.edge_to.tolist())]
+    owner = {n: (k, s) for k, grp in enumerate(names) for n, s in grp}
+    for n, _, _ in rows:
+        k, s = owner[n]
+        steps = fg.path(k).tolist()
+        wantf.append(" ".join([f"FP {n}"] + ([f"{x}-" for x in reversed(steps)] if s == "-" else [f"{x}+" for x in steps])))
+    if cons != "-":
+        wantf.append(" ".join([f"FP {cons}"] + [f"{x}+" for x in fg.path(len(uniq)).tolist()]))
+    assert lines[cut:] == wantf
+    res.close(); res2.close(); eng.close()

@@ -78,6 +78,33 @@ def test_fresh_inputs_vs_oracle(engine, oracle, kw, pk):
     assert st["edge_row_cells"] == sum(d.edge_rows for d in want)
 
 
+@pytest.mark.parametrize("isa_bits", [1, 2])
+def test_lane_count_option_gives_identical_results(isa_bits):
+    """poa_b200_engine_opts_t::flags bits 4-5 select the SIMD width whose band-start rounding is reproduced (AVX2 = 16 int16 lanes,
+    SSE4.1 / NEON = 8; default AVX-512BW = 32).  The rule only moves a row's band start over -inf cells, so the results are the
+    same as the golden vectors pinned with the AVX-512 build (SURVEY 6.2 found the three abPOA builds identical too) -- the
+    in-band cell COUNT may differ, results may not."""
+    eng = E.PoaEngine(device=0, emit_cigar=True, flags=isa_bits << 4)
+    for name, batch, p, dumps in load_real_cases() + [c for c in CASES if c[0] in ("syn_indel", "syn_global_band", "abpoa_heter_fa_global")]:
+        res = eng.run_batch(batch, engine_params(p))
+        for b in range(batch.n_blocks):
+            assert np.array_equal(view_to_dump(res.block(b)).result_part(), dumps[b].result_part()), f"{name} block {b}"
+        res.close()
+    eng.close()
+
+
+def test_engine_trim_returns_pooled_memory():
+    import torch
+    eng = E.PoaEngine(device=0)
+    batch = synth.make_batch(n_blocks=64, n_seqs=8, length=500, seed=5)
+    eng.run_batch(batch, E.make_params()).close()
+    free0 = torch.cuda.mem_get_info(0)[0]
+    eng.trim()
+    assert torch.cuda.mem_get_info(0)[0] > free0  # workspace / arena / input buffers went back to the driver
+    eng.run_batch(batch, E.make_params()).close()  # and the engine still works
+    eng.close()
+
+
 def test_wide_wire_format_and_arena_retry(engine, oracle):
     """Dedup weights whose sum passes 65 535 force the 32-bit form of the result body (WIRE_WIDE): twice the words of the
     first-guess arena estimate for unrelated sequences, so some blocks overflow the arena and are re-run with the exact size the
