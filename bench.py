@@ -49,6 +49,7 @@ WORKLOADS = {
     "10000x32x2kb_d0.1": (10000, 32, 2000, 0.001),
     "10000x32x2kb_d5": (10000, 32, 2000, 0.05),
     "10000x32x2kb_indel": (10000, 32, 2000, 0.02),   # + one 50-500 bp insertion or deletion per copy with probability 0.3
+    "8x64x4kb_probe": (8, 64, 4000, 0.02),           # profiling probe: deep-block behaviour (one block per SM, 8 warps) in a kernel short enough for ncu
 }
 EXTRA = {"10000x32x2kb_indel": dict(indel_prob=0.3, indel_len=(50, 500))}
 METRIC = "poa_dp_inband_gcells_per_s"
