@@ -266,6 +266,8 @@ struct Shared {
     int bcast[4];
     char *ring;  // previous-row cache of the packed 16-bit fill (dynamic shared memory, poa_fill16.cuh)
     int ring_bytes;
+    unsigned long long qbar;  // mbarrier of the profile bulk copies (fill_p16)
+    int q_phase;              // its current phase parity
 };
 
 #ifdef POA_HOST_EMU

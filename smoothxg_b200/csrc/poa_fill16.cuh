@@ -74,7 +74,8 @@ constexpr int P16_QBUF_OFF = P16_RING_BYTES, P16_META_OFF = P16_QBUF_OFF + P16_Q
 constexpr int P16_SLOT = 128;                                  // one row's prefetched metadata (layout: fill_p16)
 constexpr int P16_MW_SLOT = 160;                               // the multi-warp fill also prefetches the third / fourth predecessor
 constexpr int P16_OUTS_OFF = P16_META_OFF + 2 * P16_SLOT;     // + 128 B: the row's successor rows
-constexpr int P16_SMEM_BYTES = P16_OUTS_OFF + 128;
+constexpr int P16_LANEC_OFF = P16_OUTS_OFF + 128;          // + 512 B: four lane-dependent packed constants per lane (fill_p16)
+constexpr int P16_SMEM_BYTES = P16_LANEC_OFF + 512;
 
 // address of cell (plane, j) of a row stored in the chunked layout; pm = {first chunk-plane of the row, beg, end, _}
 POA_D const short *cell_ptr16(const Ws &w, const int4 &pm, int plane, int j) {
@@ -133,6 +134,35 @@ POA_D void cpa_wait_pending(int n) {  // wait until at most n of the most recent
 POA_D int ring_ld32(ring_ptr_t p, unsigned off) { int v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p + off)); return v; }
 #endif
 
+// One-dimensional bulk copy global -> shared (TMA, cp.async.bulk; SASS UBLKCP) tracked by an mbarrier: ONE lane moves a whole
+// run of contiguous 512-byte chunk-planes with one instruction, and only the lanes that read the data wait for it (a phase
+// flip of the mbarrier), independently of any cp.async group in flight.  Used for the row's query-profile chunks (fill_p16).
+#ifndef POA_P16_QTMA
+#define POA_P16_QTMA 0
+#endif
+#ifdef POA_HOST_EMU
+static inline void qbar_init(unsigned long long *) {}
+static inline void q_bulk(ring_ptr_t s, unsigned off, const void *g, unsigned bytes, unsigned long long *) { memcpy(s + off, g, bytes); }
+static inline void q_wait(unsigned long long *, unsigned) { poa_sync_warp(); }  // the issuing lane copied before it got here
+#else
+POA_D void qbar_init(unsigned long long *bar) {  // one thread, once per kernel; made visible to the async proxy
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(b) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+POA_D void q_bulk(ring_ptr_t s, unsigned off, const void *g, unsigned bytes, unsigned long long *bar) {  // one lane
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(s + off), "l"(g), "r"(bytes), "r"(b) : "memory");
+}
+POA_D void q_wait(unsigned long long *bar, unsigned parity) {  // every lane that reads the copied bytes
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n.reg .pred p;\nQ_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra Q_DONE;\nbra Q_WAIT;\nQ_DONE:\n}"
+                 :: "r"(b), "r"(parity) : "memory");
+}
+#endif
+
 POA_D uint4 p16_ld(const char *p) { return *reinterpret_cast<const uint4 *>(p); }
 // band inputs are updated with L2 reductions (poa_red_max/min), so they are read at L2, never from a stale L1 line
 #ifdef POA_HOST_EMU
@@ -148,6 +178,14 @@ POA_D void p16_st(char *p, unsigned a, unsigned b, unsigned c, unsigned d) {
     *reinterpret_cast<uint4 *>(p) = u;
 #endif
 }
+
+// A value the compiler may not move or speculate: keeps the "-inf" fill of an out-of-range predecessor chunk on its (rare) branch
+// instead of twelve unconditional register initialisations in front of every chunk's loads.
+#ifdef POA_HOST_EMU
+static inline unsigned p16_pinned(unsigned v) { return v; }
+#else
+POA_D unsigned p16_pinned(unsigned v) { unsigned r; asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+#endif
 
 // Can this alignment run in packed 16-bit arithmetic without any intermediate leaving the int16 range?
 // (scores <= qlen*match; the scan adds at most e*256 of position offset on top.)
@@ -233,6 +271,10 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
     const unsigned OFF1 = p_pack(e1 * 4 * (lane + 1), e1 * 4 * (lane + 33)), NOFF1 = p_pack(-e1 * 4 * lane, -e1 * 4 * (lane + 32));
     const unsigned OFF2 = p_pack(e2 * 4 * (lane + 1), e2 * 4 * (lane + 33)), NOFF2 = p_pack(-e2 * 4 * lane, -e2 * 4 * (lane + 32));
     const int f0_1 = imax(inf_min - oe1, inf_min - e1), f0_2 = imax(inf_min - oe2, inf_min - e2);
+    // The four lane-dependent constants of the scan live in shared memory (one 16-byte slice per lane) and are re-read by every
+    // chunk pass with ONE ld.shared.v4: with 128 registers per thread they do not stay in registers, and the compiler otherwise
+    // rebuilds them from the lane number in every pass (22 of the pass's 243 instructions).
+    ring_st(ring_base(sh.ring, lane), P16_LANEC_OFF, OFF1, NOFF1, OFF2, NOFF2);
 
     // ---- query profile in the chunked layout: qp[base][chunk][lane] (abpoa_align_simd.c:531-546)
     const int nchq = (qlen >> 8) + 1;
@@ -310,6 +352,28 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
     else if (lane == 6 && wb >= 0) { gsrc = (const char *)mprr; gdst = 64; gkind = 2; }
     else if (lane == 7) { gsrc = (const char *)rowmeta; gdst = 80; gkind = 1; }
     else if (lane == 8) { gsrc = (const char *)sp; gdst = 96; gkind = 3; }
+#ifndef POA_P16_GFLAT
+#define POA_P16_GFLAT 1
+#endif
+#if POA_P16_GFLAT
+    // which row the lane's item belongs to (0: row n1, 1 / 2: its first / second predecessor, 3: the row after n1), and how its
+    // element index becomes a byte offset: all fixed per lane, so the gather itself is branch-free
+    const int gsel = lane == 1 ? 1 : lane == 7 ? 2 : (lane == 3 || lane == 8 || (POA_P16_QTMA && lane == 2)) ? 3 : 0;
+    const int gmask = (gkind == 2 || lane == 2) ? ~3 : ~0, gshift = gkind == 1 ? 4 : lane == 2 ? 0 : 2;
+    auto gather = [&](const int n1, const int np0_n1, const int nsp_n1, const int cur) {  // row n1 into its slot; `cur`: row being evaluated
+        if (n1 >= rows) return;
+        const unsigned slot = P16_META_OFF + (unsigned)(n1 & 1) * P16_SLOT + gdst;
+        const int idx = gsel == 1 ? np0_n1 : gsel == 2 ? nsp_n1 : n1 + (gsel == 3 ? 1 : 0);
+        // a predecessor's descriptor is fetched only if that row is complete (rows >= cur: forwarded in registers instead)
+        const bool live = (unsigned)idx < (unsigned)((gsel == 1 || gsel == 2) ? cur : rows);
+        const char *src = gsrc + ((unsigned)(idx & gmask) << gshift);
+        if (live) {
+            if (gkind == 1) cpa16(sm, slot, src, false);
+            else if (gkind == 2) cpa16(sm, slot, src, true);
+            else if (gkind == 3) cpa4(sm, slot, src);
+        }
+    };
+#else
     auto gather = [&](const int n1, const int np0_n1, const int nsp_n1, const int cur) {  // row n1 into its slot; `cur`: row being evaluated
         if (n1 >= rows) return;
         const unsigned slot = P16_META_OFF + (unsigned)(n1 & 1) * P16_SLOT + gdst;
@@ -319,15 +383,32 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
         bool live = true;
         if (lane == 1) { idx = np0_n1; live = np0_n1 < cur; }
         else if (lane == 7) { idx = nsp_n1; live = nsp_n1 >= 0 && nsp_n1 < cur; }
-        else if (lane == 3 || lane == 8) { idx = n1 + 1; live = n1 + 1 < rows; }
+        else if (lane == 3 || lane == 8 || (POA_P16_QTMA && lane == 2)) { idx = n1 + 1; live = n1 + 1 < rows; }
         if (gkind == 1 && live) cpa16(sm, slot, gsrc + (size_t)(unsigned)idx * 16, false);
         else if (gkind == 2) cpa16(sm, slot, gsrc + (size_t)(unsigned)(idx & ~3) * 4, true);
         else if (gkind == 3 && live) cpa4(sm, slot, gsrc + (lane == 2 ? (size_t)(unsigned)(idx & ~3) : (size_t)(unsigned)idx * 4));
     };
+#endif
     int np0 = fp[rows > 1 ? 1 : 0];   // first predecessor of the row about to be evaluated
     int nsp = rows > 1 ? sp[1] : -1;  // its second predecessor, or -1
     gather(1, np0, nsp, 1);
     cpa_commit();
+#if POA_P16_QTMA
+    // The row's profile chunks qp[base][scb..sce] are contiguous in memory: ONE bulk copy per row, issued by lane 0 a row ahead
+    // (right after the previous row's last chunk, for the chunk range that row covered plus one -- bands move slowly), and
+    // waited for on the mbarrier by the first chunk pass.  Every copy issued is waited for exactly once (q_pend).
+    unsigned q_ph = (unsigned)sh.q_phase;
+    bool q_pend = false;
+    int q_scb = 0, q_sce = -1;  // chunk range staged (or in flight) in the profile buffer
+    auto q_issue = [&](const int rbn, const int cb_, const int ce_) {
+        q_scb = cb_; q_sce = ce_;
+        if (lane == 0) q_bulk(sm, P16_QBUF_OFF, qp + (size_t)(unsigned)(rbn * nchq + cb_) * P16_CPB, (unsigned)(ce_ - cb_ + 1) * P16_CPB, &sh.qbar);
+        q_pend = true;
+    };
+    auto q_drain = [&]() { if (q_pend) { q_wait(&sh.qbar, q_ph); q_ph ^= 1u; q_pend = false; } };
+    int rb_next = rows > 1 ? rbase[1] : 0;
+    if (rows > 1) { const int g0 = prev_meta.y >> 8; q_issue(rb_next, g0, imin(imin((prev_meta.z >> 8) + 1, g0 + P16_QCH - 1), nchq - 1)); }
+#endif
 
     // ---- rows in index order (abpoa_align_simd.c:1205-1221)
     for (int i = 1; i < rows; ++i) {
@@ -336,7 +417,12 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
         const unsigned slot = P16_META_OFF + (unsigned)(i & 1) * P16_SLOT;
         const uint4 ri_u = ring_ld(sm, slot), npm_u = ring_ld(sm, slot + 16), spm_u = ring_ld(sm, slot + 80);
         const int4 ri = poa_make_int4((int)ri_u.x, (int)ri_u.y, (int)ri_u.z, (int)ri_u.w);  // {in_off, in_n, out_off, out_n}
+#if POA_P16_QTMA
+        const int rb = rb_next, p0 = np0, s0 = nsp;  // the slot holds the base word of row i + 1
+        rb_next = i + 1 < rows ? (ring_ld32(sm, slot + 32) >> (8 * ((i + 1) & 3))) & 0xff : 0;
+#else
         const int rb = (ring_ld32(sm, slot + 32) >> (8 * (i & 3))) & 0xff, p0 = np0, s0 = nsp;
+#endif
         const int nnp0 = i + 1 < rows ? ring_ld32(sm, slot + 36) : 0;
         const int nnsp = i + 1 < rows ? ring_ld32(sm, slot + 96) : -1;
         const int r = ring_ld32(sm, slot + 40);
@@ -344,26 +430,50 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
         // the first two predecessors' row descriptors: from registers when it is the row just evaluated (the common case)
         const int4 pm0 = p0 == i - 1 ? prev_meta : poa_make_int4((int)npm_u.x, (int)npm_u.y, (int)npm_u.z, (int)npm_u.w);
         const int4 pm1 = s0 == i - 1 ? prev_meta : poa_make_int4((int)spm_u.x, (int)spm_u.y, (int)spm_u.z, (int)spm_u.w);
+#ifndef POA_P16_QORDER
+#define POA_P16_QORDER 1
+#endif
+#if !POA_P16_QORDER || POA_P16_QTMA
         // next row's metadata; its band inputs miss only this row's contribution, forwarded below
         gather(i + 1, nnp0, nnsp, i);
         // rows this row hands its arg-max columns to (one per lane; staged now, used after the last chunk)
         if (lane < ri.w) cpa4(sm, P16_OUTS_OFF + lane * 4, &pool_row[ri.z + lane]);
         cpa_commit();
         np0 = nnp0; nsp = nnsp;
+#endif
         // profile chunks of this row: staged now for the chunk range the previous row covered plus one (bands move
         // slowly), so the copies overlap the band computation below; corrected after it if the guess was wrong
+#if POA_P16_QTMA
+        int scb = q_scb, sce = q_sce;
+#else
         int scb = prev_meta.y >> 8, sce = imin(imin((prev_meta.z >> 8) + 1, scb + P16_QCH - 1), nchq - 1);
         {
+            // at most P16_QCH copies: written as predicated straight-line code (a counted loop makes the compiler emit unroll-by-16 /
+            // 8 / 4 bodies for a trip count it cannot see is <= 4: 60 instructions of row-loop code that never run)
             const char *qg = qp + (size_t)(unsigned)(rb * nchq + scb) * P16_CPB + lane * 16;
-            for (int k = 0; k <= sce - scb; ++k) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qg + (size_t)k * P16_CPB, false);
+            const int nq = sce - scb;
+#pragma unroll
+            for (int k = 0; k < P16_QCH; ++k) if (k <= nq) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qg + (size_t)k * P16_CPB, false);
             cpa_commit();
         }
+#endif
+#if POA_P16_QORDER && !POA_P16_QTMA
+        // The profile copies are committed FIRST and the gather of the next row's metadata after them: the first chunk pass then
+        // waits for "all but the newest group" = the profile only, and the gather has the whole row to land.
+        gather(i + 1, nnp0, nnsp, i);
+        // rows this row hands its arg-max columns to (one per lane; staged now, used after the last chunk)
+        if (lane < ri.w) cpa4(sm, P16_OUTS_OFF + lane * 4, &pool_row[ri.z + lane]);
+        cpa_commit();
+        np0 = nnp0; nsp = nnsp;
+        int q_newer = 1;  // cp.async groups committed after the profile's
+#endif
         int beg, end;
         if (wb < 0) { beg = 0; end = qlen; }
         else {  // abpoa_align.h:34-35, abpoa_align_simd.c:946-960
             int min_pre_beg = pm0.y;
             bool from_prev = p0 == i - 1;
             if (ri.y > 1) { from_prev |= s0 == i - 1; min_pre_beg = imin(min_pre_beg, pm1.y); }
+#pragma unroll 1
             for (int k = 2; k < ri.y; ++k) {
                 const int pk = pool_row[ri.x + k];
                 from_prev |= pk == i - 1;
@@ -376,7 +486,15 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
         }
         if (end < beg) end = beg;
         const int cb = beg >> 8, ce = end >> 8, nch = ce - cb + 1;
-        if (used + (long long)P16_PLANES * nch > slab_units) { if (lane == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+        if (used + (long long)P16_PLANES * nch > slab_units) {
+#if POA_P16_QTMA
+            q_drain();
+            if (lane == 0) sh.q_phase = (int)q_ph;
+#endif
+            if (lane == 0) sh.err = ST_ESLAB;
+            sync_block<NW>();
+            return;
+        }
         const unsigned roff = (unsigned)used;
         used += (long long)P16_PLANES * nch;
         inband += end - beg + 1;
@@ -391,10 +509,23 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
 
         // the row's profile chunks are staged in shared memory
         bool qst = cb >= scb && ce <= sce;
-        if (!qst && nch <= P16_QCH) {  // wrong guess (rare): let the speculative copies land, then stage the exact range over them
+        if (!qst && nch <= P16_QCH) {  // wrong guess (rare): let the speculative copy land, then stage the exact range over it
+#if POA_P16_QTMA
+            q_drain();
+            poa_sync_warp();  // every lane is past its wait before the mbarrier is armed again
+            q_issue(rb, cb, ce);
+#else
             cpa_wait_pending(0);
-            for (int k = 0; k < nch; ++k) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qrow + (size_t)(unsigned)(cb + k) * P16_CPB, false);
+            {
+                const char *qg = qrow + (size_t)(unsigned)cb * P16_CPB;
+#pragma unroll
+                for (int k = 0; k < P16_QCH; ++k) if (k < nch) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qg + (size_t)k * P16_CPB, false);
+            }
             cpa_commit();
+#if POA_P16_QORDER
+            q_newer = 0;
+#endif
+#endif
             scb = cb; qst = true;
         }
         char *dst = slab_lane + (size_t)roff * P16_CPB;
@@ -418,7 +549,6 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
             for (int u = 0; u < N; ++u) {
                 const int cu = c + u;
                 uint4 h, a, b;
-                h.x = h.y = h.z = h.w = INFP; a = h; b = h;
                 if (cu >= pcb0 && cu <= pce0) {
                     if (ring0) {
                         const unsigned rs = rslot + (unsigned)u * (3 * P16_CPB), rsw = rs >= P16_SMCH * (3 * P16_CPB) ? rs - P16_SMCH * (3 * P16_CPB) : rs;
@@ -429,6 +559,9 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
                         a = p16_ld(slab_lane + (size_t)(idx + pn0) * P16_CPB);
                         b = p16_ld(slab_lane + (size_t)(idx + 2 * pn0) * P16_CPB);
                     }
+                } else {  // the chunk lies outside the predecessor's band (rare)
+                    const unsigned inf = p16_pinned(INFP);
+                    h.x = h.y = h.z = h.w = inf; a = h; b = h;
                 }
                 const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
                 M[u][0] = lane == 0 ? p_pack(plast, p_lo(rot)) : rot; M[u][1] = h.x; M[u][2] = h.y; M[u][3] = h.z;
@@ -474,7 +607,15 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
             }
             if (local && c == 0 && lane == 0) M[0][0] = p_max(M[0][0], p_pack(0, inf_min));  // abpoa_align_simd.c:974 (`first` = 0)
             // ---- H~ = max(M + profile, E1, E2) (abpoa_align_simd.c:1032-1050); the profile chunks are read as late as possible
+#if POA_P16_QTMA
+            if (first_pass) q_drain();
+#else
+#if POA_P16_QORDER
+            if (qst && first_pass) { if (q_newer) cpa_wait_pending(1); else cpa_wait_pending(0); }
+#else
             if (qst && first_pass) cpa_wait_pending(0);
+#endif
+#endif
             first_pass = false;
 #pragma unroll
             for (int u = 0; u < N; ++u) {
@@ -506,13 +647,14 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
             }
             // ---- horizontal gaps (abpoa_align_simd.c:1052-1059): per-lane chains and the lane-half scans of all N chunks
             unsigned l[N][3], k_[N][3], g1[N], g2[N];
+            const uint4 lc4 = ring_ld(ring, P16_LANEC_OFF);  // OFF1, NOFF1, OFF2, NOFF2 of this lane
 #pragma unroll
             for (int u = 0; u < N; ++u) {
                 l[u][0] = p_add(H[u][0], NOE1); l[u][1] = p_addmax(l[u][0], NE1, p_add(H[u][1], NOE1)); l[u][2] = p_addmax(l[u][1], NE1, p_add(H[u][2], NOE1));
                 const unsigned lout = p_addmax(l[u][2], NE1, p_add(H[u][3], NOE1));
                 k_[u][0] = p_add(H[u][0], NOE2); k_[u][1] = p_addmax(k_[u][0], NE2, p_add(H[u][1], NOE2)); k_[u][2] = p_addmax(k_[u][1], NE2, p_add(H[u][2], NOE2));
                 const unsigned kout = p_addmax(k_[u][2], NE2, p_add(H[u][3], NOE2));
-                g1[u] = p_add(lout, OFF1); g2[u] = p_add(kout, OFF2);
+                g1[u] = p_add(lout, lc4.x); g2[u] = p_add(kout, lc4.z);
             }
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -534,7 +676,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
             for (int u = 0; u < N; ++u) {
                 const unsigned xx1 = p_max3(x1[u], p_lolo(NEGLP, t1[u]), carry1);  // high halves continue after all low halves
                 const unsigned xx2 = p_max3(x2[u], p_lolo(NEGLP, t2[u]), carry2);
-                const unsigned fin1 = p_add(xx1, NOFF1), fin2 = p_add(xx2, NOFF2);
+                const unsigned fin1 = p_add(xx1, lc4.y), fin2 = p_add(xx2, lc4.w);
                 carry1 = p_add(p_max3(t1[u], p_swap(t1[u]), carry1), NCW1);
                 carry2 = p_add(p_max3(t2[u], p_swap(t2[u]), carry2), NCW2);
                 const unsigned F10 = fin1, F11 = p_addmax(fin1, NE1, l[u][0]), F12 = p_addmax(fin1, NE1_2, l[u][1]), F13 = p_addmax(fin1, NE1_3, l[u][2]);
@@ -601,26 +743,28 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
             if (c <= ce) pass(p16_n<1>(), c);
 #endif
         }
+#if POA_P16_QTMA
+        if (i + 1 < rows) {  // next row's profile chunks: every lane has consumed this row's (the passes are behind us)
+            poa_sync_warp();
+            q_issue(rb_next, cb, imin(imin(ce + 1, cb + P16_QCH - 1), nchq - 1));
+        }
+#endif
         prev_meta = poa_make_int4((int)roff, beg, end, 0);
         prev_res = cur_res;
         if (lane == 0) rowmeta[i] = prev_meta;
         if (track) {
             // first / last column holding the row maximum: bit r of a lane's mask = low-half cell r equals it, bit 4+r = high half
             const unsigned pat = p_pack(rmx, rmx);
-            uint4 fh, lh;  // H of the first / last chunk holding the maximum: from the ring, else from the slab
-            if (cur_res) {
-                fh = ring_ld(ring, (unsigned)(fc % P16_SMCH) * (3 * P16_CPB));
-                lh = ring_ld(ring, (unsigned)(lc % P16_SMCH) * (3 * P16_CPB));
-            } else {
-                fh = p16_ld(slab_lane + (size_t)(roff + (unsigned)(fc - cb)) * P16_CPB);
-                lh = p16_ld(slab_lane + (size_t)(roff + (unsigned)(lc - cb)) * P16_CPB);
-            }
-            const unsigned fh0 = fh.x, fh1 = fh.y, fh2 = fh.z, fh3 = fh.w, lh0 = lh.x, lh1 = lh.y, lh2 = lh.z, lh3 = lh.w;
-            const unsigned fz = p_minu(fh0 ^ pat, 0x00010001u) | (p_minu(fh1 ^ pat, 0x00010001u) << 1)
-                              | (p_minu(fh2 ^ pat, 0x00010001u) << 2) | (p_minu(fh3 ^ pat, 0x00010001u) << 3);
-            const unsigned lz = p_minu(lh0 ^ pat, 0x00010001u) | (p_minu(lh1 ^ pat, 0x00010001u) << 1)
-                              | (p_minu(lh2 ^ pat, 0x00010001u) << 2) | (p_minu(lh3 ^ pat, 0x00010001u) << 3);
-            const unsigned fm = (~fz & 0xfu) | ((~fz >> 12) & 0xf0u), lm = (~lz & 0xfu) | ((~lz >> 12) & 0xf0u);
+            // H of the first / last chunk holding the maximum: from the ring, else from the slab (one chunk for most rows)
+            auto eqmask = [&](const int ch) {
+                const uint4 h = cur_res ? ring_ld(ring, (unsigned)(ch % P16_SMCH) * (3 * P16_CPB)) : p16_ld(slab_lane + (size_t)(roff + (unsigned)(ch - cb)) * P16_CPB);
+                const unsigned z = p_minu(h.x ^ pat, 0x00010001u) | (p_minu(h.y ^ pat, 0x00010001u) << 1)
+                                 | (p_minu(h.z ^ pat, 0x00010001u) << 2) | (p_minu(h.w ^ pat, 0x00010001u) << 3);
+                return (~z & 0xfu) | ((~z >> 12) & 0xf0u);
+            };
+            const unsigned fm = eqmask(fc);
+            unsigned lm = fm;
+            if (lc != fc) lm = eqmask(lc);
             int first = INT_MAX, last = -1;
             if (fm) { const int b = p_ctz(fm); first = fc * P16_CW + lane * 4 + b + (b >= 4 ? 124 : 0); }
             if (lm) { const int b = 31 - p_clz(lm); last = lc * P16_CW + lane * 4 + b + (b >= 4 ? 124 : 0); }
@@ -630,6 +774,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
             if (wb >= 0) {  // abpoa_align_simd.c:1121-1130; reductions without a return value: nothing to wait for
                 cpa_wait_pending(0);
                 if (lane < ri.w) { const int out_row = ring_ld32(sm, P16_OUTS_OFF + lane * 4); poa_red_max(&mprr[out_row], right + 1); poa_red_min(&mplr[out_row], left + 1); }
+#pragma unroll 1
                 for (int k = lane + POA_WARP; k < ri.w; k += POA_WARP) {
                     const int o = pool_row[ri.z + k];
                     poa_red_max(&mprr[o], right + 1); poa_red_min(&mplr[o], left + 1);
@@ -639,6 +784,10 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
         // no barrier here: the next row starts with one (after its cp.async wait)
     }
     cpa_wait_pending(0);
+#if POA_P16_QTMA
+    q_drain();
+    if (lane == 0) sh.q_phase = (int)q_ph;
+#endif
     sync_block<NW>();
     // ---- global best (abpoa_align_simd.c:1092-1105)
     if (lane == 0) {
