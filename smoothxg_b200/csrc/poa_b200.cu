@@ -49,7 +49,7 @@ __global__ void POA_KERNEL_BOUNDS poa_b200_block_kernel(const __grid_constant__ 
     __shared__ Shared sh;
     extern __shared__ __align__(16) char dyn_smem[];  // NW == 1: P16_SMEM_BYTES, else p16_mw_smem_bytes<NW>()
     constexpr int dyn_bytes = NW == 1 ? P16_SMEM_BYTES : p16_mw_smem<NW>::bytes;
-    if (threadIdx.x == 0) { ws_bind(sh.ws, ws_base + (long long)blockIdx.x * L.stride, L); sh.ring = dyn_smem; sh.ring_bytes = dyn_bytes; sh.q_phase = 0; if (NW == 1) qbar_init(&sh.qbar); }
+    if (threadIdx.x == 0) { ws_bind(sh.ws, ws_base + (long long)blockIdx.x * L.stride, L); sh.ring = dyn_smem; sh.ring_bytes = dyn_bytes; }
     for (;;) {
         if (threadIdx.x == 0) sh.blk = atomicAdd(O.counter, 1);
         __syncthreads();

@@ -222,6 +222,7 @@ struct WsLayout {
     long long o_rowinfo, o_rowmeta, o_rbase, o_rr, o_mplr, o_mprr, o_pred4;
     long long o_cig, o_path, o_best, o_ncig, o_plen, o_nrun, o_qp, o_slab;
     long long slab_bytes;
+    unsigned slab_planes;  // 512-byte chunk-planes the slab holds, capped at 0xfff00000 (packed 16-bit fill: 32-bit bookkeeping)
     int nmax;      // node capacity
     int pool_cap;  // edge pool capacity (entries)
     int cig_cap;   // cigar words capacity per block (all sequences when emit_cigar, else one alignment)
@@ -266,8 +267,6 @@ struct Shared {
     int bcast[4];
     char *ring;  // previous-row cache of the packed 16-bit fill (dynamic shared memory, poa_fill16.cuh)
     int ring_bytes;
-    unsigned long long qbar;  // mbarrier of the profile bulk copies (fill_p16)
-    int q_phase;              // its current phase parity
 };
 
 #ifdef POA_HOST_EMU

@@ -71,7 +71,7 @@ constexpr int P16_SMCH = POA_P16_SMCH;  // chunks of the previous row kept in sh
 constexpr int P16_RING_BYTES = P16_SMCH * 3 * P16_CPB;
 constexpr int P16_QCH = POA_P16_QCH;   // profile chunks of the row in flight staged in shared memory
 constexpr int P16_QBUF_OFF = P16_RING_BYTES, P16_META_OFF = P16_QBUF_OFF + P16_QCH * P16_CPB;
-constexpr int P16_SLOT = 128;                                  // one row's prefetched metadata (layout: fill_p16)
+constexpr int P16_SLOT = 144;                                  // one row's prefetched metadata: nine 16-byte cells (layout: fill_p16)
 constexpr int P16_MW_SLOT = 160;                               // the multi-warp fill also prefetches the third / fourth predecessor
 constexpr int P16_OUTS_OFF = P16_META_OFF + 2 * P16_SLOT;     // + 128 B: the row's successor rows
 constexpr int P16_LANEC_OFF = P16_OUTS_OFF + 128;          // + 512 B: four lane-dependent packed constants per lane (fill_p16)
@@ -110,6 +110,7 @@ POA_D void ring_st(ring_ptr_t p, unsigned off, unsigned a, unsigned b, unsigned 
 // `ring_ptr_t` arithmetic: shared-space byte address (device) / host pointer (emulation).
 #ifdef POA_HOST_EMU
 static inline void cpa16(ring_ptr_t s, unsigned off, const void *g, bool l2_only) { (void)l2_only; memcpy(s + off, g, 16); }
+static inline void cpa16z(ring_ptr_t s, unsigned off, const void *g, unsigned n) { if (n) memcpy(s + off, g, 16); else memset(s + off, 0, 16); }
 static inline void cpa4(ring_ptr_t s, unsigned off, const void *g) { memcpy(s + off, g, 4); }
 static inline void cpa_commit() {}
 static inline void cpa_wait_pending(int n) { (void)n; }
@@ -119,6 +120,9 @@ POA_D void cpa16(ring_ptr_t s, unsigned off, const void *g, bool l2_only) {
     if (l2_only) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s + off), "l"(g) : "memory");
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(s + off), "l"(g) : "memory");
 }
+// 16-byte copy at L2 that moves `n` = 16 or 0 source bytes and zero-fills the rest: lets every lane of a gather issue the same
+// instruction whether or not its item exists
+POA_D void cpa16z(ring_ptr_t s, unsigned off, const void *g, unsigned n) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(s + off), "l"(g), "r"(n) : "memory"); }
 POA_D void cpa4(ring_ptr_t s, unsigned off, const void *g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(s + off), "l"(g) : "memory"); }
 POA_D void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 POA_D void cpa_wait_pending(int n) {  // wait until at most n of the most recent groups are still in flight (uniform n)
@@ -132,35 +136,6 @@ POA_D void cpa_wait_pending(int n) {  // wait until at most n of the most recent
     }
 }
 POA_D int ring_ld32(ring_ptr_t p, unsigned off) { int v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p + off)); return v; }
-#endif
-
-// One-dimensional bulk copy global -> shared (TMA, cp.async.bulk; SASS UBLKCP) tracked by an mbarrier: ONE lane moves a whole
-// run of contiguous 512-byte chunk-planes with one instruction, and only the lanes that read the data wait for it (a phase
-// flip of the mbarrier), independently of any cp.async group in flight.  Used for the row's query-profile chunks (fill_p16).
-#ifndef POA_P16_QTMA
-#define POA_P16_QTMA 0
-#endif
-#ifdef POA_HOST_EMU
-static inline void qbar_init(unsigned long long *) {}
-static inline void q_bulk(ring_ptr_t s, unsigned off, const void *g, unsigned bytes, unsigned long long *) { memcpy(s + off, g, bytes); }
-static inline void q_wait(unsigned long long *, unsigned) { poa_sync_warp(); }  // the issuing lane copied before it got here
-#else
-POA_D void qbar_init(unsigned long long *bar) {  // one thread, once per kernel; made visible to the async proxy
-    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(b) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-POA_D void q_bulk(ring_ptr_t s, unsigned off, const void *g, unsigned bytes, unsigned long long *bar) {  // one lane
-    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(s + off), "l"(g), "r"(bytes), "r"(b) : "memory");
-}
-POA_D void q_wait(unsigned long long *bar, unsigned parity) {  // every lane that reads the copied bytes
-    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("{\n.reg .pred p;\nQ_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra Q_DONE;\nbra Q_WAIT;\nQ_DONE:\n}"
-                 :: "r"(b), "r"(parity) : "memory");
-}
 #endif
 
 POA_D uint4 p16_ld(const char *p) { return *reinterpret_cast<const uint4 *>(p); }
@@ -183,8 +158,10 @@ POA_D void p16_st(char *p, unsigned a, unsigned b, unsigned c, unsigned d) {
 // instead of twelve unconditional register initialisations in front of every chunk's loads.
 #ifdef POA_HOST_EMU
 static inline unsigned p16_pinned(unsigned v) { return v; }
+static inline const char *p16_pinned_ptr(const char *p) { return p; }
 #else
 POA_D unsigned p16_pinned(unsigned v) { unsigned r; asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+POA_D const char *p16_pinned_ptr(const char *p) { asm volatile("" : "+l"(p)); return p; }  // the compiler may not re-derive it per use
 #endif
 
 // Can this alignment run in packed 16-bit arithmetic without any intermediate leaving the int16 range?
@@ -215,7 +192,6 @@ template <int N> struct p16_n { static constexpr int value = N; };
 // slower still (150 / 122).  So N = 1 ships; the switch stays for the next machine with a larger L0/L1.5 I-cache.
 template <int NW, bool LOCAL>
 POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *const wsb, const uint8_t *q, int qlen, const int pn) {
-    const long long slab_bytes = L.slab_bytes;
     const int lane = poa_tid();
     const int n_node = sh.n_node;
     const int rows = n_node - 1;  // the sink row is never filled
@@ -247,8 +223,10 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
     __builtin_assume(__isGlobal(mplr)); __builtin_assume(__isGlobal(mprr)); __builtin_assume(__isGlobal(rbase));
     __builtin_assume(__isGlobal(q)); __builtin_assume(__isGlobal(fp)); __builtin_assume(__isGlobal(sp));
 #endif
-    const long long slab_units = slab_bytes / P16_CPB;
-    long long used = 0, inband = 0, edge_rows = 0;
+    // chunk-planes the slab holds / already used: 32-bit (a row's offset is stored as one 32-bit chunk-plane index anyway)
+    const unsigned slab_units = L.slab_planes;
+    unsigned used = 0;
+    long long inband = 0, edge_rows = 0;
 
     // packed constants
     const int emax = imax(e1, e2);
@@ -302,7 +280,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
             end0 = imin(qlen, imax(0, rr[0]) + bw);
         } else end0 = qlen;
         const int nch = (end0 >> 8) + 1;
-        if ((long long)P16_PLANES * nch > slab_units) { if (lane == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
+        if ((unsigned)(P16_PLANES * nch) > slab_units) { if (lane == 0) sh.err = ST_ESLAB; sync_block<NW>(); return; }
         if (lane == 0) rowmeta[0] = poa_make_int4(0, 0, end0, 0);
         for (int c = 0; c < nch; ++c) {
             unsigned v[5][4];
@@ -321,7 +299,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
             for (int p = 0; p < 3; ++p)  // H, E1, E2 (row 0 is never a traceback row: the walk stops at i == 0)
                 p16_st(slab + ((long long)p * nch + c) * P16_CPB + lane * 16, v[p][0], v[p][1], v[p][2], v[p][3]);
         }
-        used = (long long)P16_PLANES * nch;
+        used = (unsigned)(P16_PLANES * nch);
         inband += end0 + 1;
         sync_block<NW>();
     }
@@ -337,78 +315,35 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
     bool prev_res = false;  // is the previous row in the ring? (row 0 is not; rows wider than the ring are not)
     // Metadata of the next row is gathered into shared memory one row ahead by cp.async, one item per lane (the numbers
     // of its first and second predecessor two ahead, so that those rows' descriptors can be fetched one ahead too).
-    // Layout of a 128-byte slot: +0 rowinfo, +16 rowmeta[first pred], +32 base word, +36 fp two ahead, +40 rr,
-    // +48 mplr window, +64 mprr window (16-byte windows read at L2: they are updated by reductions),
-    // +80 rowmeta[second pred], +96 sp two ahead.
+    // A slot is nine 16-byte cells, each the aligned 16-byte window of its array that holds the item (read at L2: the band
+    // inputs are updated by reductions): +0 rowinfo, +16 rowmeta[first pred], +32 bases (16 rows), +48 mplr, +64 mprr (4 rows),
+    // +80 rowmeta[second pred], +96 fp (4 rows; the next row's entry is used), +112 rr (4 rows), +128 sp (4 rows, next row's).
     const ring_ptr_t sm = ring_base(sh.ring, 0);
-    // each of lanes 0..8 owns one item: its array, element size and slot offset are fixed for the whole alignment
-    const char *gsrc = nullptr; unsigned gdst = 0; int gkind = 0;  // kind: 1 = 16 bytes, 2 = 16 bytes at L2, 3 = 4 bytes
-    if (lane == 0) { gsrc = (const char *)rowinfo; gdst = 0; gkind = 1; }
-    else if (lane == 1) { gsrc = (const char *)rowmeta; gdst = 16; gkind = 1; }
-    else if (lane == 2) { gsrc = (const char *)rbase; gdst = 32; gkind = 3; }
-    else if (lane == 3) { gsrc = (const char *)fp; gdst = 36; gkind = 3; }
-    else if (lane == 4 && wb >= 0) { gsrc = (const char *)rr; gdst = 40; gkind = 3; }
-    else if (lane == 5 && wb >= 0) { gsrc = (const char *)mplr; gdst = 48; gkind = 2; }
-    else if (lane == 6 && wb >= 0) { gsrc = (const char *)mprr; gdst = 64; gkind = 2; }
-    else if (lane == 7) { gsrc = (const char *)rowmeta; gdst = 80; gkind = 1; }
-    else if (lane == 8) { gsrc = (const char *)sp; gdst = 96; gkind = 3; }
-#ifndef POA_P16_GFLAT
-#define POA_P16_GFLAT 1
-#endif
-#if POA_P16_GFLAT
-    // which row the lane's item belongs to (0: row n1, 1 / 2: its first / second predecessor, 3: the row after n1), and how its
-    // element index becomes a byte offset: all fixed per lane, so the gather itself is branch-free
-    const int gsel = lane == 1 ? 1 : lane == 7 ? 2 : (lane == 3 || lane == 8 || (POA_P16_QTMA && lane == 2)) ? 3 : 0;
-    const int gmask = (gkind == 2 || lane == 2) ? ~3 : ~0, gshift = gkind == 1 ? 4 : lane == 2 ? 0 : 2;
+    // each of lanes 0..8 owns one cell: its array, element size and slot offset are fixed for the whole alignment
+    const char *gsrc = nullptr; unsigned gdst = 0; int gshift = 0, gmask = ~0;  // element index -> byte offset of its 16-byte window
+    if (lane == 0) { gsrc = (const char *)rowinfo; gdst = 0; gshift = 4; }
+    else if (lane == 1) { gsrc = (const char *)rowmeta; gdst = 16; gshift = 4; }
+    else if (lane == 2) { gsrc = (const char *)rbase; gdst = 32; gshift = 0; gmask = ~15; }
+    else if (lane == 3) { gsrc = (const char *)fp; gdst = 96; gshift = 2; gmask = ~3; }
+    else if (lane == 4 && wb >= 0) { gsrc = (const char *)rr; gdst = 112; gshift = 2; gmask = ~3; }
+    else if (lane == 5 && wb >= 0) { gsrc = (const char *)mplr; gdst = 48; gshift = 2; gmask = ~3; }
+    else if (lane == 6 && wb >= 0) { gsrc = (const char *)mprr; gdst = 64; gshift = 2; gmask = ~3; }
+    else if (lane == 7) { gsrc = (const char *)rowmeta; gdst = 80; gshift = 4; }
+    else if (lane == 8) { gsrc = (const char *)sp; gdst = 128; gshift = 2; gmask = ~3; }
+    // which row the lane's item belongs to (0: row n1, 1 / 2: its first / second predecessor, 3: the row after n1): fixed per lane
+    // too, so the gather is ONE copy instruction for the nine lanes, no branches (an item that does not exist is zero-filled)
+    const int gsel = lane == 1 ? 1 : lane == 7 ? 2 : (lane == 3 || lane == 8) ? 3 : 0;
     auto gather = [&](const int n1, const int np0_n1, const int nsp_n1, const int cur) {  // row n1 into its slot; `cur`: row being evaluated
-        if (n1 >= rows) return;
-        const unsigned slot = P16_META_OFF + (unsigned)(n1 & 1) * P16_SLOT + gdst;
+        if (n1 >= rows || gsrc == nullptr) return;
         const int idx = gsel == 1 ? np0_n1 : gsel == 2 ? nsp_n1 : n1 + (gsel == 3 ? 1 : 0);
         // a predecessor's descriptor is fetched only if that row is complete (rows >= cur: forwarded in registers instead)
         const bool live = (unsigned)idx < (unsigned)((gsel == 1 || gsel == 2) ? cur : rows);
-        const char *src = gsrc + ((unsigned)(idx & gmask) << gshift);
-        if (live) {
-            if (gkind == 1) cpa16(sm, slot, src, false);
-            else if (gkind == 2) cpa16(sm, slot, src, true);
-            else if (gkind == 3) cpa4(sm, slot, src);
-        }
+        cpa16z(sm, P16_META_OFF + (unsigned)(n1 & 1) * P16_SLOT + gdst, gsrc + (live ? (unsigned)(idx & gmask) << gshift : 0u), live ? 16u : 0u);
     };
-#else
-    auto gather = [&](const int n1, const int np0_n1, const int nsp_n1, const int cur) {  // row n1 into its slot; `cur`: row being evaluated
-        if (n1 >= rows) return;
-        const unsigned slot = P16_META_OFF + (unsigned)(n1 & 1) * P16_SLOT + gdst;
-        // element index of this lane's item: the row itself, one of its first two predecessors (lanes 1, 7), the row after
-        // (lanes 3, 8), or the 4-element window holding it (byte / reduction-updated arrays)
-        int idx = n1;
-        bool live = true;
-        if (lane == 1) { idx = np0_n1; live = np0_n1 < cur; }
-        else if (lane == 7) { idx = nsp_n1; live = nsp_n1 >= 0 && nsp_n1 < cur; }
-        else if (lane == 3 || lane == 8 || (POA_P16_QTMA && lane == 2)) { idx = n1 + 1; live = n1 + 1 < rows; }
-        if (gkind == 1 && live) cpa16(sm, slot, gsrc + (size_t)(unsigned)idx * 16, false);
-        else if (gkind == 2) cpa16(sm, slot, gsrc + (size_t)(unsigned)(idx & ~3) * 4, true);
-        else if (gkind == 3 && live) cpa4(sm, slot, gsrc + (lane == 2 ? (size_t)(unsigned)(idx & ~3) : (size_t)(unsigned)idx * 4));
-    };
-#endif
     int np0 = fp[rows > 1 ? 1 : 0];   // first predecessor of the row about to be evaluated
     int nsp = rows > 1 ? sp[1] : -1;  // its second predecessor, or -1
     gather(1, np0, nsp, 1);
     cpa_commit();
-#if POA_P16_QTMA
-    // The row's profile chunks qp[base][scb..sce] are contiguous in memory: ONE bulk copy per row, issued by lane 0 a row ahead
-    // (right after the previous row's last chunk, for the chunk range that row covered plus one -- bands move slowly), and
-    // waited for on the mbarrier by the first chunk pass.  Every copy issued is waited for exactly once (q_pend).
-    unsigned q_ph = (unsigned)sh.q_phase;
-    bool q_pend = false;
-    int q_scb = 0, q_sce = -1;  // chunk range staged (or in flight) in the profile buffer
-    auto q_issue = [&](const int rbn, const int cb_, const int ce_) {
-        q_scb = cb_; q_sce = ce_;
-        if (lane == 0) q_bulk(sm, P16_QBUF_OFF, qp + (size_t)(unsigned)(rbn * nchq + cb_) * P16_CPB, (unsigned)(ce_ - cb_ + 1) * P16_CPB, &sh.qbar);
-        q_pend = true;
-    };
-    auto q_drain = [&]() { if (q_pend) { q_wait(&sh.qbar, q_ph); q_ph ^= 1u; q_pend = false; } };
-    int rb_next = rows > 1 ? rbase[1] : 0;
-    if (rows > 1) { const int g0 = prev_meta.y >> 8; q_issue(rb_next, g0, imin(imin((prev_meta.z >> 8) + 1, g0 + P16_QCH - 1), nchq - 1)); }
-#endif
 
     // ---- rows in index order (abpoa_align_simd.c:1205-1221)
     for (int i = 1; i < rows; ++i) {
@@ -417,47 +352,27 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
         const unsigned slot = P16_META_OFF + (unsigned)(i & 1) * P16_SLOT;
         const uint4 ri_u = ring_ld(sm, slot), npm_u = ring_ld(sm, slot + 16), spm_u = ring_ld(sm, slot + 80);
         const int4 ri = poa_make_int4((int)ri_u.x, (int)ri_u.y, (int)ri_u.z, (int)ri_u.w);  // {in_off, in_n, out_off, out_n}
-#if POA_P16_QTMA
-        const int rb = rb_next, p0 = np0, s0 = nsp;  // the slot holds the base word of row i + 1
-        rb_next = i + 1 < rows ? (ring_ld32(sm, slot + 32) >> (8 * ((i + 1) & 3))) & 0xff : 0;
-#else
-        const int rb = (ring_ld32(sm, slot + 32) >> (8 * (i & 3))) & 0xff, p0 = np0, s0 = nsp;
-#endif
-        const int nnp0 = i + 1 < rows ? ring_ld32(sm, slot + 36) : 0;
-        const int nnsp = i + 1 < rows ? ring_ld32(sm, slot + 96) : -1;
-        const int r = ring_ld32(sm, slot + 40);
-        int ml = ring_ld32(sm, slot + 48 + 4 * (i & 3)), mr = ring_ld32(sm, slot + 64 + 4 * (i & 3));
+        const unsigned w0 = slot + 4u * (unsigned)(i & 3), w1 = slot + 4u * (unsigned)((i + 1) & 3);  // this / the next row's word of a window
+        const int rb = (ring_ld32(sm, slot + 32 + 4u * (unsigned)((i >> 2) & 3)) >> (8 * (i & 3))) & 0xff, p0 = np0, s0 = nsp;
+        const int nnp0 = i + 1 < rows ? ring_ld32(sm, w1 + 96) : 0;
+        const int nnsp = i + 1 < rows ? ring_ld32(sm, w1 + 128) : -1;
+        const int r = ring_ld32(sm, w0 + 112);
+        int ml = ring_ld32(sm, w0 + 48), mr = ring_ld32(sm, w0 + 64);
         // the first two predecessors' row descriptors: from registers when it is the row just evaluated (the common case)
         const int4 pm0 = p0 == i - 1 ? prev_meta : poa_make_int4((int)npm_u.x, (int)npm_u.y, (int)npm_u.z, (int)npm_u.w);
         const int4 pm1 = s0 == i - 1 ? prev_meta : poa_make_int4((int)spm_u.x, (int)spm_u.y, (int)spm_u.z, (int)spm_u.w);
-#ifndef POA_P16_QORDER
-#define POA_P16_QORDER 1
-#endif
-#if !POA_P16_QORDER || POA_P16_QTMA
-        // next row's metadata; its band inputs miss only this row's contribution, forwarded below
-        gather(i + 1, nnp0, nnsp, i);
-        // rows this row hands its arg-max columns to (one per lane; staged now, used after the last chunk)
-        if (lane < ri.w) cpa4(sm, P16_OUTS_OFF + lane * 4, &pool_row[ri.z + lane]);
-        cpa_commit();
-        np0 = nnp0; nsp = nnsp;
-#endif
         // profile chunks of this row: staged now for the chunk range the previous row covered plus one (bands move
         // slowly), so the copies overlap the band computation below; corrected after it if the guess was wrong
-#if POA_P16_QTMA
-        int scb = q_scb, sce = q_sce;
-#else
         int scb = prev_meta.y >> 8, sce = imin(imin((prev_meta.z >> 8) + 1, scb + P16_QCH - 1), nchq - 1);
         {
             // at most P16_QCH copies: written as predicated straight-line code (a counted loop makes the compiler emit unroll-by-16 /
             // 8 / 4 bodies for a trip count it cannot see is <= 4: 60 instructions of row-loop code that never run)
-            const char *qg = qp + (size_t)(unsigned)(rb * nchq + scb) * P16_CPB + lane * 16;
+            const char *qg = p16_pinned_ptr(qp + (size_t)(unsigned)(rb * nchq + scb) * P16_CPB + lane * 16);  // one address, four immediate offsets
             const int nq = sce - scb;
 #pragma unroll
             for (int k = 0; k < P16_QCH; ++k) if (k <= nq) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qg + (size_t)k * P16_CPB, false);
             cpa_commit();
         }
-#endif
-#if POA_P16_QORDER && !POA_P16_QTMA
         // The profile copies are committed FIRST and the gather of the next row's metadata after them: the first chunk pass then
         // waits for "all but the newest group" = the profile only, and the gather has the whole row to land.
         gather(i + 1, nnp0, nnsp, i);
@@ -466,7 +381,6 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
         cpa_commit();
         np0 = nnp0; nsp = nnsp;
         int q_newer = 1;  // cp.async groups committed after the profile's
-#endif
         int beg, end;
         if (wb < 0) { beg = 0; end = qlen; }
         else {  // abpoa_align.h:34-35, abpoa_align_simd.c:946-960
@@ -486,17 +400,13 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
         }
         if (end < beg) end = beg;
         const int cb = beg >> 8, ce = end >> 8, nch = ce - cb + 1;
-        if (used + (long long)P16_PLANES * nch > slab_units) {
-#if POA_P16_QTMA
-            q_drain();
-            if (lane == 0) sh.q_phase = (int)q_ph;
-#endif
+        if (used + (unsigned)(P16_PLANES * nch) > slab_units) {
             if (lane == 0) sh.err = ST_ESLAB;
             sync_block<NW>();
             return;
         }
-        const unsigned roff = (unsigned)used;
-        used += (long long)P16_PLANES * nch;
+        const unsigned roff = used;
+        used += (unsigned)(P16_PLANES * nch);
         inband += end - beg + 1;
         edge_rows += (long long)ri.y * (end - beg + 1);
 
@@ -510,22 +420,14 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
         // the row's profile chunks are staged in shared memory
         bool qst = cb >= scb && ce <= sce;
         if (!qst && nch <= P16_QCH) {  // wrong guess (rare): let the speculative copy land, then stage the exact range over it
-#if POA_P16_QTMA
-            q_drain();
-            poa_sync_warp();  // every lane is past its wait before the mbarrier is armed again
-            q_issue(rb, cb, ce);
-#else
             cpa_wait_pending(0);
             {
-                const char *qg = qrow + (size_t)(unsigned)cb * P16_CPB;
+                const char *qg = p16_pinned_ptr(qrow + (size_t)(unsigned)cb * P16_CPB);
 #pragma unroll
                 for (int k = 0; k < P16_QCH; ++k) if (k < nch) cpa16(sm, P16_QBUF_OFF + (unsigned)k * P16_CPB + lane * 16, qg + (size_t)k * P16_CPB, false);
             }
             cpa_commit();
-#if POA_P16_QORDER
             q_newer = 0;
-#endif
-#endif
             scb = cb; qst = true;
         }
         char *dst = slab_lane + (size_t)roff * P16_CPB;
@@ -539,7 +441,9 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
         // after a chunk it is simply the last cell of the predecessor chunk just read (inf_min if that was out of range)
         int plast = inf_min;
         if (cb > pcb0 && cb <= pce0 + 1) plast = *reinterpret_cast<const short *>(slab + (size_t)((unsigned)pm0.x + (unsigned)(cb - pcb0)) * P16_CPB - 2);
-        bool first_pass = true;
+        // the profile chunks were requested before the band computation: wait for them here, once, instead of testing "first pass?"
+        // in every chunk pass (the gather committed after them stays in flight)
+        if (qst) { if (q_newer) cpa_wait_pending(1); else cpa_wait_pending(0); }
 
         auto pass = [&](auto nc, const int c) {  // chunks c .. c + N - 1 of row i, side by side
             constexpr int N = decltype(nc)::value;
@@ -585,7 +489,6 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
                 for (int u = 0; u < N; ++u) {
                     const int cu = c + u;
                     uint4 h, a, b;
-                    h.x = h.y = h.z = h.w = INFP; a = h; b = h;
                     if (cu >= pcb && cu <= pce) {
                         if (in_ring) {
                             const unsigned rs = rslot + (unsigned)u * (3 * P16_CPB), rsw = rs >= P16_SMCH * (3 * P16_CPB) ? rs - P16_SMCH * (3 * P16_CPB) : rs;
@@ -596,6 +499,9 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
                             a = p16_ld(slab_lane + (size_t)(idx + pn_) * P16_CPB);
                             b = p16_ld(slab_lane + (size_t)(idx + 2 * pn_) * P16_CPB);
                         }
+                    } else {
+                        const unsigned inf = p16_pinned(INFP);
+                        h.x = h.y = h.z = h.w = inf; a = h; b = h;
                     }
                     const unsigned rot = (unsigned)poa_shfl((int)h.w, (lane + 31) & 31);
                     const unsigned s0_ = lane == 0 ? p_pack(pl, p_lo(rot)) : rot;
@@ -607,16 +513,6 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
             }
             if (local && c == 0 && lane == 0) M[0][0] = p_max(M[0][0], p_pack(0, inf_min));  // abpoa_align_simd.c:974 (`first` = 0)
             // ---- H~ = max(M + profile, E1, E2) (abpoa_align_simd.c:1032-1050); the profile chunks are read as late as possible
-#if POA_P16_QTMA
-            if (first_pass) q_drain();
-#else
-#if POA_P16_QORDER
-            if (qst && first_pass) { if (q_newer) cpa_wait_pending(1); else cpa_wait_pending(0); }
-#else
-            if (qst && first_pass) cpa_wait_pending(0);
-#endif
-#endif
-            first_pass = false;
 #pragma unroll
             for (int u = 0; u < N; ++u) {
                 uint4 qv;
@@ -743,12 +639,6 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
             if (c <= ce) pass(p16_n<1>(), c);
 #endif
         }
-#if POA_P16_QTMA
-        if (i + 1 < rows) {  // next row's profile chunks: every lane has consumed this row's (the passes are behind us)
-            poa_sync_warp();
-            q_issue(rb_next, cb, imin(imin(ce + 1, cb + P16_QCH - 1), nchq - 1));
-        }
-#endif
         prev_meta = poa_make_int4((int)roff, beg, end, 0);
         prev_res = cur_res;
         if (lane == 0) rowmeta[i] = prev_meta;
@@ -784,10 +674,6 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
         // no barrier here: the next row starts with one (after its cp.async wait)
     }
     cpa_wait_pending(0);
-#if POA_P16_QTMA
-    q_drain();
-    if (lane == 0) sh.q_phase = (int)q_ph;
-#endif
     sync_block<NW>();
     // ---- global best (abpoa_align_simd.c:1092-1105)
     if (lane == 0) {

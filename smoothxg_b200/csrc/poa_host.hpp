@@ -95,6 +95,7 @@ inline void make_layout(WsLayout &L, long long nmax, long long max_bases, long l
     L.o_nrun = take(8 * (std::max<long long>(max_seq, 1) + 2));
     L.o_qp = take(5 * ((max_len >> 8) + 2) * 512);
     L.slab_bytes = align_up(slab_bytes, 512);
+    L.slab_planes = (unsigned)std::min<long long>(L.slab_bytes / 512, 0xfff00000ll);
     L.o_slab = take(L.slab_bytes);
     L.stride = o;
 }
