@@ -173,6 +173,7 @@ POA_D bool p16_eligible(const DevParams &P, int qlen) {
 
 // Compile-time chunk count of one pass of the row loop (fill_p16): generic lambdas take it as a value of this type.
 template <int N> struct p16_n { static constexpr int value = N; };
+template <bool B> struct p16_b { static constexpr bool value = B; };
 #ifndef POA_P16_ILP
 #define POA_P16_ILP 1  // chunks of a row evaluated side by side by one warp; 1 is what ships (see below), 2..4 are experiments
 #endif
@@ -445,8 +446,12 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
         // in every chunk pass (the gather committed after them stays in flight)
         if (qst) { if (q_newer) cpa_wait_pending(1); else cpa_wait_pending(0); }
 
-        auto pass = [&](auto nc, const int c) {  // chunks c .. c + N - 1 of row i, side by side
+        const bool bnd_first = (beg & (P16_CW - 1)) != 0, bnd_last = (end & (P16_CW - 1)) != P16_CW - 1;  // cells outside the band in the first / last chunk?
+        // STAGED: the row's profile chunks are in shared memory (every row of a batch whose bands fit P16_QCH chunks); rows wider than
+        // that read the profile from global memory in a second instantiation of the pass, which costs the common one nothing
+        auto pass = [&](auto nc, auto staged, const int c) {  // chunks c .. c + N - 1 of row i, side by side
             constexpr int N = decltype(nc)::value;
+            constexpr bool STAGED = decltype(staged)::value;
             unsigned M[N][4], A[N][4], B[N][4], H[N][4];
             // ---- first predecessor: its chunk (H shifted one column right for M, E1, E2 as they are), or inf_min
 #pragma unroll
@@ -516,13 +521,13 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
 #pragma unroll
             for (int u = 0; u < N; ++u) {
                 uint4 qv;
-                if (qst) qv = ring_ld(sm, P16_QBUF_OFF + (unsigned)(c + u - scb) * P16_CPB + lane * 16);
+                if (STAGED) qv = ring_ld(sm, P16_QBUF_OFF + (unsigned)(c + u - scb) * P16_CPB + lane * 16);
                 else qv = p16_ld(qrow + (size_t)(unsigned)(c + u) * P16_CPB);
                 H[u][0] = p_max3(p_add(M[u][0], qv.x), A[u][0], B[u][0]); H[u][1] = p_max3(p_add(M[u][1], qv.y), A[u][1], B[u][1]);
                 H[u][2] = p_max3(p_add(M[u][2], qv.z), A[u][2], B[u][2]); H[u][3] = p_max3(p_add(M[u][3], qv.w), A[u][3], B[u][3]);
             }
             // ---- cells outside [beg,end]: only the row's first and last chunk can hold any
-            const bool bnd = (c == cb && beg > c * P16_CW) || (c + N - 1 == ce && end < (c + N) * P16_CW - 1);
+            const bool bnd = (c == cb && bnd_first) || (c + N - 1 == ce && bnd_last);
             unsigned m[N][4];
 #pragma unroll
             for (int u = 0; u < N; ++u) { m[u][0] = 0; m[u][1] = 0; m[u][2] = 0; m[u][3] = 0; }
@@ -625,20 +630,21 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
                 }
             }
         };
-        {
+        auto row_passes = [&](auto staged) {
             int c = cb;
 #pragma unroll 1
-            for (; c + (POA_P16_ILP - 1) <= ce; c += POA_P16_ILP) pass(p16_n<POA_P16_ILP>(), c);
+            for (; c + (POA_P16_ILP - 1) <= ce; c += POA_P16_ILP) pass(p16_n<POA_P16_ILP>(), staged, c);
 #if POA_P16_ILP >= 4
-            if (c + 2 <= ce) { pass(p16_n<3>(), c); c += 3; }
+            if (c + 2 <= ce) { pass(p16_n<3>(), staged, c); c += 3; }
 #endif
 #if POA_P16_ILP >= 3
-            if (c + 1 <= ce) { pass(p16_n<2>(), c); c += 2; }
+            if (c + 1 <= ce) { pass(p16_n<2>(), staged, c); c += 2; }
 #endif
 #if POA_P16_ILP >= 2
-            if (c <= ce) pass(p16_n<1>(), c);
+            if (c <= ce) pass(p16_n<1>(), staged, c);
 #endif
-        }
+        };
+        if (qst) row_passes(p16_b<true>()); else row_passes(p16_b<false>());
         prev_meta = poa_make_int4((int)roff, beg, end, 0);
         prev_res = cur_res;
         if (lane == 0) rowmeta[i] = prev_meta;
