@@ -923,11 +923,22 @@ int poa_b200_run_batch(poa_b200_engine_t *eng, const poa_b200_params_t *params, 
     if (!result) return set_err(POA_B200_EARG, "NULL result");
     *result = nullptr;
     poa_b200_batch_t *b = nullptr;
+    static const bool trace = getenv("POA_B200_TRACE") != nullptr;  // host wall time of the four stages, to stderr
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = poa_b200_batch_upload(eng, params, n_blocks, block_seq_off, seq_len, seq_off, bases, weight, &b);
     if (rc) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     rc = poa_b200_batch_launch(b, nullptr);
+    const auto t2 = std::chrono::steady_clock::now();
     if (rc == POA_B200_OK) rc = poa_b200_batch_download(b, nullptr, result);
+    const auto t3 = std::chrono::steady_clock::now();
     poa_b200_batch_free(b);
+    if (trace) {
+        const auto t4 = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point z) { return std::chrono::duration<double, std::milli>(z - a).count(); };
+        fprintf(stderr, "[poa_b200] run_batch %lld blocks: upload %.2f ms, launch+wait %.2f ms, download %.2f ms, free %.2f ms\n",
+                (long long)n_blocks, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
+    }
     return rc;
 }
 
