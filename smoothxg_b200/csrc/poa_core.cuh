@@ -169,6 +169,7 @@ struct DevParams {
     int pn16, pn32;  // lane counts of the reference build whose band-start rule we reproduce (AVX-512BW: 32/16)
     int emit_cigar;
     int p16_ok;  // scoring parameters allow the packed 16-bit fill (poa_fill16.cuh)
+    int p16_default;  // ... and are smoothxg's defaults 1,4,6,2,26,1: fill_p16<.., PRESET = true> has them as immediates
     int gap_mode;  // 0 convex, 1 affine, 2 linear (abpoa_set_gap_mode, abpoa_align.c:87-91)
     // Packed (two int16 per word) constants of the 16-bit fill, prepared on the host (build_params): as fields of a
     // __grid_constant__ parameter they are constant-bank operands of the packed-integer instructions instead of a dozen
@@ -1559,7 +1560,10 @@ POA_D void poa_block(Shared &sh, const DevParams &P, const DevBatch &B, const Ws
             if (p16) {
                 t_ph[PH_SPARE] += 1;  // alignments that took the packed 16-bit fill
 #if POA_WARP == 32
-                if (NW == 1) { if (P.local) fill_p16<NW, true>(sh, P, L, wsb, q, qlen, p16_pn); else fill_p16<NW, false>(sh, P, L, wsb, q, qlen, p16_pn); }
+                if (NW == 1) {
+                    if (P.p16_default) { if (P.local) fill_p16<NW, true, true>(sh, P, L, wsb, q, qlen, p16_pn); else fill_p16<NW, false, true>(sh, P, L, wsb, q, qlen, p16_pn); }
+                    else { if (P.local) fill_p16<NW, true, false>(sh, P, L, wsb, q, qlen, p16_pn); else fill_p16<NW, false, false>(sh, P, L, wsb, q, qlen, p16_pn); }
+                }
                 else { if (P.local) fill_p16_mw<NW, true>(sh, P, q, qlen, L.slab_bytes, p16_pn); else fill_p16_mw<NW, false>(sh, P, q, qlen, L.slab_bytes, p16_pn); }
 #endif
             } else if (P.gap_mode == 0) {

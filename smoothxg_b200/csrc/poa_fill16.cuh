@@ -191,12 +191,14 @@ template <bool B> struct p16_b { static constexpr bool value = B; };
 // fits the SM's instruction caches (726 instead of 373 instructions; `no_instruction` stalls rise from 0.49 to 1.41 per issue)
 // and it needs 168 registers (12 resident warps per SM instead of 16): 188-211 Gcells/s against 250 for N = 1; N = 3 and 4 are
 // slower still (150 / 122).  So N = 1 ships; the switch stays for the next machine with a larger L0/L1.5 I-cache.
-template <int NW, bool LOCAL>
+// PRESET: the scoring parameters are smoothxg's defaults (match 1, mismatch 4, gaps 6,2,26,1; DevParams::p16_default): the packed
+// constants below are then immediates of the instructions that use them instead of nine constant-bank loads per chunk pass.
+template <int NW, bool LOCAL, bool PRESET>
 POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *const wsb, const uint8_t *q, int qlen, const int pn) {
     const int lane = poa_tid();
     const int n_node = sh.n_node;
     const int rows = n_node - 1;  // the sink row is never filled
-    const int inf_min = inf_min_of<short>(P);
+    const int inf_min = PRESET ? -31717 : inf_min_of<short>(P);
     constexpr bool local = LOCAL;
     const int wb = local ? -1 : P.wb;  // abpoa_align.c:158
 #ifdef POA_HOST_EMU
@@ -204,7 +206,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
 #else
     const int bw = wb < 0 ? qlen : wb + (int)__fmul_rn(P.wf, (float)qlen);
 #endif
-    const int e1 = P.e1, e2 = P.e2, oe1 = P.oe1, oe2 = P.oe2;
+    const int e1 = PRESET ? 2 : P.e1, e2 = PRESET ? 1 : P.e2, oe1 = PRESET ? 8 : P.oe1, oe2 = PRESET ? 27 : P.oe2;
     // Workspace pointers are formed from the CTA's workspace base (a kernel parameter plus blockIdx.x * stride: warp-uniform) and
     // the layout's offsets (constant bank), NOT read back from the Ws struct in shared memory: values loaded from memory are
     // not provably uniform, so a dozen 64-bit pointers would each pin two vector registers for the whole alignment -- with
@@ -234,18 +236,19 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
     const int negl = -32768 + 8 * emax + 8;  // below every value a band cell can take, never wraps when used
     (void)negl;
     // uniform ones come from the constant bank (DevParams::pk_*, build_params()); the lane-dependent four stay in registers
-#define INFP (P.pk_inf)
-#define NEGLP (P.pk_negl)
-#define NOE1 (P.pk_noe1)
-#define NOE2 (P.pk_noe2)
-#define NE1 (P.pk_ne1)
-#define NE2 (P.pk_ne2)
-#define NE1_2 (P.pk_ne1_2)
-#define NE1_3 (P.pk_ne1_3)
-#define NE2_2 (P.pk_ne2_2)
-#define NE2_3 (P.pk_ne2_3)
-#define NCW1 (P.pk_ncw1)
-#define NCW2 (P.pk_ncw2)
+#define P16_PK(v) ((((unsigned)(v)) & 0xffffu) | (((unsigned)(v)) << 16))
+#define INFP (PRESET ? P16_PK(-31717) : P.pk_inf)
+#define NEGLP (PRESET ? P16_PK(-32744) : P.pk_negl)
+#define NOE1 (PRESET ? P16_PK(-8) : P.pk_noe1)
+#define NOE2 (PRESET ? P16_PK(-27) : P.pk_noe2)
+#define NE1 (PRESET ? P16_PK(-2) : P.pk_ne1)
+#define NE2 (PRESET ? P16_PK(-1) : P.pk_ne2)
+#define NE1_2 (PRESET ? P16_PK(-4) : P.pk_ne1_2)
+#define NE1_3 (PRESET ? P16_PK(-6) : P.pk_ne1_3)
+#define NE2_2 (PRESET ? P16_PK(-2) : P.pk_ne2_2)
+#define NE2_3 (PRESET ? P16_PK(-3) : P.pk_ne2_3)
+#define NCW1 (PRESET ? P16_PK(-512) : P.pk_ncw1)
+#define NCW2 (PRESET ? P16_PK(-256) : P.pk_ncw2)
     const unsigned ZERO = 0u;
     const unsigned OFF1 = p_pack(e1 * 4 * (lane + 1), e1 * 4 * (lane + 33)), NOFF1 = p_pack(-e1 * 4 * lane, -e1 * 4 * (lane + 32));
     const unsigned OFF2 = p_pack(e2 * 4 * (lane + 1), e2 * 4 * (lane + 33)), NOFF2 = p_pack(-e2 * 4 * lane, -e2 * 4 * (lane + 32));
@@ -710,6 +713,7 @@ POA_D void fill_p16(Shared &sh, const DevParams &P, const WsLayout &L, char *con
 #undef NE2_3
 #undef NCW1
 #undef NCW2
+#undef P16_PK
 
 // ------------------------------------------------------------------------------------------------
 // F1 / F2 of row i at columns j and j - 1, for the traceback's insertion steps (abpoa_align_simd.c:420-445 reads

@@ -51,6 +51,15 @@ inline void build_params(const poa_b200_params_t &p, const poa_b200_engine_opts_
     }
     d.p16_ok = d.gap_mode == 0 && (o.flags & 1) == 0 && emax >= 1 && emax <= 100 && 240 * emax >= (long long)d.min_mis + std::max(d.oe1, d.oe2) + 64
                && d.oe1 > d.e1 && d.oe2 > d.e2;
+    // smoothxg's default scoring: fill_p16<.., PRESET = true> carries these constants as immediates; the literals there are checked
+    // against the values computed above, so a change to either side falls back to the generic instantiation instead of diverging
+    {
+        auto pk = [](long long v) { const unsigned h = (unsigned)(v & 0xffff); return h | (h << 16); };
+        d.p16_default = d.p16_ok && match == 1 && mismatch == -4 && d.o1 == 6 && d.e1 == 2 && d.o2 == 26 && d.e2 == 1
+                        && d.pk_inf == pk(-31717) && d.pk_negl == pk(-32744) && d.pk_noe1 == pk(-8) && d.pk_noe2 == pk(-27) && d.pk_ne1 == pk(-2)
+                        && d.pk_ne2 == pk(-1) && d.pk_ne1_2 == pk(-4) && d.pk_ne1_3 == pk(-6) && d.pk_ne2_2 == pk(-2) && d.pk_ne2_3 == pk(-3)
+                        && d.pk_ncw1 == pk(-512) && d.pk_ncw2 == pk(-256);
+    }
 }
 
 inline int check_params(const poa_b200_params_t &p) {
