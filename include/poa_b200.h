@@ -145,7 +145,9 @@ int  poa_b200_engine_trim(poa_b200_engine_t *eng);
  *   block_seq_off[n_blocks+1] -> index into seq_len/weight;  seq_off[n_seqs+1] -> index into bases;
  *   bases = codes 0..4 (ab_char26_table encoding, deps/abPOA/src/abpoa_seq.c:15-32); a code above 4 -- which that
  *   table cannot produce -- is treated as 4 (N), clamped on the device right after the upload;
- *   weight[n_seqs] = dedup multiplicity of each sequence (src/smooth.cpp:332-336). */
+ *   weight[n_seqs] = dedup multiplicity of each sequence (src/smooth.cpp:332-336).
+ * With POA_B200_TRACE set in the environment every call prints the host wall time of its stages (upload, launch + wait,
+ * download, free) to stderr. */
 int  poa_b200_run_batch(poa_b200_engine_t *eng, const poa_b200_params_t *params, int64_t n_blocks,
                         const int64_t *block_seq_off, const int32_t *seq_len, const int64_t *seq_off,
                         const uint8_t *bases, const int32_t *weight, poa_b200_result_t **result);
