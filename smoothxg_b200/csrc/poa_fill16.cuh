@@ -951,43 +951,40 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
     int pp_left = INT_MAX - 1, pp_right = -1;  // ... and of row i - 2 (see the band computation)
     bool prev_res = false;
     int prev_out_z = 0, prev_out_n = 0;  // successor list of the previous row (band propagation, warp 0)
-    // metadata gather (warp 0): same slot layout as fill_p16
-    const char *gsrc = nullptr; unsigned gdst = 0; int gkind = 0;
+    // metadata gather (warp 0), as in fill_p16: ten 16-byte cells per slot, each the aligned 16-byte window of its array that
+    // holds the item, fetched by ONE zero-filling copy instruction for the ten lanes.  +0 rowinfo, +16 / +80 / +112 / +128
+    // rowmeta of the first four predecessors, +32 bases (16 rows), +48 mplr, +64 mprr, +144 rr (4 rows each), +96 pred4 of the next row.
+    const char *gsrc = nullptr; unsigned gdst = 0; int gshift = 4, gmask = ~0;
     if (wid == 0) {
-        if (lane == 0) { gsrc = (const char *)rowinfo; gdst = 0; gkind = 1; }
-        else if (lane == 1) { gsrc = (const char *)rowmeta; gdst = 16; gkind = 1; }
-        else if (lane == 2) { gsrc = (const char *)rbase; gdst = 32; gkind = 3; }
-        else if (lane == 3) { gsrc = (const char *)pred4; gdst = 96; gkind = 1; }
-        else if (lane == 4 && wb >= 0) { gsrc = (const char *)rr; gdst = 40; gkind = 3; }
-        else if (lane == 5 && wb >= 0) { gsrc = (const char *)mplr; gdst = 48; gkind = 2; }
-        else if (lane == 6 && wb >= 0) { gsrc = (const char *)mprr; gdst = 64; gkind = 2; }
-        else if (lane == 7) { gsrc = (const char *)rowmeta; gdst = 80; gkind = 1; }
-        else if (lane == 8) { gsrc = (const char *)rowmeta; gdst = 112; gkind = 1; }
-        else if (lane == 9) { gsrc = (const char *)rowmeta; gdst = 128; gkind = 1; }
+        if (lane == 0) { gsrc = (const char *)rowinfo; gdst = 0; }
+        else if (lane == 1) { gsrc = (const char *)rowmeta; gdst = 16; }
+        else if (lane == 2) { gsrc = (const char *)rbase; gdst = 32; gshift = 0; gmask = ~15; }
+        else if (lane == 3) { gsrc = (const char *)pred4; gdst = 96; }
+        else if (lane == 4 && wb >= 0) { gsrc = (const char *)rr; gdst = 144; gshift = 2; gmask = ~3; }
+        else if (lane == 5 && wb >= 0) { gsrc = (const char *)mplr; gdst = 48; gshift = 2; gmask = ~3; }
+        else if (lane == 6 && wb >= 0) { gsrc = (const char *)mprr; gdst = 64; gshift = 2; gmask = ~3; }
+        else if (lane == 7) { gsrc = (const char *)rowmeta; gdst = 80; }
+        else if (lane == 8) { gsrc = (const char *)rowmeta; gdst = 112; }
+        else if (lane == 9) { gsrc = (const char *)rowmeta; gdst = 128; }
     }
+    const int gsel = lane == 1 ? 1 : lane == 7 ? 2 : lane == 8 ? 3 : lane == 9 ? 4 : lane == 3 ? 5 : 0;  // whose row: n1, a predecessor, n1 + 1
     auto gather = [&](const int n1, const int4 &p4_n1, const int cur) {  // warp 0: row n1 into its slot
-        if (n1 >= rows) return;
-        const unsigned slot = META + (unsigned)(n1 & 1) * P16_MW_SLOT + gdst;
-        int idx = n1;
-        bool live = true;
-        if (lane == 1) { idx = p4_n1.x; live = idx >= 0 && idx < cur; }
-        else if (lane == 7) { idx = p4_n1.y; live = idx >= 0 && idx < cur; }
-        else if (lane == 8) { idx = p4_n1.z; live = idx >= 0 && idx < cur; }
-        else if (lane == 9) { idx = p4_n1.w; live = idx >= 0 && idx < cur; }
-        else if (lane == 3) { idx = n1 + 1; live = n1 + 1 < rows; }
-        if (gkind == 1 && live) cpa16(sm, slot, gsrc + (size_t)(unsigned)idx * 16, false);
-        else if (gkind == 2) cpa16(sm, slot, gsrc + (size_t)(unsigned)(idx & ~3) * 4, true);
-        else if (gkind == 3 && live) cpa4(sm, slot, gsrc + (lane == 2 ? (size_t)(unsigned)(idx & ~3) : (size_t)(unsigned)idx * 4));
+        if (n1 >= rows || gsrc == nullptr) return;
+        const int idx = gsel == 1 ? p4_n1.x : gsel == 2 ? p4_n1.y : gsel == 3 ? p4_n1.z : gsel == 4 ? p4_n1.w : n1 + (gsel == 5 ? 1 : 0);
+        // a predecessor's descriptor is fetched only if that row exists and is complete (else it is forwarded in registers)
+        const bool live = (unsigned)idx < (unsigned)((gsel >= 1 && gsel <= 4) ? cur : rows);
+        cpa16z(sm, META + (unsigned)(n1 & 1) * P16_MW_SLOT + gdst, gsrc + (live ? (unsigned)(idx & gmask) << gshift : 0u), live ? 16u : 0u);
     };
     int4 np4 = rows > 1 ? pred4[1] : poa_make_int4(0, -1, -1, -1);
     if (wid == 0) { gather(1, np4, 1); cpa_commit(); }
     int par = 0;
     // previous row's arg-max columns from the candidates every warp published (rowx, parity of that row)
     auto combine = [&](const int row) {
-        const int *rx = rowx + (row & 1) * NW * 4;
-        int gmx = INT_MIN, left = INT_MAX, right = -1;
-        for (int k = 0; k < NW; ++k) gmx = imax(gmx, rx[k * 4]);
-        for (int k = 0; k < NW; ++k) if (rx[k * 4] == gmx) { left = imin(left, rx[k * 4 + 1]); right = imax(right, rx[k * 4 + 2]); }
+        // lane k < NW takes warp k's candidate {maximum, first, last column} (one 16-byte read; the other lanes repeat entry 0),
+        // three warp reductions combine them: ~12 instructions on every warp's row-to-row chain instead of two loops over NW
+        const uint4 e = ring_ld(sm, (unsigned)SM::o_rowx + (unsigned)(((row & 1) * NW + (lane < NW ? lane : 0)) * 16));
+        const int gmx = poa_redux_max((int)e.x);
+        const int left = poa_redux_min((int)e.x == gmx ? (int)e.y : INT_MAX), right = poa_redux_max((int)e.x == gmx ? (int)e.z : -1);
         prev_left = left; prev_right = right;
         if (local && gmx > best_score) { best_score = gmx; best_i = row; best_j = left; }  // abpoa_align_simd.c:1208-1210
     };
@@ -1000,6 +997,7 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
             combine(i - 1);
             if (wb >= 0 && wid == 0) {  // abpoa_align_simd.c:1121-1130 for the previous row, before the next gather reads the band inputs
                 if (lane < prev_out_n) { const int o = ring_ld32(sm, OUTS + (unsigned)((i - 1) & 1) * 128 + lane * 4); poa_red_max(&mprr[o], prev_right + 1); poa_red_min(&mplr[o], prev_left + 1); }
+#pragma unroll 1
                 for (int k = lane + POA_WARP; k < prev_out_n; k += POA_WARP) { const int o = pool_row[prev_out_z + k]; poa_red_max(&mprr[o], prev_right + 1); poa_red_min(&mplr[o], prev_left + 1); }
             }
         }
@@ -1007,10 +1005,10 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
         const uint4 ri_u = ring_ld(sm, slot), m0_u = ring_ld(sm, slot + 16), m1_u = ring_ld(sm, slot + 80), m2_u = ring_ld(sm, slot + 112), m3_u = ring_ld(sm, slot + 128);
         const uint4 nn_u = ring_ld(sm, slot + 96);
         const int4 ri = poa_make_int4((int)ri_u.x, (int)ri_u.y, (int)ri_u.z, (int)ri_u.w);
-        const int rb = (ring_ld32(sm, slot + 32) >> (8 * (i & 3))) & 0xff;
+        const int rb = (ring_ld32(sm, slot + 32 + 4u * (unsigned)((i >> 2) & 3)) >> (8 * (i & 3))) & 0xff;
         const int p0 = np4.x, s0 = np4.y, s2 = np4.z, s3 = np4.w;
         const int4 nnp4 = i + 1 < rows ? poa_make_int4((int)nn_u.x, (int)nn_u.y, (int)nn_u.z, (int)nn_u.w) : poa_make_int4(0, -1, -1, -1);
-        const int r = ring_ld32(sm, slot + 40);
+        const int r = ring_ld32(sm, slot + 144 + 4 * (i & 3));
         int ml = ring_ld32(sm, slot + 48 + 4 * (i & 3)), mr = ring_ld32(sm, slot + 64 + 4 * (i & 3));
         const int4 pm0 = p0 == i - 1 ? prev_meta : poa_make_int4((int)m0_u.x, (int)m0_u.y, (int)m0_u.z, (int)m0_u.w);
         const int4 pm1 = s0 == i - 1 ? prev_meta : poa_make_int4((int)m1_u.x, (int)m1_u.y, (int)m1_u.z, (int)m1_u.w);
@@ -1035,6 +1033,7 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
             if (ri.y > 1) { from_prev |= s0 == i - 1; from_pp |= s0 == i - 2; min_pre_beg = imin(min_pre_beg, pm1.y); }
             if (ri.y > 2) { from_prev |= s2 == i - 1; from_pp |= s2 == i - 2; min_pre_beg = imin(min_pre_beg, pm2.y); }
             if (ri.y > 3) { from_prev |= s3 == i - 1; from_pp |= s3 == i - 2; min_pre_beg = imin(min_pre_beg, pm3.y); }
+#pragma unroll 1
             for (int k = 4; k < ri.y; ++k) {
                 const int pk = pool_row[ri.x + k];
                 from_prev |= pk == i - 1; from_pp |= pk == i - 2;
@@ -1110,7 +1109,14 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
                     bool in0 = false, in1 = false, t0 = false, t1_ = false;
                     fetch(p0, pm0, h0, a0, b0, pl0, in0, t0);
                     if (ri.y > 1) fetch(s0, pm1, h1, a1, b1, pl1, in1, t1_);
-                    consume(h0, a0, b0, pl0, in0, t0);   // in in_id order (abpoa_align_simd.c:966-1029)
+                    // in in_id order (abpoa_align_simd.c:966-1029); the first predecessor's chunk is taken as it is (no max against -inf)
+                    if (in0) {
+                        const unsigned rot = (unsigned)poa_shfl((int)h0.w, (lane + 31) & 31);
+                        M0 = lane == 0 ? p_pack(pl0, p_lo(rot)) : rot; M1 = h0.x; M2 = h0.y; M3 = h0.z;
+                        A0 = a0.x; A1 = a0.y; A2 = a0.z; A3 = a0.w; B0 = b0.x; B1 = b0.y; B2 = b0.z; B3 = b0.w;
+                    } else {
+                        consume(h0, a0, b0, pl0, in0, t0);
+                    }
                     if (ri.y > 1) consume(h1, a1, b1, pl1, in1, t1_);
                 }
 #pragma unroll 1
@@ -1209,19 +1215,15 @@ POA_DN void fill_p16_mw(Shared &sh, const DevParams &P, const uint8_t *q, int ql
             int first = INT_MAX, last = -1;
             if (fc >= 0) {
                 const unsigned pat = p_pack(rmx, rmx);
-                uint4 fh, lh;
-                if (cur_res) {
-                    fh = ring_ld(ring, (unsigned)((fc / NW) % P16_MW_SMCH) * (3 * P16_CPB));
-                    lh = ring_ld(ring, (unsigned)((lc / NW) % P16_MW_SMCH) * (3 * P16_CPB));
-                } else {
-                    fh = p16_ld(slab_lane + (size_t)(roff + (unsigned)(fc - cb)) * P16_CPB);
-                    lh = p16_ld(slab_lane + (size_t)(roff + (unsigned)(lc - cb)) * P16_CPB);
-                }
-                const unsigned fz = p_minu(fh.x ^ pat, 0x00010001u) | (p_minu(fh.y ^ pat, 0x00010001u) << 1)
-                                  | (p_minu(fh.z ^ pat, 0x00010001u) << 2) | (p_minu(fh.w ^ pat, 0x00010001u) << 3);
-                const unsigned lz = p_minu(lh.x ^ pat, 0x00010001u) | (p_minu(lh.y ^ pat, 0x00010001u) << 1)
-                                  | (p_minu(lh.z ^ pat, 0x00010001u) << 2) | (p_minu(lh.w ^ pat, 0x00010001u) << 3);
-                const unsigned fm = (~fz & 0xfu) | ((~fz >> 12) & 0xf0u), lm = (~lz & 0xfu) | ((~lz >> 12) & 0xf0u);
+                auto eqmask = [&](const int ch) {  // which of the lane's eight cells of chunk ch hold the maximum
+                    const uint4 h = cur_res ? ring_ld(ring, (unsigned)((ch / NW) % P16_MW_SMCH) * (3 * P16_CPB)) : p16_ld(slab_lane + (size_t)(roff + (unsigned)(ch - cb)) * P16_CPB);
+                    const unsigned z = p_minu(h.x ^ pat, 0x00010001u) | (p_minu(h.y ^ pat, 0x00010001u) << 1)
+                                     | (p_minu(h.z ^ pat, 0x00010001u) << 2) | (p_minu(h.w ^ pat, 0x00010001u) << 3);
+                    return (~z & 0xfu) | ((~z >> 12) & 0xf0u);
+                };
+                const unsigned fm = eqmask(fc);
+                unsigned lm = fm;
+                if (lc != fc) lm = eqmask(lc);  // a warp usually owns one chunk of a row
                 if (fm) { const int b = p_ctz(fm); first = fc * P16_CW + lane * 4 + b + (b >= 4 ? 124 : 0); }
                 if (lm) { const int b = 31 - p_clz(lm); last = lc * P16_CW + lane * 4 + b + (b >= 4 ? 124 : 0); }
             }
