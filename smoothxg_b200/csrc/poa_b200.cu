@@ -35,7 +35,7 @@ using namespace poa;
 // Resident single-warp POA blocks per SM the register budget is sized for.  ptxas maps any hint of 13..16 to 128 registers
 // per thread (16 resident blocks); the hint still steers its register allocation.  Round 1 (before the row-loop diet): 12 x 168
 // registers 217.9, 13 x 152 214.0, 14 x 144 208.7, 15 x 136 206.4, 16 x 128 221.1 Gcells/s on configs[2], and 13 gave the leanest
-// chunk loop of the 128-register builds.  Re-measured on the final round-2 code (same box, scripts/gpu_r02_z.sh): 13 -> 273.3,
+// chunk loop of the 128-register builds.  Re-measured on the final round-2 code (same box, scripts/lab_r02/gpu_r02_z.sh): 13 -> 273.3,
 // 14 -> 276.8, 15 -> 274.9 Gcells/s; 14 also spills least (24 bytes, touched once per row at most, against 112).
 #define POA_MIN_BLOCKS 14
 #endif
