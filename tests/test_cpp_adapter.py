@@ -28,6 +28,18 @@ def test_adapter_header_compiles_and_links():
     assert os.path.exists(build_exe())
 
 
+def test_host_parameter_block_on_cpu():
+    """build_params (smoothxg_b200/csrc/poa_host.hpp; reference src/smooth.cpp:256-297, abpoa_align.c:12-25,87-91): score matrix,
+    packed constants of the 16-bit fill, and that the default-scoring instantiation of the fill is selected for smoothxg's
+    defaults only (its literals are checked against the host-computed constants)."""
+    exe = os.path.join(os.path.dirname(EXE), "params_test")
+    src = os.path.join(ROOT, "tests", "cpp", "params_test.cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-w", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include", src, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "params ok", out.stdout + out.stderr
+
+
 def test_dedup_and_encoding_on_cpu():
     """dedup_sequences = the XXH64 loop of src/smooth.cpp:217-241 (first-occurrence order, multiplicities, names and
     strands per group); encode_bases = ab_nt4_table."""
