@@ -241,7 +241,19 @@ def reference_arm(args, config, params_kw):
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int16", "data": "synthetic", "config": config, "blocks_per_s": sub.n_blocks / t, "cpu_baseline": base,
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line of the contract, on the process's ORIGINAL stdout (see main(): libraries are kept off it)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -261,6 +273,12 @@ def main():
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the extra weak-scaling figure")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-identity check of the gathered result against a single-GPU run")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the result: NCCL prints its version banner on file descriptor 1 when the first communicator
+    # is created, so everything else written to fd 1 from here on (libraries included) goes to stderr
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -470,7 +488,7 @@ def main():
                 line["parity_sample"] = {"blocks": sub.n_blocks, "mismatches": len(bad), "against": f"unmodified abPOA v1.5.4 ({simd})",
                                          "what": "FNV-1a of node count, bases, out-edge ids and weights per block"}
                 if bad:
-                    print(json.dumps(line))
+                    emit(line)
                     raise SystemExit(f"bench.py: GPU result differs from the reference on sampled blocks {bad[:8]}")
             if kind == "reference":
                 n2 = max(threads, sub.n_blocks // 2)
@@ -481,7 +499,7 @@ def main():
                                                     "blocks": s2.n_blocks}
         if world == 1 and not args.no_e2e and args.workload == "10000x32x2kb":
             line["next_rows"] = {"adaptive_identity_estimate": identity_estimate_leg(batch, local_rank)}
-        print(json.dumps(line))
+        emit(line)
         if verify is not None and verify["differing_from_single_gpu_run"]:
             raise SystemExit("bench.py: the gathered multi-GPU result differs from the single-GPU run")
     if last is not None:
