@@ -451,7 +451,8 @@ def main():
         achieved = (float(cells) * bytes_per_cell) / per_launch_s / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "int16",  # also for deep blocks: 16-bit cells provably hold every real value there (p16_safe_for_long_graph), abPOA itself would use int32 "data": "synthetic", "config": config,
+                # dtype: also for deep blocks -- 16-bit cells provably hold every real value there (p16_safe_for_long_graph); abPOA itself would use int32
+                "dtype": "int16", "data": "synthetic", "config": config,
                 "blocks_per_s": tot_blocks * K / sec, "inband_cells_per_step": tot_cells, "p_bar": pbar,
                 "clocks": clocks, "gpu_launches": int(launches_all),
                 "engine": {"n_ctas": st["n_ctas"], "warps_per_block": st["warps_per_block"], "workspace_gb": st["workspace_bytes"] / 1e9,
